@@ -1,0 +1,1040 @@
+// TEST INFRASTRUCTURE ONLY — see lrf_oracle.h for the rules and the parity status.
+//
+// Serial (OpenMP only over independent rays of the forward) plain-C++17 restatement of the
+// LiteRF hot path.  Build: -O2 -ffp-contract=off, no -march (FMA contraction changes results).
+// Every function cites the reference file:line (relative to /root/reference) it follows.
+#include "lrf_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+#include <omp.h>
+
+namespace {
+
+constexpr int CELL = 13;  // example_tracer.h:25-32  density, RGB[3], sh[9]
+
+// ------------------------------------------------------------------ LiteMath restatements
+// LiteMath.h:97  clamp(u,a,b) = std::min(std::max(a,u),b)
+template <class R> inline R lm_max(R a, R b) { return (a < b) ? b : a; }  // std::max(a,b)
+template <class R> inline R lm_min(R a, R b) { return (b < a) ? b : a; }  // std::min(a,b)
+template <class R> inline R lm_clamp(R u, R a, R b) { return lm_min(lm_max(a, u), b); }
+// LiteMath.h:109
+template <class R> inline R lm_lerp(R u, R v, R t) { return u + t * (v - u); }
+
+// LiteMath.h:1362-1368  column-major mat * vec
+inline void mat_mul_vec(float *res, const float *B, const float *V)
+{
+  res[0] = V[0] * B[0] + V[1] * B[4] + V[2] * B[8] + V[3] * B[12];
+  res[1] = V[0] * B[1] + V[1] * B[5] + V[2] * B[9] + V[3] * B[13];
+  res[2] = V[0] * B[2] + V[1] * B[6] + V[2] * B[10] + V[3] * B[14];
+  res[3] = V[0] * B[3] + V[1] * B[7] + V[2] * B[11] + V[3] * B[15];
+}
+// LiteMath.h:1556-1569
+inline void mat_mul_mat(float *res, const float *A, const float *B)
+{
+  float tmp[16];
+  for (int c = 0; c < 4; c++) mat_mul_vec(tmp + 4 * c, A, B + 4 * c);
+  std::memcpy(res, tmp, sizeof(tmp));
+}
+inline void mat_identity(float *m)
+{
+  for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+}
+inline void normalize3(float *v)  // LiteMath.h:805-808
+{
+  float len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  float inv = float(1) / len;
+  v[0] = v[0] * inv; v[1] = v[1] * inv; v[2] = v[2] * inv;
+}
+inline void cross3(const float *a, const float *b, float *r)  // LiteMath.h:829-834
+{
+  // shuffle_yzx(a*b_yzx - a_yzx*b)
+  float t0 = a[0] * b[1] - a[1] * b[0];
+  float t1 = a[1] * b[2] - a[2] * b[1];
+  float t2 = a[2] * b[0] - a[0] * b[2];
+  r[0] = t1; r[1] = t2; r[2] = t0;
+}
+#define M(m, r, c) (m)[(c) * 4 + (r)]  // LiteMath.h:1433  operator()(row,col) = m_col[col][row]
+
+// LiteMath.h:1571-1653
+void inverse4x4(const float *m1, float *out)
+{
+  float tmp[12];
+  float m[16];
+  tmp[0] = M(m1, 2, 2) * M(m1, 3, 3);
+  tmp[1] = M(m1, 2, 3) * M(m1, 3, 2);
+  tmp[2] = M(m1, 2, 1) * M(m1, 3, 3);
+  tmp[3] = M(m1, 2, 3) * M(m1, 3, 1);
+  tmp[4] = M(m1, 2, 1) * M(m1, 3, 2);
+  tmp[5] = M(m1, 2, 2) * M(m1, 3, 1);
+  tmp[6] = M(m1, 2, 0) * M(m1, 3, 3);
+  tmp[7] = M(m1, 2, 3) * M(m1, 3, 0);
+  tmp[8] = M(m1, 2, 0) * M(m1, 3, 2);
+  tmp[9] = M(m1, 2, 2) * M(m1, 3, 0);
+  tmp[10] = M(m1, 2, 0) * M(m1, 3, 1);
+  tmp[11] = M(m1, 2, 1) * M(m1, 3, 0);
+
+  M(m, 0, 0) = tmp[0] * M(m1, 1, 1) + tmp[3] * M(m1, 1, 2) + tmp[4] * M(m1, 1, 3);
+  M(m, 0, 0) -= tmp[1] * M(m1, 1, 1) + tmp[2] * M(m1, 1, 2) + tmp[5] * M(m1, 1, 3);
+  M(m, 1, 0) = tmp[1] * M(m1, 1, 0) + tmp[6] * M(m1, 1, 2) + tmp[9] * M(m1, 1, 3);
+  M(m, 1, 0) -= tmp[0] * M(m1, 1, 0) + tmp[7] * M(m1, 1, 2) + tmp[8] * M(m1, 1, 3);
+  M(m, 2, 0) = tmp[2] * M(m1, 1, 0) + tmp[7] * M(m1, 1, 1) + tmp[10] * M(m1, 1, 3);
+  M(m, 2, 0) -= tmp[3] * M(m1, 1, 0) + tmp[6] * M(m1, 1, 1) + tmp[11] * M(m1, 1, 3);
+  M(m, 3, 0) = tmp[5] * M(m1, 1, 0) + tmp[8] * M(m1, 1, 1) + tmp[11] * M(m1, 1, 2);
+  M(m, 3, 0) -= tmp[4] * M(m1, 1, 0) + tmp[9] * M(m1, 1, 1) + tmp[10] * M(m1, 1, 2);
+  M(m, 0, 1) = tmp[1] * M(m1, 0, 1) + tmp[2] * M(m1, 0, 2) + tmp[5] * M(m1, 0, 3);
+  M(m, 0, 1) -= tmp[0] * M(m1, 0, 1) + tmp[3] * M(m1, 0, 2) + tmp[4] * M(m1, 0, 3);
+  M(m, 1, 1) = tmp[0] * M(m1, 0, 0) + tmp[7] * M(m1, 0, 2) + tmp[8] * M(m1, 0, 3);
+  M(m, 1, 1) -= tmp[1] * M(m1, 0, 0) + tmp[6] * M(m1, 0, 2) + tmp[9] * M(m1, 0, 3);
+  M(m, 2, 1) = tmp[3] * M(m1, 0, 0) + tmp[6] * M(m1, 0, 1) + tmp[11] * M(m1, 0, 3);
+  M(m, 2, 1) -= tmp[2] * M(m1, 0, 0) + tmp[7] * M(m1, 0, 1) + tmp[10] * M(m1, 0, 3);
+  M(m, 3, 1) = tmp[4] * M(m1, 0, 0) + tmp[9] * M(m1, 0, 1) + tmp[10] * M(m1, 0, 2);
+  M(m, 3, 1) -= tmp[5] * M(m1, 0, 0) + tmp[8] * M(m1, 0, 1) + tmp[11] * M(m1, 0, 2);
+
+  tmp[0] = M(m1, 0, 2) * M(m1, 1, 3);
+  tmp[1] = M(m1, 0, 3) * M(m1, 1, 2);
+  tmp[2] = M(m1, 0, 1) * M(m1, 1, 3);
+  tmp[3] = M(m1, 0, 3) * M(m1, 1, 1);
+  tmp[4] = M(m1, 0, 1) * M(m1, 1, 2);
+  tmp[5] = M(m1, 0, 2) * M(m1, 1, 1);
+  tmp[6] = M(m1, 0, 0) * M(m1, 1, 3);
+  tmp[7] = M(m1, 0, 3) * M(m1, 1, 0);
+  tmp[8] = M(m1, 0, 0) * M(m1, 1, 2);
+  tmp[9] = M(m1, 0, 2) * M(m1, 1, 0);
+  tmp[10] = M(m1, 0, 0) * M(m1, 1, 1);
+  tmp[11] = M(m1, 0, 1) * M(m1, 1, 0);
+
+  M(m, 0, 2) = tmp[0] * M(m1, 3, 1) + tmp[3] * M(m1, 3, 2) + tmp[4] * M(m1, 3, 3);
+  M(m, 0, 2) -= tmp[1] * M(m1, 3, 1) + tmp[2] * M(m1, 3, 2) + tmp[5] * M(m1, 3, 3);
+  M(m, 1, 2) = tmp[1] * M(m1, 3, 0) + tmp[6] * M(m1, 3, 2) + tmp[9] * M(m1, 3, 3);
+  M(m, 1, 2) -= tmp[0] * M(m1, 3, 0) + tmp[7] * M(m1, 3, 2) + tmp[8] * M(m1, 3, 3);
+  M(m, 2, 2) = tmp[2] * M(m1, 3, 0) + tmp[7] * M(m1, 3, 1) + tmp[10] * M(m1, 3, 3);
+  M(m, 2, 2) -= tmp[3] * M(m1, 3, 0) + tmp[6] * M(m1, 3, 1) + tmp[11] * M(m1, 3, 3);
+  M(m, 3, 2) = tmp[5] * M(m1, 3, 0) + tmp[8] * M(m1, 3, 1) + tmp[11] * M(m1, 3, 2);
+  M(m, 3, 2) -= tmp[4] * M(m1, 3, 0) + tmp[9] * M(m1, 3, 1) + tmp[10] * M(m1, 3, 2);
+  M(m, 0, 3) = tmp[2] * M(m1, 2, 2) + tmp[5] * M(m1, 2, 3) + tmp[1] * M(m1, 2, 1);
+  M(m, 0, 3) -= tmp[4] * M(m1, 2, 3) + tmp[0] * M(m1, 2, 1) + tmp[3] * M(m1, 2, 2);
+  M(m, 1, 3) = tmp[8] * M(m1, 2, 3) + tmp[0] * M(m1, 2, 0) + tmp[7] * M(m1, 2, 2);
+  M(m, 1, 3) -= tmp[6] * M(m1, 2, 2) + tmp[9] * M(m1, 2, 3) + tmp[1] * M(m1, 2, 0);
+  M(m, 2, 3) = tmp[6] * M(m1, 2, 1) + tmp[11] * M(m1, 2, 3) + tmp[3] * M(m1, 2, 0);
+  M(m, 2, 3) -= tmp[10] * M(m1, 2, 3) + tmp[2] * M(m1, 2, 0) + tmp[7] * M(m1, 2, 1);
+  M(m, 3, 3) = tmp[10] * M(m1, 2, 2) + tmp[4] * M(m1, 2, 0) + tmp[9] * M(m1, 2, 1);
+  M(m, 3, 3) -= tmp[8] * M(m1, 2, 1) + tmp[11] * M(m1, 2, 2) + tmp[5] * M(m1, 2, 0);
+
+  const float k = 1.0f / (M(m1, 0, 0) * M(m, 0, 0) + M(m1, 0, 1) * M(m, 1, 0) + M(m1, 0, 2) * M(m, 2, 0) +
+                          M(m1, 0, 3) * M(m, 3, 0));
+  for (int i = 0; i < 16; i++) out[i] = m[i] * k;
+}
+
+// LiteMath.h:1770-1795
+void look_at(const float *eye, const float *center, const float *up, float *Mo)
+{
+  float x[3], y[3], z[3];
+  z[0] = eye[0] - center[0]; z[1] = eye[1] - center[1]; z[2] = eye[2] - center[2];
+  normalize3(z);
+  y[0] = up[0]; y[1] = up[1]; y[2] = up[2];
+  cross3(y, z, x);
+  float y2[3];
+  cross3(z, x, y2);
+  normalize3(x);
+  normalize3(y2);
+  float col0[4] = {x[0], y2[0], z[0], 0.0f}, col1[4] = {x[1], y2[1], z[1], 0.0f}, col2[4] = {x[2], y2[2], z[2], 0.0f};
+  float col3[4] = {-x[0] * eye[0] - x[1] * eye[1] - x[2] * eye[2], -y2[0] * eye[0] - y2[1] * eye[1] - y2[2] * eye[2],
+                   -z[0] * eye[0] - z[1] * eye[1] - z[2] * eye[2], 1.0f};
+  std::memcpy(Mo, col0, 16); std::memcpy(Mo + 4, col1, 16); std::memcpy(Mo + 8, col2, 16); std::memcpy(Mo + 12, col3, 16);
+}
+
+// ------------------------------------------------------------------ state
+struct Oracle
+{
+  int gs = 0;
+  std::vector<float> grid, grad, V, S;
+  std::vector<int32_t> box_xyz;        // 3 per box, id = position
+  std::vector<int64_t> vox2id;         // (gs-1)^3, -1 = absent
+  float bb_min[3] = {0, 0, 0}, bb_max[3] = {1, 1, 1};
+  float view_inv[16], proj_inv[16];
+  float lr = 0.15f, beta_1 = 0.9f, beta_2 = 0.999f, eps = 1e-8;  // example_tracer.h:120-123
+  size_t N() const { return (size_t)gs * gs * gs; }
+  int n() const { return gs - 1; }
+  void rebuild_map()
+  {
+    size_t nv = (size_t)n() * n() * n();
+    vox2id.assign(nv, -1);
+    for (size_t i = 0; i < box_xyz.size() / 3; i++) {
+      int x = box_xyz[3 * i], y = box_xyz[3 * i + 1], z = box_xyz[3 * i + 2];
+      vox2id[(size_t)x + (size_t)y * n() + (size_t)z * n() * n()] = (int64_t)i;
+    }
+  }
+};
+
+// box planes: example_tracer.h:79-82  (float)x / (float)gs widened to double.  (Exact k/gs for the
+// power-of-two sizes the library supports; the float expression is kept for fidelity.)
+inline double plane(int i, int gs) { return (double)((float)i / (float)gs); }
+
+// ------------------------------------------------------------------ a4: IsRayHit, octree.h:449-488
+// returns true and the distance if hit.  dim-generic for the Octree KATs.
+bool is_ray_hit(int dim, const double *bmin, const double *bmax, const double *o, const double *hd, double tol, double *dist)
+{
+  bool contains = true;  // DoesBoxContainPoint, octree.h:314-322
+  for (int a = 0; a < dim; a++)
+    if (!(bmin[a] - tol <= o[a] && o[a] <= bmax[a] + tol)) { contains = false; break; }
+  if (contains) { *dist = 0.0; return true; }
+  const double inf = std::numeric_limits<double>::infinity();
+  double mn[8], mx[8];
+  for (int a = 0; a < dim; a++) {
+    const double h = hd[a];
+    if (h == 0) {
+      if (bmax[a] + tol < o[a]) return false;
+      if (bmin[a] - tol > o[a]) return false;
+      mn[a] = -inf; mx[a] = +inf;
+      continue;
+    }
+    mn[a] = ((h > 0.0 ? bmin[a] : bmax[a]) - tol - o[a]) / h;
+    mx[a] = ((h < 0.0 ? bmin[a] : bmax[a]) + tol - o[a]) / h;
+  }
+  double rMin = mn[0], rMax = mx[0];  // std::ranges::max_element / min_element (first of equals; value is what matters)
+  for (int a = 1; a < dim; a++) { if (rMin < mn[a]) rMin = mn[a]; if (mx[a] < rMax) rMax = mx[a]; }
+  if (rMin > rMax || rMax < 0.0) return false;
+  *dist = rMin < 0 ? rMax : rMin;
+  return true;
+}
+
+struct Hit { double dist; uint64_t id; };
+inline bool hit_less(const Hit &a, const Hit &b)  // defaulted operator<=> on (Distance, EntityID), octree.h:850-860
+{
+  if (a.dist < b.dist) return true;
+  if (b.dist < a.dist) return false;
+  return a.id < b.id;
+}
+
+// RayIntersectedAll result for the lattice box set: every box passing IsRayHit, sorted by (dist,id),
+// (octree.h:3210-3232, 3278-3301).  Deliberately NOT a DDA: a three-level exhaustive search
+// (z slabs -> rows -> boxes) that prunes only with IsRayHit itself on enclosing boxes, which is
+// conservative because the rounded slab expressions are monotone in the box bounds.
+void ray_hits(const Oracle &S, const float *of, const float *df, std::vector<Hit> &out)
+{
+  out.clear();
+  const int n = S.n(), gs = S.gs;
+  if (n <= 0) return;
+  const double o[3] = {of[0], of[1], of[2]}, d[3] = {df[0], df[1], df[2]};
+  const double lo = plane(0, gs), hi = plane(n, gs);
+  for (int z = 0; z < n; z++) {
+    double smin[3] = {lo, lo, plane(z, gs)}, smax[3] = {hi, hi, plane(z + 1, gs)}, dist;
+    if (!is_ray_hit(3, smin, smax, o, d, 0.0, &dist)) continue;
+    for (int y = 0; y < n; y++) {
+      double rmin[3] = {lo, plane(y, gs), smin[2]}, rmax[3] = {hi, plane(y + 1, gs), smax[2]};
+      if (!is_ray_hit(3, rmin, rmax, o, d, 0.0, &dist)) continue;
+      for (int x = 0; x < n; x++) {
+        int64_t id = S.vox2id[(size_t)x + (size_t)y * n + (size_t)z * n * n];
+        if (id < 0) continue;
+        double bmin[3] = {plane(x, gs), rmin[1], rmin[2]}, bmax[3] = {plane(x + 1, gs), rmax[1], rmax[2]};
+        if (is_ray_hit(3, bmin, bmax, o, d, 0.0, &dist)) out.push_back({dist, (uint64_t)id});
+      }
+    }
+  }
+  std::sort(out.begin(), out.end(), hit_less);
+}
+
+// ------------------------------------------------------------------ a3: ray generation
+// EyeRayDir example_tracer.cpp:542-548, transform_ray3f :550-557, call site :635-639
+void gen_ray(const float *view_inv, const float *proj_inv, uint32_t x, uint32_t y, uint32_t w, uint32_t h, float *o, float *d)
+{
+  float u = (float(x) + 0.5f) / float(w), v = (float(y) + 0.5f) / float(h);
+  float pos[4] = {2.0f * u - 1.0f, 2.0f * v - 1.0f, 0.0f, 1.0f}, p2[4];
+  mat_mul_vec(p2, proj_inv, pos);
+  const float pw = p2[3];
+  p2[0] /= pw; p2[1] /= pw; p2[2] /= pw; p2[3] /= pw;  // LiteMath.h:417
+  float dir[3] = {p2[0], p2[1], p2[2]};
+  normalize3(dir);
+  float rp[4] = {0.0f, 0.0f, 0.0f, 1.0f}, rd[4] = {dir[0], dir[1], dir[2], 0.0f}, rpt[4], rdt[4];
+  mat_mul_vec(rpt, view_inv, rp);
+  mat_mul_vec(rdt, view_inv, rd);
+  // normalize(float4) LiteMath.h:453-456
+  float len = std::sqrt(rdt[0] * rdt[0] + rdt[1] * rdt[1] + rdt[2] * rdt[2] + rdt[3] * rdt[3]);
+  float inv = float(1) / len;
+  o[0] = rpt[0]; o[1] = rpt[1]; o[2] = rpt[2];
+  d[0] = rdt[0] * inv; d[1] = rdt[1] * inv; d[2] = rdt[2] * inv;
+}
+
+// ------------------------------------------------------------------ a7: SH basis, example_tracer.cpp:83-106
+template <class R> void sh_eval_2(const R *d, R *out)
+{
+  R x = d[0], y = d[1], z = d[2], z2 = z * z;
+  R c0, c1, s0, s1, tmp_a, tmp_b, tmp_c;
+  out[0] = (R)0.28209479177387814;
+  out[2] = (R)(z * 0.488602511902919923);            // float*double -> double -> stored float
+  out[6] = (R)(z2 * 0.94617469575756008 + -0.315391565252520045);
+  c0 = x; s0 = y;
+  tmp_a = (R)-0.488602511902919978;
+  out[3] = tmp_a * c0;
+  out[1] = tmp_a * s0;
+  tmp_b = (R)(z * -1.09254843059207896);
+  out[7] = tmp_b * c0;
+  out[5] = tmp_b * s0;
+  c1 = x * c0 - y * s0;
+  s1 = x * s0 + y * c0;
+  tmp_c = (R)0.546274215296039478;
+  out[8] = tmp_c * c1;
+  out[4] = tmp_c * s1;
+}
+
+inline float r_exp(float x) { return std::exp(x); }    // expf
+inline double r_exp(double x) { return std::exp(x); }
+inline float r_log(float x) { return std::log(x); }    // logf
+inline double r_log(double x) { return std::log(x); }
+inline float r_sqrt(float x) { return std::sqrt(x); }
+inline double r_sqrt(double x) { return std::sqrt(x); }
+
+// per-sample record kept for the reverse sweep
+template <class R> struct Sample
+{
+  int nx, ny, nz, fx_, fy_, fz_;  // near / far node coords
+  R f[3];                         // lerp factors
+  R dens_raw, sigma, delta, tr, Tk;
+  R raw, s, rgb[3], c[3];
+};
+
+// a5 RayBoxIntersection example_tracer.cpp:18-43
+template <class R> inline void ray_box(const R *o, const R *d, const R *bmin, const R *bmax, R *tn, R *tf)
+{
+  R ix = (R)1.0f / d[0], iy = (R)1.0f / d[1], iz = (R)1.0f / d[2];
+  R lo = ix * (bmin[0] - o[0]), hi = ix * (bmax[0] - o[0]);
+  R tmin = lm_min(lo, hi), tmax = lm_max(lo, hi);
+  R lo1 = iy * (bmin[1] - o[1]), hi1 = iy * (bmax[1] - o[1]);
+  tmin = lm_max(tmin, lm_min(lo1, hi1));
+  tmax = lm_min(tmax, lm_max(lo1, hi1));
+  R lo2 = iz * (bmin[2] - o[2]), hi2 = iz * (bmax[2] - o[2]);
+  tmin = lm_max(tmin, lm_min(lo2, hi2));
+  tmax = lm_min(tmax, lm_max(lo2, hi2));
+  *tn = tmin; *tf = tmax;
+}
+
+// a6 RayGridIntersection example_tracer.cpp:120-194.  R = float reproduces the reference's mixed
+// float/double arithmetic; R = double is the all-fp64 restatement used for finite differences.
+// grid is AoS 13 values of type R.  Returns n_shaded.
+template <class R>
+size_t shade(const Oracle &S, const R *grid, const float *of, const float *df, double step, const uint64_t *ids, size_t n_ids,
+             bool grey, R *colour_out, R *colour_raw, R *T_out, R *cauchy_out, std::vector<Sample<R>> *tape, R *Y_out)
+{
+  const int gs = S.gs;
+  const R o[3] = {(R)of[0], (R)of[1], (R)of[2]}, d[3] = {(R)df[0], (R)df[1], (R)df[2]};
+  R thr = (R)1.0, col[3] = {0, 0, 0}, cauchy = 0, tPrev = (R)-1;
+  R Y[9];
+  sh_eval_2<R>(d, Y);
+  if (Y_out) std::memcpy(Y_out, Y, sizeof(Y));
+  size_t shaded = 0;
+  for (size_t k = 0; k < n_ids; k++) {
+    if (thr < 0.1) break;  // :131  float promoted to double vs the double literal 0.1
+    const int32_t *b = &S.box_xyz[3 * ids[k]];
+    // :134-135  boxes[i].Min/Max doubles narrowed to float
+    R bmin[3], bmax[3];
+    for (int a = 0; a < 3; a++) { bmin[a] = (R)(float)plane(b[a], gs); bmax[a] = (R)(float)plane(b[a] + 1, gs); }
+    R tn, tf;
+    ray_box<R>(o, d, bmin, bmax, &tn, &tf);
+    if (tPrev < (R)0.0f) tPrev = tn;                       // :139
+    R t = (tn + tf) / (R)2.0f;                             // :142
+    R actual = t - tPrev;                                  // :144
+    if ((double)actual > std::sqrt(3.0) * step)            // :145  sqrt(int) -> double
+      actual = (R)((double)actual - ((int)((double)actual / step) - 1) * step);  // :146
+    R p[3], lf[3];
+    for (int a = 0; a < 3; a++) { p[a] = o[a] + t * d[a]; lf[a] = (p[a] - bmin[a]) / (bmax[a] - bmin[a]); }  // :148-150
+    int nc[3], fc[3];
+    for (int a = 0; a < 3; a++) {  // :152-153
+      nc[a] = lm_clamp<int>((int)((float)bmin[a] * (float)gs), 0, gs - 1);
+      fc[a] = lm_clamp<int>(nc[a] + 1, 0, gs - 1);
+    }
+    auto node = [&](int x, int y, int z) { return grid + ((size_t)x + (size_t)y * gs + (size_t)z * gs * gs) * CELL; };
+    const R *c000 = node(nc[0], nc[1], nc[2]), *c100 = node(fc[0], nc[1], nc[2]);
+    const R *c010 = node(nc[0], fc[1], nc[2]), *c110 = node(fc[0], fc[1], nc[2]);
+    const R *c001 = node(nc[0], nc[1], fc[2]), *c101 = node(fc[0], nc[1], fc[2]);
+    const R *c011 = node(nc[0], fc[1], fc[2]), *c111 = node(fc[0], fc[1], fc[2]);
+    R g[CELL];
+    for (int j = 0; j < CELL; j++) {  // :155-167 via lerpCell :72-80
+      R xy00 = lm_lerp(c000[j], c100[j], lf[0]);
+      R xy10 = lm_lerp(c010[j], c110[j], lf[0]);
+      R xy01 = lm_lerp(c001[j], c101[j], lf[0]);
+      R xy11 = lm_lerp(c011[j], c111[j], lf[0]);
+      R xyz0 = lm_lerp(xy00, xy10, lf[1]);
+      R xyz1 = lm_lerp(xy01, xy11, lf[1]);
+      g[j] = lm_lerp(xyz0, xyz1, lf[2]);
+    }
+    R dens_raw = g[0];
+    if (g[0] < 0.0) g[0] = 0.0;                            // :170-171
+    cauchy += r_log((R)1 + (R)2 * g[0] * g[0]);            // :173
+    R tr = r_exp(-g[0] * actual);                          // :175
+    R rgb[3], raw = 0, s = 0;
+    if (grey) { rgb[0] = rgb[1] = rgb[2] = (R)1.0f; }
+    else {
+      R sum = (R)0.0f;                                     // eval_sh :108-118
+      for (int i = 0; i < 9; i++) sum += g[4 + i] * Y[i];
+      raw = sum;
+      s = lm_clamp<R>(sum, (R)0.0f, (R)1.0f);              // :181
+      for (int c = 0; c < 3; c++) rgb[c] = lm_clamp<R>(g[1 + c] * s, (R)0.0f, (R)1.0f);  // :182-184
+    }
+    if (tape) {
+      Sample<R> sm;
+      sm.nx = nc[0]; sm.ny = nc[1]; sm.nz = nc[2]; sm.fx_ = fc[0]; sm.fy_ = fc[1]; sm.fz_ = fc[2];
+      sm.f[0] = lf[0]; sm.f[1] = lf[1]; sm.f[2] = lf[2];
+      sm.dens_raw = dens_raw; sm.sigma = g[0]; sm.delta = actual; sm.tr = tr; sm.Tk = thr;
+      sm.raw = raw; sm.s = s;
+      for (int c = 0; c < 3; c++) { sm.rgb[c] = g[1 + c]; sm.c[c] = rgb[c]; }
+      tape->push_back(sm);
+    }
+    R wgt = thr * ((R)1 - tr);                             // :187  throughput * (1 - tr) * RGB
+    for (int c = 0; c < 3; c++) col[c] = col[c] + wgt * rgb[c];
+    thr *= tr;                                             // :189
+    tPrev = t;
+    shaded++;
+  }
+  *T_out = thr;
+  *cauchy_out = cauchy;
+  for (int c = 0; c < 3; c++) {
+    if (colour_raw) colour_raw[c] = col[c];
+    colour_out[c] = lm_clamp<R>(col[c], (R)0.0, (R)1.0);   // :193
+  }
+  return shaded;
+}
+
+// a10 RayGridLoss example_tracer.cpp:258-268
+inline float loss_from(const float *c, const float *ref, float cauchy, float T)
+{
+  // float + float + float + float + (float * double)  -> double -> float
+  return (float)(std::abs(c[0] - ref[0]) + std::abs(c[1] - ref[1]) + std::abs(c[2] - ref[2]) + 0.0005f * cauchy +
+                 0.0001f * (std::log(T + 1e-3) + std::log(1 - T + 1e-3)));
+}
+inline double loss_from(const double *c, const double *ref, double cauchy, double T)
+{
+  return std::abs(c[0] - ref[0]) + std::abs(c[1] - ref[1]) + std::abs(c[2] - ref[2]) + (double)0.0005f * cauchy +
+         (double)0.0001f * (std::log(T + 1e-3) + std::log(1 - T + 1e-3));
+}
+
+// a11: hand-derived reverse sweep of RayGridLoss wrt grid (what Enzyme generates at :270-279).
+// Tie conventions: clamp passes iff a < u <= b; relu passes iff density >= 0.
+template <class R>
+void ray_backward(const Oracle &S, const R *grid, R *grad, const float *ref_rgba, const float *of, const float *df, double step,
+                  const uint64_t *ids, size_t n_ids, bool grey)
+{
+  std::vector<Sample<R>> tape;
+  tape.reserve(n_ids);
+  R C[3], Craw[3], T, cauchy, Y[9];
+  shade<R>(S, grid, of, df, step, ids, n_ids, grey, C, Craw, &T, &cauchy, &tape, Y);
+  R aC[3];
+  for (int c = 0; c < 3; c++) {
+    R diff = C[c] - (R)ref_rgba[c];
+    R sg = diff < 0 ? (R)-1 : (R)1;                        // d|x|/dx, +1 at 0 (measure zero)
+    bool pass = ((R)0 < Craw[c]) && (Craw[c] <= (R)1);
+    aC[c] = pass ? sg : (R)0;
+  }
+  // d/dT of 0.0001f*(log(T+1e-3)+log(1-T+1e-3)), evaluated in double like the forward
+  R aT = (R)((double)0.0001f * (1.0 / ((double)T + 1e-3) - 1.0 / ((double)((R)1 - T) + 1e-3)));
+  const int gs = S.gs;
+  for (size_t kk = tape.size(); kk-- > 0;) {
+    const Sample<R> &sm = tape[kk];
+    R dot = sm.c[0] * aC[0] + sm.c[1] * aC[1] + sm.c[2] * aC[2];
+    R a_tr = -sm.Tk * dot + sm.Tk * aT;
+    R aT_new = sm.tr * aT + ((R)1 - sm.tr) * dot;
+    R a_sigma = -sm.delta * sm.tr * a_tr + (R)0.0005f * ((R)4 * sm.sigma / ((R)1 + (R)2 * sm.sigma * sm.sigma));
+    R a[CELL];
+    for (int j = 0; j < CELL; j++) a[j] = 0;
+    a[0] = (sm.dens_raw < 0) ? (R)0 : a_sigma;
+    if (!grey) {
+      R w = sm.Tk * ((R)1 - sm.tr), a_s = 0;
+      for (int c = 0; c < 3; c++) {
+        R a_c = w * aC[c];
+        R u = sm.rgb[c] * sm.s;
+        bool p = ((R)0 < u) && (u <= (R)1);
+        if (p) { a[1 + c] = sm.s * a_c; a_s += sm.rgb[c] * a_c; }
+      }
+      R a_raw = (((R)0 < sm.raw) && (sm.raw <= (R)1)) ? a_s : (R)0;
+      for (int j = 0; j < 9; j++) a[4 + j] = Y[j] * a_raw;
+    }
+    const int xs[2] = {sm.nx, sm.fx_}, ys[2] = {sm.ny, sm.fy_}, zs[2] = {sm.nz, sm.fz_};
+    for (int bz = 0; bz < 2; bz++)
+      for (int by = 0; by < 2; by++)
+        for (int bx = 0; bx < 2; bx++) {
+          R w = (bx ? sm.f[0] : (R)1 - sm.f[0]) * (by ? sm.f[1] : (R)1 - sm.f[1]) * (bz ? sm.f[2] : (R)1 - sm.f[2]);
+          R *gp = grad + ((size_t)xs[bx] + (size_t)ys[by] * gs + (size_t)zs[bz] * gs * gs) * CELL;
+          for (int j = 0; j < CELL; j++) gp[j] += w * a[j];
+        }
+    aT = aT_new;
+  }
+}
+
+// a12 TVRegularisation example_tracer.cpp:196-248 — density term only (the SH loop at :241-245
+// writes out of bounds of a stack float and never reaches the return value; SURVEY §2 defects).
+template <class R> inline R tv_voxel(const R *dens, int gs, size_t x, size_t y, size_t z, int stride)
+{
+  // getVoxel :203-230.  coords = (x,y,z)+0.5; near = trunc; far = clamp(near+1); factors = 0.5
+  int nc[3] = {lm_clamp<int>((int)((float)x + 0.5f), 0, gs - 1), lm_clamp<int>((int)((float)y + 0.5f), 0, gs - 1),
+               lm_clamp<int>((int)((float)z + 0.5f), 0, gs - 1)};
+  int fc[3] = {lm_clamp<int>((int)((float)x + 0.5f) + 1, 0, gs - 1), lm_clamp<int>((int)((float)y + 0.5f) + 1, 0, gs - 1),
+               lm_clamp<int>((int)((float)z + 0.5f) + 1, 0, gs - 1)};
+  R lf[3] = {(R)(((float)x + 0.5f) - (float)nc[0]), (R)(((float)y + 0.5f) - (float)nc[1]), (R)(((float)z + 0.5f) - (float)nc[2])};
+  auto at = [&](int a, int b, int c) { return dens[((size_t)a + (size_t)b * gs + (size_t)c * gs * gs) * stride]; };
+  R xy00 = lm_lerp(at(nc[0], nc[1], nc[2]), at(fc[0], nc[1], nc[2]), lf[0]);
+  R xy10 = lm_lerp(at(nc[0], fc[1], nc[2]), at(fc[0], fc[1], nc[2]), lf[0]);
+  R xy01 = lm_lerp(at(nc[0], nc[1], fc[2]), at(fc[0], nc[1], fc[2]), lf[0]);
+  R xy11 = lm_lerp(at(nc[0], fc[1], fc[2]), at(fc[0], fc[1], fc[2]), lf[0]);
+  R xyz0 = lm_lerp(xy00, xy10, lf[1]);
+  R xyz1 = lm_lerp(xy01, xy11, lf[1]);
+  return lm_lerp(xyz0, xyz1, lf[2]);  // relu applied by the caller (needs the raw value for the gate)
+}
+template <class R> inline R relu(R v) { return (v < 0.0) ? (R)0 : v; }
+
+template <class R> R tv_value(const R *dens, int gs, size_t x, size_t y, size_t z, int stride)
+{
+  R v = relu(tv_voxel(dens, gs, x, y, z, stride)), vx = relu(tv_voxel(dens, gs, x + 1, y, z, stride));
+  R vy = relu(tv_voxel(dens, gs, x, y + 1, z, stride)), vz = relu(tv_voxel(dens, gs, x, y, z + 1, stride));
+  R lambda_density = (R)0.01f;
+  return lambda_density * r_sqrt((v - vx) * (v - vx) + (v - vy) * (v - vy) + (v - vz) * (v - vz));  // :237-239
+}
+
+// adjoint of tv_value wrt the density nodes, accumulated into grad (stride = CELL for AoS).
+// sqrt'(0) := 0 (Enzyme's rule; the only convention under which the uniform InitGrid can train).
+template <class R> void tv_backward(const R *dens, R *grad, int gs, size_t x, size_t y, size_t z, int stride)
+{
+  const size_t px[4] = {x, x + 1, x, x}, py[4] = {y, y, y + 1, y}, pz[4] = {z, z, z, z + 1};
+  R raw[4], v[4];
+  for (int i = 0; i < 4; i++) { raw[i] = tv_voxel(dens, gs, px[i], py[i], pz[i], stride); v[i] = relu(raw[i]); }
+  R dx = v[0] - v[1], dy = v[0] - v[2], dz = v[0] - v[3];
+  R sum = dx * dx + dy * dy + dz * dz;
+  if (!(sum > 0)) return;
+  R r = r_sqrt(sum), lam = (R)0.01f;
+  R gv[4] = {lam * (dx + dy + dz) / r, -lam * dx / r, -lam * dy / r, -lam * dz / r};
+  for (int i = 0; i < 4; i++) {
+    if (raw[i] < 0.0) continue;  // relu gate
+    int nc[3] = {lm_clamp<int>((int)px[i], 0, gs - 1), lm_clamp<int>((int)py[i], 0, gs - 1), lm_clamp<int>((int)pz[i], 0, gs - 1)};
+    int fc[3] = {lm_clamp<int>((int)px[i] + 1, 0, gs - 1), lm_clamp<int>((int)py[i] + 1, 0, gs - 1), lm_clamp<int>((int)pz[i] + 1, 0, gs - 1)};
+    for (int b = 0; b < 8; b++) {
+      int a = (b & 1) ? fc[0] : nc[0], bb = (b & 2) ? fc[1] : nc[1], c = (b & 4) ? fc[2] : nc[2];
+      grad[((size_t)a + (size_t)bb * gs + (size_t)c * gs * gs) * stride] += (R)0.125 * gv[i];
+    }
+  }
+}
+
+// trilinear sample of all 13 channels used by UpsampleGrid / UpsampleOctree / RebuildOctree
+inline void lerp_cell8(const float *grid, int gs, const int *nc, const int *fc, const float *lf, float *out)
+{
+  auto node = [&](int x, int y, int z) { return grid + ((size_t)x + (size_t)y * gs + (size_t)z * gs * gs) * CELL; };
+  const float *c000 = node(nc[0], nc[1], nc[2]), *c100 = node(fc[0], nc[1], nc[2]);
+  const float *c010 = node(nc[0], fc[1], nc[2]), *c110 = node(fc[0], fc[1], nc[2]);
+  const float *c001 = node(nc[0], nc[1], fc[2]), *c101 = node(fc[0], nc[1], fc[2]);
+  const float *c011 = node(nc[0], fc[1], fc[2]), *c111 = node(fc[0], fc[1], fc[2]);
+  for (int j = 0; j < CELL; j++) {
+    float xy00 = lm_lerp(c000[j], c100[j], lf[0]), xy10 = lm_lerp(c010[j], c110[j], lf[0]);
+    float xy01 = lm_lerp(c001[j], c101[j], lf[0]), xy11 = lm_lerp(c011[j], c111[j], lf[0]);
+    float xyz0 = lm_lerp(xy00, xy10, lf[1]), xyz1 = lm_lerp(xy01, xy11, lf[1]);
+    out[j] = lm_lerp(xyz0, xyz1, lf[2]);
+  }
+}
+
+// getDensity lambda of UpsampleOctree (example_tracer.cpp:331-357) / body of RebuildOctree (:459-483)
+// for the lattice box (x,y,z): un-relu'd trilinear density at the box centre.
+float box_centre_density(const Oracle &S, int x, int y, int z)
+{
+  const int gs = S.gs;
+  const int b[3] = {x, y, z};
+  float bmin[3], bmax[3], p[3], lf[3];
+  int nc[3], fc[3];
+  for (int a = 0; a < 3; a++) {
+    bmin[a] = (float)plane(b[a], gs); bmax[a] = (float)plane(b[a] + 1, gs);
+    p[a] = (bmin[a] + bmax[a]) / 2.0f;
+    lf[a] = (p[a] - bmin[a]) / (bmax[a] - bmin[a]);
+    nc[a] = lm_clamp<int>((int)(bmin[a] * (float)gs), 0, gs - 1);
+    fc[a] = lm_clamp<int>(nc[a] + 1, 0, gs - 1);
+  }
+  float g[CELL];
+  lerp_cell8(S.grid.data(), gs, nc, fc, lf, g);
+  return g[0];
+}
+
+double step_of(const Oracle &S) { return (double)((S.bb_max[0] - S.bb_min[0]) / (float)S.gs); }  // :649 / :692
+
+uint32_t pack_color(const float *c)  // example_tracer.cpp:578-591
+{
+  float r = c[0] * 255.0f, g = c[1] * 255.0f, b = c[2] * 255.0f, a = c[3] * 255.0f;
+  uint32_t red = (uint32_t)r, green = (uint32_t)g, blue = (uint32_t)b, alpha = (uint32_t)a;
+  return red | (green << 8) | (blue << 16) | (alpha << 24);
+}
+
+void trace_one(const Oracle &S, const float *o, const float *d, bool grey, uint32_t *n_hit, uint32_t *n_shaded, float *rgbtc,
+               std::vector<Hit> &hits, std::vector<uint64_t> &ids)
+{
+  ray_hits(S, o, d, hits);
+  ids.resize(hits.size());
+  for (size_t i = 0; i < hits.size(); i++) ids[i] = hits[i].id;
+  *n_hit = (uint32_t)hits.size();
+  *n_shaded = 0;
+  rgbtc[0] = rgbtc[1] = rgbtc[2] = rgbtc[3] = rgbtc[4] = 0.0f;
+  if (!hits.empty())  // example_tracer.cpp:646
+    *n_shaded = (uint32_t)shade<float>(S, S.grid.data(), o, d, step_of(S), ids.data(), ids.size(), grey, rgbtc, nullptr, rgbtc + 3,
+                                       rgbtc + 4, nullptr, nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+void orc_perspective(float fovy, float aspect, float zNear, float zFar, float *out)  // LiteMath.h:1797-1815
+{
+  const float ymax = zNear * tanf(fovy * 3.14159265358979323846f / 360.0f);
+  const float xmax = ymax * aspect;
+  const float left = -xmax, right = +xmax, bottom = -ymax, top = +ymax;
+  const float temp = 2.0f * zNear, temp2 = right - left, temp3 = top - bottom, temp4 = zFar - zNear;
+  float m[16] = {temp / temp2, 0.0f, 0.0f, 0.0f, 0.0f, temp / temp3, 0.0f, 0.0f,
+                 (right + left) / temp2, (top + bottom) / temp3, (-zFar - zNear) / temp4, (float)-1.0,
+                 0.0f, 0.0f, (-temp * zFar) / temp4, 0.0f};
+  std::memcpy(out, m, sizeof(m));
+}
+
+void orc_orbit_view(int k, int n_views, float *out)  // main.cpp:99-102
+{
+  float eye[3] = {0.0f, 0.0f, 1.3f}, center[3] = {0, 0, 0}, up[3] = {0, 1, 0};
+  float la[16], rot[16], tr[16], tmp[16];
+  look_at(eye, center, up, la);
+  const float DEG_TO_RAD = float(3.14159265358979323846f) / 180.0f;  // LiteMath.h:60
+  float phi = -float(360.0 / n_views * k) * DEG_TO_RAD;
+  mat_identity(rot);  // rotate4x4Y LiteMath.h:1521-1529
+  rot[0] = +cosf(phi); rot[1] = 0.0f; rot[2] = -sinf(phi); rot[3] = 0.0f;
+  rot[8] = +sinf(phi); rot[9] = 0.0f; rot[10] = +cosf(phi); rot[11] = 0.0f;
+  mat_identity(tr);   // translate4x4 LiteMath.h:1494-1499
+  tr[12] = -0.5f; tr[13] = -0.5f; tr[14] = -0.5f; tr[15] = 1.0f;
+  mat_mul_mat(tmp, la, rot);
+  mat_mul_mat(out, tmp, tr);
+}
+void orc_inverse4x4(const float *in16, float *out16) { inverse4x4(in16, out16); }
+
+void *orc_create(int gs)  // InitGrid example_tracer.h:51-91 (+ optimizerInit, InitGrad)
+{
+  Oracle *S = new Oracle();
+  S->gs = gs;
+  S->grid.resize(S->N() * CELL);
+  for (size_t i = 0; i < S->N(); i++) {
+    S->grid[i * CELL] = 0.01;
+    for (int j = 1; j < CELL; j++) S->grid[i * CELL + j] = 0.1;
+  }
+  const int n = gs - 1;
+  S->box_xyz.resize((size_t)n * n * n * 3);
+  for (int z = 0; z < n; z++)
+    for (int y = 0; y < n; y++)
+      for (int x = 0; x < n; x++) {
+        size_t i = (size_t)x + (size_t)y * n + (size_t)z * n * n;  // :77
+        S->box_xyz[3 * i] = x; S->box_xyz[3 * i + 1] = y; S->box_xyz[3 * i + 2] = z;
+      }
+  S->rebuild_map();
+  S->grad.assign(S->N() * CELL, 0.0f);
+  S->V.assign(S->N() * CELL, 0.0f);
+  S->S.assign(S->N() * CELL, 0.0f);
+  mat_identity(S->view_inv);
+  mat_identity(S->proj_inv);
+  return S;
+}
+void orc_destroy(void *h) { delete (Oracle *)h; }
+int orc_grid_size(void *h) { return ((Oracle *)h)->gs; }
+float *orc_grid_ptr(void *h) { return ((Oracle *)h)->grid.data(); }
+float *orc_grad_ptr(void *h) { return ((Oracle *)h)->grad.data(); }
+float *orc_adam_v_ptr(void *h) { return ((Oracle *)h)->V.data(); }
+float *orc_adam_s_ptr(void *h) { return ((Oracle *)h)->S.data(); }
+size_t orc_box_count(void *h) { return ((Oracle *)h)->box_xyz.size() / 3; }
+void orc_get_boxes_xyz(void *h, int32_t *xyz) { auto *S = (Oracle *)h; std::memcpy(xyz, S->box_xyz.data(), S->box_xyz.size() * 4); }
+void orc_set_boxes_xyz(void *h, const int32_t *xyz, size_t n)
+{
+  auto *S = (Oracle *)h;
+  S->box_xyz.assign(xyz, xyz + 3 * n);
+  S->rebuild_map();
+}
+void orc_set_bbox(void *h, const float *mn, const float *mx)
+{
+  auto *S = (Oracle *)h;
+  for (int a = 0; a < 3; a++) { S->bb_min[a] = mn[a]; S->bb_max[a] = mx[a]; }
+}
+void orc_set_view_inv(void *h, const float *m) { std::memcpy(((Oracle *)h)->view_inv, m, 64); }
+void orc_set_proj_inv(void *h, const float *m) { std::memcpy(((Oracle *)h)->proj_inv, m, 64); }
+
+void orc_gen_ray(void *h, uint32_t x, uint32_t y, uint32_t w, uint32_t hgt, float *o, float *d)
+{
+  auto *S = (Oracle *)h;
+  gen_ray(S->view_inv, S->proj_inv, x, y, w, hgt, o, d);
+}
+
+size_t orc_ray_hits(void *h, const float *o, const float *d, uint64_t *ids, size_t cap)
+{
+  std::vector<Hit> hits;
+  ray_hits(*(Oracle *)h, o, d, hits);
+  for (size_t i = 0; i < hits.size() && i < cap; i++) ids[i] = hits[i].id;
+  return hits.size();
+}
+
+size_t orc_ray_hits_generic(int dim, const double *bx, size_t n, const double *origin, const double *heading, uint64_t *ids, size_t cap)
+{
+  std::vector<Hit> hits;
+  for (size_t i = 0; i < n; i++) {
+    double dist;
+    if (is_ray_hit(dim, bx + i * 2 * dim, bx + i * 2 * dim + dim, origin, heading, 0.0, &dist)) hits.push_back({dist, (uint64_t)i});
+  }
+  std::sort(hits.begin(), hits.end(), hit_less);
+  for (size_t i = 0; i < hits.size() && i < cap; i++) ids[i] = hits[i].id;
+  return hits.size();
+}
+
+size_t orc_shade(void *h, const float *o, const float *d, const uint64_t *ids, size_t n, int grey, float *rgb, float *T, float *cauchy)
+{
+  auto *S = (Oracle *)h;
+  return shade<float>(*S, S->grid.data(), o, d, step_of(*S), ids, n, grey != 0, rgb, nullptr, T, cauchy, nullptr, nullptr);
+}
+
+// kernel2D_RayMarch example_tracer.cpp:627-663
+void orc_render(void *h, uint32_t *out, uint32_t w, uint32_t hgt, int grey)
+{
+  auto *S = (Oracle *)h;
+#pragma omp parallel
+  {
+    std::vector<Hit> hits;
+    std::vector<uint64_t> ids;
+#pragma omp for schedule(dynamic, 1)
+    for (uint32_t y = 0; y < hgt; y++)
+      for (uint32_t x = 0; x < w; x++) {
+        float o[3], d[3], rgbtc[5];
+        uint32_t nh, ns;
+        gen_ray(S->view_inv, S->proj_inv, x, y, w, hgt, o, d);
+        trace_one(*S, o, d, grey != 0, &nh, &ns, rgbtc, hits, ids);
+        float res[4] = {0, 0, 0, 0};
+        if (nh) { res[0] = rgbtc[0]; res[1] = rgbtc[1]; res[2] = rgbtc[2]; res[3] = 1.0f; }
+        out[(size_t)y * w + x] = pack_color(res);
+      }
+  }
+}
+
+void orc_render_debug(void *h, uint32_t w, uint32_t hgt, int grey, uint32_t *n_hit, uint32_t *n_shaded, float *rgbtc, int64_t *ids_out,
+                      uint32_t keep)
+{
+  auto *S = (Oracle *)h;
+#pragma omp parallel
+  {
+    std::vector<Hit> hits;
+    std::vector<uint64_t> ids;
+#pragma omp for schedule(dynamic, 1)
+    for (uint32_t y = 0; y < hgt; y++)
+      for (uint32_t x = 0; x < w; x++) {
+        size_t pix = (size_t)y * w + x;
+        float o[3], d[3];
+        gen_ray(S->view_inv, S->proj_inv, x, y, w, hgt, o, d);
+        trace_one(*S, o, d, grey != 0, n_hit + pix, n_shaded + pix, rgbtc + pix * 5, hits, ids);
+        for (uint32_t i = 0; i < keep; i++) ids_out[pix * keep + i] = i < ids.size() ? (int64_t)ids[i] : -1;
+      }
+  }
+}
+
+void orc_trace_rays(void *h, size_t n, const float *o, const float *d, int grey, uint32_t *n_hit, uint32_t *n_shaded, float *rgbtc,
+                    int32_t *vox_xyz_out, uint32_t keep)
+{
+  auto *S = (Oracle *)h;
+#pragma omp parallel
+  {
+    std::vector<Hit> hits;
+    std::vector<uint64_t> ids;
+#pragma omp for schedule(dynamic, 16)
+    for (size_t r = 0; r < n; r++) {
+      trace_one(*S, o + 3 * r, d + 3 * r, grey != 0, n_hit + r, n_shaded + r, rgbtc + r * 5, hits, ids);
+      for (uint32_t i = 0; i < keep; i++)
+        for (int a = 0; a < 3; a++)
+          vox_xyz_out[(r * keep + i) * 3 + a] = i < ids.size() ? S->box_xyz[3 * ids[i] + a] : -1;
+    }
+  }
+}
+
+uint64_t orc_count_touched_nodes(void *h, uint32_t w, uint32_t hgt, int grey)
+{
+  auto *S = (Oracle *)h;
+  std::vector<uint8_t> touched(S->N(), 0);
+  const int gs = S->gs;
+#pragma omp parallel
+  {
+    std::vector<Hit> hits;
+    std::vector<uint64_t> ids;
+#pragma omp for schedule(dynamic, 1)
+    for (uint32_t y = 0; y < hgt; y++)
+      for (uint32_t x = 0; x < w; x++) {
+        float o[3], d[3], rgbtc[5];
+        uint32_t nh, ns;
+        gen_ray(S->view_inv, S->proj_inv, x, y, w, hgt, o, d);
+        trace_one(*S, o, d, grey != 0, &nh, &ns, rgbtc, hits, ids);
+        for (uint32_t i = 0; i < ns; i++) {
+          const int32_t *b = &S->box_xyz[3 * ids[i]];
+          for (int c = 0; c < 8; c++) {
+            size_t idx = (size_t)(b[0] + (c & 1)) + (size_t)(b[1] + ((c >> 1) & 1)) * gs + (size_t)(b[2] + ((c >> 2) & 1)) * gs * gs;
+            touched[idx] = 1;  // benign race: all writers store 1
+          }
+        }
+      }
+  }
+  uint64_t cnt = 0;
+  for (uint8_t t : touched) cnt += t;
+  return cnt;
+}
+
+float orc_ray_loss(void *h, const float *ref, const float *o, const float *d, const uint64_t *ids, size_t n, int grey)
+{
+  auto *S = (Oracle *)h;
+  float c[3], T, cauchy;
+  shade<float>(*S, S->grid.data(), o, d, step_of(*S), ids, n, grey != 0, c, nullptr, &T, &cauchy, nullptr, nullptr);
+  return loss_from(c, ref, cauchy, T);
+}
+double orc_ray_loss_f64(void *h, const double *grid64, const float *ref, const float *o, const float *d, const uint64_t *ids, size_t n,
+                        int grey)
+{
+  auto *S = (Oracle *)h;
+  double c[3], T, cauchy, r[3] = {ref[0], ref[1], ref[2]};
+  shade<double>(*S, grid64, o, d, step_of(*S), ids, n, grey != 0, c, nullptr, &T, &cauchy, nullptr, nullptr);
+  return loss_from(c, r, cauchy, T);
+}
+void orc_ray_grad(void *h, const float *ref, const float *o, const float *d, const uint64_t *ids, size_t n, int grey)
+{
+  auto *S = (Oracle *)h;
+  ray_backward<float>(*S, S->grid.data(), S->grad.data(), ref, o, d, step_of(*S), ids, n, grey != 0);
+}
+void orc_ray_grad_f64(void *h, const double *grid64, double *grad64, const float *ref, const float *o, const float *d,
+                      const uint64_t *ids, size_t n, int grey)
+{
+  auto *S = (Oracle *)h;
+  ray_backward<double>(*S, grid64, grad64, ref, o, d, step_of(*S), ids, n, grey != 0);
+}
+
+// kernel2D_RayMarchGrad example_tracer.cpp:665-718, SERIAL accumulation (the reference's OpenMP
+// loop races on grid_d; serial order y,x is the defined semantics, SURVEY §2 defects)
+void orc_render_grad(void *h, uint32_t w, uint32_t hgt, const float *ref_rgba, int grey)
+{
+  auto *S = (Oracle *)h;
+  std::vector<Hit> hits;
+  std::vector<uint64_t> ids;
+  for (uint32_t y = 0; y < hgt; y++)
+    for (uint32_t x = 0; x < w; x++) {
+      float o[3], d[3];
+      gen_ray(S->view_inv, S->proj_inv, x, y, w, hgt, o, d);
+      ray_hits(*S, o, d, hits);
+      if (hits.empty()) continue;
+      ids.resize(hits.size());
+      for (size_t i = 0; i < hits.size(); i++) ids[i] = hits[i].id;
+      const float *rp = ref_rgba + ((size_t)y * w + x) * 4;
+      float ref[4] = {rp[0], rp[1], rp[2], rp[3]};
+      if (grey) {  // :696-704
+        float gsc = 0.11f * rp[2] + 0.59f * rp[1] + 0.3f * rp[0];
+        ref[0] = ref[1] = ref[2] = gsc;
+      }
+      ray_backward<float>(*S, S->grid.data(), S->grad.data(), ref, o, d, step_of(*S), ids.data(), ids.size(), grey != 0);
+    }
+}
+void orc_rays_grad(void *h, size_t n, const float *o, const float *d, const float *ref_rgba, int grey)
+{
+  auto *S = (Oracle *)h;
+  std::vector<Hit> hits;
+  std::vector<uint64_t> ids;
+  for (size_t r = 0; r < n; r++) {
+    ray_hits(*S, o + 3 * r, d + 3 * r, hits);
+    if (hits.empty()) continue;
+    ids.resize(hits.size());
+    for (size_t i = 0; i < hits.size(); i++) ids[i] = hits[i].id;
+    const float *rp = ref_rgba + r * 4;
+    float ref[4] = {rp[0], rp[1], rp[2], rp[3]};
+    if (grey) { float gsc = 0.11f * rp[2] + 0.59f * rp[1] + 0.3f * rp[0]; ref[0] = ref[1] = ref[2] = gsc; }
+    ray_backward<float>(*S, S->grid.data(), S->grad.data(), ref, o + 3 * r, d + 3 * r, step_of(*S), ids.data(), ids.size(), grey != 0);
+  }
+}
+
+float orc_tv(void *h, size_t x, size_t y, size_t z)
+{
+  auto *S = (Oracle *)h;
+  return tv_value<float>(S->grid.data(), S->gs, x, y, z, CELL);
+}
+double orc_tv_total_f64(void *h, const double *density64)
+{
+  auto *S = (Oracle *)h;
+  double tot = 0;
+  for (int z = 0; z < S->gs - 1; z++)
+    for (int y = 0; y < S->gs - 1; y++)
+      for (int x = 0; x < S->gs - 1; x++) tot += tv_value<double>(density64, S->gs, x, y, z, 1);
+  return tot;
+}
+// kernel2D_TVGrad example_tracer.cpp:737-749, serial z,y,x order
+void orc_tv_grad(void *h)
+{
+  auto *S = (Oracle *)h;
+  for (int z = 0; z < S->gs - 1; z++)
+    for (int y = 0; y < S->gs - 1; y++)
+      for (int x = 0; x < S->gs - 1; x++) tv_backward<float>(S->grid.data(), S->grad.data(), S->gs, x, y, z, CELL);
+}
+void orc_zero_grad(void *h) { auto *S = (Oracle *)h; std::fill(S->grad.begin(), S->grad.end(), 0.0f); }  // example_tracer.h:104-109
+void orc_adam_init(void *h)  // example_tracer.h:111-126
+{
+  auto *S = (Oracle *)h;
+  S->lr = 0.15f; S->beta_1 = 0.9f; S->beta_2 = 0.999f; S->eps = 1e-8;
+  S->V.assign(S->N() * CELL, 0.0f);
+  S->S.assign(S->N() * CELL, 0.0f);
+  S->grad.resize(S->N() * CELL);
+}
+// optimizerStep / optimizerStepDensity / optimizerStepSH example_tracer.h:128-206
+void orc_adam_step(void *h, int iter, int which)
+{
+  auto *S = (Oracle *)h;
+  const size_t vecSize = S->N() * CELL;
+  float *p = S->grid.data(), *g_ = S->grad.data();
+  const float beta_1 = S->beta_1, beta_2 = S->beta_2, lr = S->lr, eps = S->eps;
+  const double b1 = std::pow(beta_1, iter + 1);  // std::pow(float,int) -> double
+  const double b2 = std::pow(beta_2, iter + 1);
+  for (size_t i = 0; i < vecSize; i++) {
+    bool dens = (i % CELL) == 0;
+    if (which == 1 && !dens) continue;
+    if (which == 2 && dens) continue;
+    float g = g_[i];
+    S->V[i] = beta_1 * S->V[i] + (1 - beta_1) * g;
+    double Vh = S->V[i] / ((1) - b1);
+    S->S[i] = beta_2 * S->S[i] + (1 - beta_2) * g * g;
+    double Sh = S->S[i] / ((1) - b2);
+    p[i] -= lr * Vh / (std::sqrt(Sh) + eps);
+  }
+}
+
+// UpsampleGrid example_tracer.cpp:281-323 (+ InitGrad/optimizerInit as main.cpp:129-130 does)
+void orc_upsample_grid(void *h)
+{
+  auto *S = (Oracle *)h;
+  const int oldG = S->gs, gs = oldG * 2;
+  const float step = 1.0f / (float)gs;
+  std::vector<float> ng((size_t)gs * gs * gs * CELL);
+  for (int z = 0; z < gs; z++)
+    for (int y = 0; y < gs; y++)
+      for (int x = 0; x < gs; x++) {
+        const int xyz[3] = {x, y, z};
+        float coords[3], lf[3];
+        int nc[3], fc[3];
+        for (int a = 0; a < 3; a++) {
+          coords[a] = (0.0f + step * ((float)xyz[a] + 0.5f)) * (float)oldG;  // :294
+          nc[a] = lm_clamp<int>((int)coords[a], 0, oldG - 1);
+          fc[a] = lm_clamp<int>((int)coords[a] + 1, 0, oldG - 1);
+          lf[a] = coords[a] - (float)nc[a];
+        }
+        float g[CELL];
+        lerp_cell8(S->grid.data(), oldG, nc, fc, lf, g);
+        if (g[0] < 0.0) g[0] = 0.0;
+        std::memcpy(&ng[((size_t)x + (size_t)y * gs + (size_t)z * gs * gs) * CELL], g, sizeof(g));
+      }
+  S->grid.swap(ng);
+  S->gs = gs;
+  S->grad.assign(S->N() * CELL, 0.0f);
+  orc_adam_init(h);
+  // the box list is NOT touched here (UpsampleOctree does that); the voxel->id map is rebuilt for the new lattice size
+  S->rebuild_map();
+}
+
+// UpsampleOctree example_tracer.cpp:325-447: each box -> 8 half-size children in the fixed order
+// (---),(+++),(+--),(-+-),(++-),(--+),(+-+),(-++); child kept iff centre density > 0.
+void orc_upsample_boxes(void *h)
+{
+  auto *S = (Oracle *)h;
+  static const int order[8][3] = {{0, 0, 0}, {1, 1, 1}, {1, 0, 0}, {0, 1, 0}, {1, 1, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};
+  std::vector<int32_t> nb;
+  const size_t n_old = S->box_xyz.size() / 3;
+  for (size_t i = 0; i < n_old; i++)
+    for (int c = 0; c < 8; c++) {
+      int x = 2 * S->box_xyz[3 * i] + order[c][0], y = 2 * S->box_xyz[3 * i + 1] + order[c][1], z = 2 * S->box_xyz[3 * i + 2] + order[c][2];
+      if (box_centre_density(*S, x, y, z) > 0.0) { nb.push_back(x); nb.push_back(y); nb.push_back(z); }
+    }
+  S->box_xyz.swap(nb);
+  S->rebuild_map();
+}
+// RebuildOctree example_tracer.cpp:449-489
+void orc_rebuild_boxes(void *h)
+{
+  auto *S = (Oracle *)h;
+  std::vector<int32_t> nb;
+  const size_t n_old = S->box_xyz.size() / 3;
+  for (size_t i = 0; i < n_old; i++) {
+    int x = S->box_xyz[3 * i], y = S->box_xyz[3 * i + 1], z = S->box_xyz[3 * i + 2];
+    if (box_centre_density(*S, x, y, z) > 0.0) { nb.push_back(x); nb.push_back(y); nb.push_back(z); }
+  }
+  S->box_xyz.swap(nb);
+  S->rebuild_map();
+}
+
+uint32_t orc_pack_color(const float *rgba) { return pack_color(rgba); }
+
+// glibc expf (sysdeps/ieee754/flt-32/e_expf.c, ARM optimized-routines algorithm, glibc 2.27..2.40),
+// restated: N = 32 table, degree-3 polynomial, all in double, result narrowed to float.
+// use_fma selects the contraction the x86_64 ifunc variant __expf_fma is compiled with.
+float orc_expf_model(float x, int use_fma)
+{
+  static const uint64_t T[32] = {
+      0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL, 0x3fef72b83c7d517bULL,
+      0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL, 0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL,
+      0x3feedea64c123422ULL, 0x3feece086061892dULL, 0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL,
+      0x3feea47eb03a5585ULL, 0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL,
+      0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL, 0x3feee89f995ad3adULL,
+      0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL, 0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL,
+      0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
+  const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
+  uint32_t ix;
+  std::memcpy(&ix, &x, 4);
+  uint32_t abstop = (ix >> 20) & 0x7ff;
+  if (abstop >= 0x42b) {  // |x| >= 88 or nan
+    if (ix == 0xff800000u) return 0.0f;
+    if (abstop >= 0x7f8) return x + x;
+    if (x > 0x1.62e42ep6f) return std::numeric_limits<float>::infinity();
+    if (x < -0x1.9fe368p6f) return 0.0f;
+  }
+  volatile double xd = (double)x;
+  double z = InvLn2N * xd;
+  volatile double kdv = z + SHIFT;
+  double kd = kdv;
+  uint64_t ki;
+  std::memcpy(&ki, &kd, 8);
+  kd -= SHIFT;
+  double r = z - kd;
+  uint64_t t = T[ki % 32];
+  t += ki << (52 - 5);
+  double s;
+  std::memcpy(&s, &t, 8);
+  double y;
+  if (use_fma) {
+    double zz = std::fma(C0, r, C1);
+    double r2 = r * r;
+    y = std::fma(C2, r, 1.0);
+    y = std::fma(zz, r2, y);
+  } else {
+    double zz = C0 * r + C1;
+    double r2 = r * r;
+    y = C2 * r + 1;
+    y = zz * r2 + y;
+  }
+  y = y * s;
+  return (float)y;
+}
+
+// SURVEY 8(d) synthetic grid: 64-bit LCG, 13 draws per node in index order.
+void orc_lcg_fill_grid(void *h, float D, int blob)
+{
+  auto *S = (Oracle *)h;
+  uint64_t s = 0x9E3779B97F4A7C15ULL;
+  auto u01 = [&]() { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return (float)(s >> 40) / 16777216.0f; };
+  const int gs = S->gs;
+  for (size_t i = 0; i < S->N(); i++) {
+    float *c = &S->grid[i * CELL];
+    c[0] = D * (u01() - 0.25f);
+    c[1] = u01(); c[2] = u01(); c[3] = u01();
+    c[4] = 1.0f + 2.0f * u01();
+    for (int j = 5; j < CELL; j++) c[j] = u01() - 0.5f;
+    if (blob) {
+      int x = (int)(i % gs), y = (int)((i / gs) % gs), z = (int)(i / ((size_t)gs * gs));
+      float px = ((float)x + 0.5f) / (float)gs - 0.5f, py = ((float)y + 0.5f) / (float)gs - 0.5f, pz = ((float)z + 0.5f) / (float)gs - 0.5f;
+      c[0] *= expf(-(px * px + py * py + pz * pz) / (2.0f * 0.2f * 0.2f));
+    }
+  }
+}
+int orc_omp_threads(void) { return omp_get_max_threads(); }
+
+}  // extern "C"
