@@ -1,0 +1,158 @@
+/* lrf.h — C ABI of the B200-native LiteRF ray-march library (liblrf_b200.so).
+ *
+ * One entry point per member of the reference's tracer class on the hot path.  A reference
+ * maintainer binds these from a replacement example_tracer.{h,cpp} (shipped under
+ * literf-radiancefields_b200/host/example_tracer/) so that main.cpp compiles
+ * unmodified.  "ref:" cites the reference interface each function replaces, relative to the
+ * reference repository root.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on failure; lrf_last_error() gives the text.
+ *     (The reference has no error convention: all methods are void and failures are crashes.)
+ *   - There is NO CPU fallback: lrf_create fails if no CUDA device / sm_100 kernel image is usable.
+ *   - Grid host layout is the reference's: gs^3 cells x 13 floats, AoS, x fastest
+ *     (ref: example_tracer/example_tracer.h:25-32, example_tracer.cpp:62-65).
+ *   - Boxes are unit voxels of the (gs-1)^3 lattice, named by integer coordinates; the position
+ *     in the list is the box id (the octree EntityID used as tie-break, ref:
+ *     external/Octree/octree.h:856-860).  gs must be a power of two (every size the reference
+ *     uses: 16..128, main.cpp:49,125-133) so that box planes are exact in fp32.
+ *   - Matrices are 16 floats, column-major, ALREADY INVERTED on the host (the reference inverts in
+ *     its setters, example_tracer.h:214-215, with LiteMath::inverse4x4).
+ *   - Calls are synchronous unless the name ends in _async; a context is not re-entrant.
+ */
+#ifndef LRF_H
+#define LRF_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lrf_ctx lrf_ctx;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* ref: RayMarcherExample::RayMarcherExample(), example_tracer.h:43-49; CommitDeviceData() :223 */
+int lrf_create(int device, lrf_ctx **out);
+/* ref: ~RayMarcherExample (main.cpp:143) */
+int lrf_destroy(lrf_ctx *h);
+const char *lrf_last_error(void);
+/* stream-sync; ref: UpdateMembersPlainData(), example_tracer.h:224 (the natural sync point) */
+int lrf_sync(lrf_ctx *h);
+
+/* ---- grid / boxes ---------------------------------------------------------------------------- */
+/* ref: InitGrid(float), example_tracer.h:51-91 — density 0.01, other 12 floats 0.1, dense (gs-1)^3 boxes */
+int lrf_init_grid(lrf_ctx *h, int gs);
+/* ref: InitGrad(), example_tracer.h:93-96 (allocates; contents zero) */
+int lrf_init_grad(lrf_ctx *h);
+/* ref: zeroGrad(), example_tracer.h:104-109 */
+int lrf_zero_grad(lrf_ctx *h);
+/* ref: SetBoundingBox, example_tracer.h:98-102 (only bb.max.x-bb.min.x is used: example_tracer.cpp:649,692) */
+int lrf_set_bbox(lrf_ctx *h, const float mn[3], const float mx[3]);
+int lrf_grid_size(lrf_ctx *h);
+/* ref: public member `grid` (raw model.dat dump/load, main.cpp:54-56,139-141) */
+int lrf_grid_upload(lrf_ctx *h, const float *cells13);
+int lrf_grid_download(lrf_ctx *h, float *cells13);
+/* ref: public member `grid_d` */
+int lrf_grad_upload(lrf_ctx *h, const float *cells13);
+int lrf_grad_download(lrf_ctx *h, float *cells13);
+/* ref: public members V, S (example_tracer.h:248-249); which: 0 = V, 1 = S */
+int lrf_adam_state_upload(lrf_ctx *h, int which, const float *cells13);
+int lrf_adam_state_download(lrf_ctx *h, int which, float *cells13);
+/* ref: public member `boxes` (+ octree rebuild, example_tracer.h:87).  xyz = n x 3 lattice coords in id order.
+ * lrf_set_boxes_dense restores the InitGrid list. */
+int lrf_set_boxes(lrf_ctx *h, const int32_t *xyz, size_t n);
+int lrf_set_boxes_dense(lrf_ctx *h);
+/* ref: boxes.size() (main.cpp:136) */
+size_t lrf_box_count(lrf_ctx *h);
+int lrf_get_boxes(lrf_ctx *h, int32_t *xyz);
+
+/* ---- camera ---------------------------------------------------------------------------------- */
+/* ref: SetWorldViewMatrix / SetWorldViewMProjatrix, example_tracer.h:214-215 (members m_worldViewInv, m_worldViewProjInv) */
+int lrf_set_view_inv(lrf_ctx *h, const float m16[16]);
+int lrf_set_proj_inv(lrf_ctx *h, const float m16[16]);
+/* caller-side helpers, bit-identical restatements of the LiteMath routines main.cpp uses
+ * (main.cpp:78,99-102; LiteMath.h:1494-1499,1521-1529,1556-1569,1571-1653,1770-1815) for hosts
+ * that do not have LiteMath (the Python harness): */
+void lrf_cam_perspective(float fovy, float aspect, float zn, float zf, float out16[16]);
+void lrf_cam_orbit_view(int k, int n_views, float out16[16]);
+void lrf_mat4_inverse(const float in16[16], float out16[16]);
+void lrf_mat4_mul(const float a16[16], const float b16[16], float out16[16]);
+
+/* ---- forward --------------------------------------------------------------------------------- */
+/* ref: kernel2D_RayMarch(uint32_t*,uint32_t,uint32_t,bool), example_tracer.cpp:627-663.
+ * out = width*height packed pixels (R | G<<8 | B<<16 | A<<24, row 0 = bottom), HOST memory. */
+int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t width, uint32_t height, int greyscale);
+/* same, output left in DEVICE memory (out_dev), asynchronous on the context stream */
+int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t width, uint32_t height, int greyscale);
+/* parity taps (no reference counterpart; what RayIntersectedAll + RayGridIntersection compute per
+ * ray, example_tracer.cpp:641-651).  Host arrays, any may be NULL: n_hit[w*h], n_shaded[w*h],
+ * rgbtc[w*h*5] = {r,g,b,T,cauchy}, vox_xyz[w*h*keep*3] first `keep` hit voxels (-1 padded). */
+int lrf_render_debug(lrf_ctx *h, uint32_t width, uint32_t height, int greyscale, uint32_t *n_hit, uint32_t *n_shaded,
+                     float *rgbtc, int32_t *vox_xyz, uint32_t keep);
+/* packed rays (n x 3 origins, n x 3 directions, HOST memory): same taps */
+int lrf_trace_rays(lrf_ctx *h, size_t n, const float *o, const float *d, int greyscale, uint32_t *n_hit, uint32_t *n_shaded,
+                   float *rgbtc, int32_t *vox_xyz, uint32_t keep);
+
+/* ---- backward -------------------------------------------------------------------------------- */
+/* ref: kernel2D_RayMarchGrad(uint32_t,uint32_t,float4*,bool), example_tracer.cpp:665-718 (+ RayGridLossGrad
+ * :270-279, the Enzyme call).  ref_rgba = width*height float4 (stbi layout, alpha ignored), HOST memory;
+ * it is fully consumed before the call returns.  Accumulates (+=) into the gradient grid. */
+int lrf_render_grad(lrf_ctx *h, uint32_t width, uint32_t height, const float *ref_rgba_host, int greyscale);
+/* device-resident variant: ref image already in DEVICE memory, asynchronous */
+int lrf_render_grad_dev_async(lrf_ctx *h, uint32_t width, uint32_t height, const float *ref_rgba_dev, int greyscale);
+/* packed-ray batch (BASELINE config 3): n rays, o/d n x 3, ref n x 4, all DEVICE memory, asynchronous */
+int lrf_rays_grad_dev_async(lrf_ctx *h, size_t n, const float *o_dev, const float *d_dev, const float *ref_rgba_dev,
+                            int greyscale);
+/* host-memory convenience wrapper of the above (synchronous) */
+int lrf_rays_grad(lrf_ctx *h, size_t n, const float *o, const float *d, const float *ref_rgba, int greyscale);
+/* device-side ray generation for a batch of (view, pixel) picks: view_inv = n_views x 16 floats (DEVICE),
+ * picks = n x 2 uint32 {view, pixel index y*w+x} (DEVICE); writes o_dev/d_dev.  ref: example_tracer.cpp:635-639 */
+int lrf_gen_rays_dev_async(lrf_ctx *h, size_t n, const float *view_inv_dev, const uint32_t *picks_dev, uint32_t width,
+                           uint32_t height, float *o_dev, float *d_dev);
+
+/* ---- TV / optimiser -------------------------------------------------------------------------- */
+/* ref: kernel2D_TVGrad(), example_tracer.cpp:737-749 (+ TVRegularisationGrad :250-256) */
+int lrf_tv_grad(lrf_ctx *h);
+/* ref: optimizerInit(), example_tracer.h:111-126 */
+int lrf_adam_init(lrf_ctx *h);
+/* ref: optimizerStep(int) :128-163 (which = 0), optimizerStepDensity :165-183 (1), optimizerStepSH :185-206 (2) */
+int lrf_adam_step(lrf_ctx *h, int iter, int which);
+/* fused per-cell pass for training loops: TV gradient + Adam (all channels) + gradient zeroing for the
+ * next iteration in one call (same results as lrf_tv_grad; lrf_adam_step(iter,0); lrf_zero_grad).  Asynchronous. */
+int lrf_train_percell_async(lrf_ctx *h, int iter);
+int lrf_set_adam_hparams(lrf_ctx *h, float lr, float beta1, float beta2, float eps);
+
+/* ---- level transition ------------------------------------------------------------------------ */
+/* ref: UpsampleGrid(), example_tracer.cpp:281-323 */
+int lrf_upsample_grid(lrf_ctx *h);
+/* ref: UpsampleOctree(), example_tracer.cpp:325-447 */
+int lrf_upsample_boxes(lrf_ctx *h);
+/* ref: RebuildOctree(), example_tracer.cpp:449-489 */
+int lrf_rebuild_boxes(lrf_ctx *h);
+
+/* ---- plumbing -------------------------------------------------------------------------------- */
+/* ref: GetExecutionTime(const char*, float[4]), example_tracer.cpp:759-763.  name in {"RayMarch",
+ * "RayMarchGrad","TVGrad","Adam"}: out[0] = device ms of the last such call (CUDA events). */
+int lrf_last_time_ms(lrf_ctx *h, const char *name, float out[4]);
+/* device pointers of the parameter / gradient storage in DEVICE layout (density plane [gs^3] followed by
+ * colour plane [gs^3 x 12]) for NCCL all-reduce by the multi-GPU harness; n_floats = 13*gs^3 */
+float *lrf_param_device_ptr(lrf_ctx *h);
+float *lrf_grad_device_ptr(lrf_ctx *h);
+size_t lrf_param_count(lrf_ctx *h);
+void *lrf_stream(lrf_ctx *h);              /* cudaStream_t the context launches on */
+int lrf_use_stream(lrf_ctx *h, void *cuda_stream);   /* launch on the caller's stream (e.g. torch's current stream) */
+int lrf_device_alloc(lrf_ctx *h, size_t bytes, void **out_dev);
+int lrf_device_free(lrf_ctx *h, void *dev);
+int lrf_host_alloc_pinned(size_t bytes, void **out_host);
+int lrf_host_free_pinned(void *host);
+int lrf_memcpy_h2d_async(lrf_ctx *h, void *dst_dev, const void *src_host, size_t bytes);
+int lrf_memcpy_d2h_async(lrf_ctx *h, void *dst_host, const void *src_dev, size_t bytes);
+/* counters the benchmark reports: kernels launched by this context since creation; distinct nodes
+ * read by the last lrf_count_touched call */
+uint64_t lrf_launch_count(lrf_ctx *h);
+int lrf_count_touched_nodes(lrf_ctx *h, uint32_t width, uint32_t height, int greyscale, uint64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,705 @@
+// lrf_capi.cu — the C-ABI of include/lrf.h over the sm_100a kernels.  State that the reference keeps in
+// std::vector members of RayMarcherExample (example_tracer/example_tracer.h:232-251) lives in HBM here.
+//
+// HBM layout per context (N = gs^3):
+//   params / grad / adam V / adam S : 13*N floats each = [density plane N][colour plane N x 12]
+//   boxes                           : n_boxes x 3 int32 lattice coordinates, id order
+//   occ, vox2id (sparse sets only)  : bitmap and id table over the (gs-1)^3 voxel lattice
+#include "../../include/lrf.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lrf_kernels.cuh"
+
+using namespace lrf;
+
+struct lrf_ctx
+{
+  int device = 0;
+  int gs = 0;
+  size_t N = 0;
+  float *params = nullptr, *grad = nullptr, *V = nullptr, *S = nullptr;
+  float *tv_tmp = nullptr;            // 2*N floats
+  int32_t *boxes = nullptr;           // device, n_boxes*3 (null while dense)
+  uint32_t *occ = nullptr, *vox2id = nullptr;
+  size_t n_boxes = 0;
+  bool dense = true;
+  float bb_min[3] = {0, 0, 0}, bb_max[3] = {1, 1, 1};
+  float view_inv[16], proj_inv[16];
+  float lr = 0.15f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8;   // example_tracer.h:120-123
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float t_march = 0, t_grad = 0, t_tv = 0, t_adam = 0;
+  uint64_t launches = 0;
+  // staging
+  void *stage = nullptr;
+  size_t stage_bytes = 0;
+};
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+  } while (0)
+#define NEED(h) do { if (!(h)) return fail("null context"); CK(cudaSetDevice((h)->device)); } while (0)
+#define NEED_GRID(h) do { NEED(h); if (!(h)->params) return fail("grid not initialised (call lrf_init_grid)"); } while (0)
+
+static int ensure_stage(lrf_ctx *h, size_t bytes)
+{
+  if (h->stage_bytes >= bytes) return 0;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr; h->stage_bytes = 0;
+  CK(cudaMalloc(&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return 0;
+}
+
+static SceneDev scene_of(const lrf_ctx *h)
+{
+  SceneDev S{};
+  S.gs = h->gs;
+  S.n = h->gs - 1;
+  S.dens = h->params;
+  S.col = reinterpret_cast<const float4 *>(h->params + h->N);
+  S.gdens = h->grad;
+  S.gcol = h->grad ? reinterpret_cast<float4 *>(h->grad + h->N) : nullptr;
+  S.occ = h->dense ? nullptr : h->occ;
+  S.vox2id = h->dense ? nullptr : h->vox2id;
+  S.gs_f = (float)h->gs;
+  S.inv_gs_f = 1.0f / (float)h->gs;
+  S.inv_gs = 1.0 / (double)h->gs;
+  const float step_f = (h->bb_max[0] - h->bb_min[0]) / (float)h->gs;   // example_tracer.cpp:649 (float), :692 (same value widened)
+  S.step = (double)step_f;
+  const double gate = std::sqrt(3.0) * S.step;                          // :145
+  float gf = (float)gate;
+  if ((double)gf > gate) gf = std::nextafterf(gf, -INFINITY);           // largest float <= gate:  a > gate  <=>  a > gf  for float a
+  S.step_gate_f = gf;
+  std::memcpy(S.view_inv, h->view_inv, 64);
+  std::memcpy(S.proj_inv, h->proj_inv, 64);
+  return S;
+}
+
+static void free_grid(lrf_ctx *h)
+{
+  cudaFree(h->params); cudaFree(h->grad); cudaFree(h->V); cudaFree(h->S); cudaFree(h->tv_tmp);
+  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id);
+  h->params = h->grad = h->V = h->S = h->tv_tmp = nullptr;
+  h->boxes = nullptr; h->occ = h->vox2id = nullptr;
+}
+
+static int alloc_grid(lrf_ctx *h, int gs)
+{
+  free_grid(h);
+  h->gs = gs;
+  h->N = (size_t)gs * gs * gs;
+  const size_t bytes = h->N * kCell * sizeof(float);
+  CK(cudaMalloc(&h->params, bytes));
+  CK(cudaMalloc(&h->grad, bytes));
+  CK(cudaMalloc(&h->V, bytes));
+  CK(cudaMalloc(&h->S, bytes));
+  CK(cudaMemsetAsync(h->grad, 0, bytes, h->stream));
+  CK(cudaMemsetAsync(h->V, 0, bytes, h->stream));
+  CK(cudaMemsetAsync(h->S, 0, bytes, h->stream));
+  h->dense = true;
+  h->n_boxes = (size_t)(gs - 1) * (gs - 1) * (gs - 1);
+  return 0;
+}
+
+extern "C" {
+
+const char *lrf_last_error(void) { return g_err.c_str(); }
+
+int lrf_create(int device, lrf_ctx **out)
+{
+  if (!out) return fail("null out");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+  if (device < 0 || device >= count) return fail("device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; this build carries sm_100a code only");
+  lrf_ctx *h = new lrf_ctx();
+  h->device = device;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  // defaults of the reference constructor (example_tracer.h:43-49): caller overrides through the setters
+  for (int i = 0; i < 16; i++) h->view_inv[i] = h->proj_inv[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  *out = h;
+  return 0;
+}
+
+int lrf_destroy(lrf_ctx *h)
+{
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_grid(h);
+  cudaFree(h->stage);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int lrf_sync(lrf_ctx *h) { NEED(h); CK(cudaStreamSynchronize(h->stream)); return 0; }
+
+int lrf_init_grid(lrf_ctx *h, int gs)
+{
+  NEED(h);
+  if (gs < 2 || gs > 1024 || (gs & (gs - 1))) return fail("gridSize must be a power of two in [2, 1024]");
+  if (alloc_grid(h, gs)) return 1;
+  launch_fill(h->params, h->N, 0.01f, h->stream);               // density  (example_tracer.h:65)
+  launch_fill(h->params + h->N, h->N * 12, 0.1f, h->stream);    // RGB + SH (example_tracer.h:66-67)
+  h->launches += 2;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int lrf_init_grad(lrf_ctx *h) { return lrf_zero_grad(h); }   // resize() value-initialises in the reference
+
+int lrf_zero_grad(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  launch_fill(h->grad, h->N * kCell, 0.0f, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int lrf_set_bbox(lrf_ctx *h, const float mn[3], const float mx[3])
+{
+  NEED(h);
+  for (int a = 0; a < 3; a++) { h->bb_min[a] = mn[a]; h->bb_max[a] = mx[a]; }
+  return 0;
+}
+int lrf_grid_size(lrf_ctx *h) { return h ? h->gs : 0; }
+
+static int upload13(lrf_ctx *h, float *dst_planes, const float *src_host)
+{
+  NEED_GRID(h);
+  const size_t bytes = h->N * kCell * sizeof(float);
+  if (ensure_stage(h, bytes)) return 1;
+  CK(cudaMemcpyAsync(h->stage, src_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  launch_aos_to_planes((const float *)h->stage, dst_planes, h->N, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+static int download13(lrf_ctx *h, const float *src_planes, float *dst_host)
+{
+  NEED_GRID(h);
+  const size_t bytes = h->N * kCell * sizeof(float);
+  if (ensure_stage(h, bytes)) return 1;
+  launch_planes_to_aos(src_planes, (float *)h->stage, h->N, h->stream);
+  h->launches++;
+  CK(cudaMemcpyAsync(dst_host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int lrf_grid_upload(lrf_ctx *h, const float *c) { return h ? upload13(h, h->params, c) : fail("null context"); }
+int lrf_grid_download(lrf_ctx *h, float *c) { return h ? download13(h, h->params, c) : fail("null context"); }
+int lrf_grad_upload(lrf_ctx *h, const float *c) { return h ? upload13(h, h->grad, c) : fail("null context"); }
+int lrf_grad_download(lrf_ctx *h, float *c) { return h ? download13(h, h->grad, c) : fail("null context"); }
+int lrf_adam_state_upload(lrf_ctx *h, int which, const float *c) { return h ? upload13(h, which ? h->S : h->V, c) : fail("null context"); }
+int lrf_adam_state_download(lrf_ctx *h, int which, float *c) { return h ? download13(h, which ? h->S : h->V, c) : fail("null context"); }
+
+static int install_boxes_dev(lrf_ctx *h, int32_t *xyz_dev, size_t n)  // takes ownership of xyz_dev
+{
+  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id);
+  h->boxes = xyz_dev;
+  h->occ = h->vox2id = nullptr;
+  h->n_boxes = n;
+  h->dense = false;
+  const size_t nv = (size_t)(h->gs - 1) * (h->gs - 1) * (h->gs - 1);
+  const size_t words = (nv + 31) / 32 + 1;
+  CK(cudaMalloc(&h->occ, words * 4));
+  CK(cudaMalloc(&h->vox2id, (nv + 1) * 4));
+  CK(cudaMemsetAsync(h->occ, 0, words * 4, h->stream));
+  CK(cudaMemsetAsync(h->vox2id, 0, (nv + 1) * 4, h->stream));
+  launch_build_box_maps(h->gs - 1, h->boxes, n, h->occ, h->vox2id, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int lrf_set_boxes(lrf_ctx *h, const int32_t *xyz, size_t n)
+{
+  NEED_GRID(h);
+  const int nv = h->gs - 1;
+  for (size_t i = 0; i < 3 * n; i++)
+    if (xyz[i] < 0 || xyz[i] >= nv) return fail("box coordinate outside the (gs-1)^3 lattice");
+  int32_t *dev = nullptr;
+  CK(cudaMalloc(&dev, (n ? n : 1) * 3 * sizeof(int32_t)));
+  if (n) CK(cudaMemcpyAsync(dev, xyz, n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  return install_boxes_dev(h, dev, n);
+}
+int lrf_set_boxes_dense(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id);
+  h->boxes = nullptr; h->occ = h->vox2id = nullptr;
+  h->dense = true;
+  h->n_boxes = (size_t)(h->gs - 1) * (h->gs - 1) * (h->gs - 1);
+  return 0;
+}
+size_t lrf_box_count(lrf_ctx *h) { return h ? h->n_boxes : 0; }
+int lrf_get_boxes(lrf_ctx *h, int32_t *xyz)
+{
+  NEED_GRID(h);
+  if (h->dense) {
+    const int n = h->gs - 1;
+    size_t i = 0;
+    for (int z = 0; z < n; z++)
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++, i++) { xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z; }   // id = x + y(gs-1) + z(gs-1)^2, example_tracer.h:77
+    return 0;
+  }
+  if (h->n_boxes) CK(cudaMemcpyAsync(xyz, h->boxes, h->n_boxes * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int lrf_set_view_inv(lrf_ctx *h, const float m[16]) { NEED(h); std::memcpy(h->view_inv, m, 64); return 0; }
+int lrf_set_proj_inv(lrf_ctx *h, const float m[16]) { NEED(h); std::memcpy(h->proj_inv, m, 64); return 0; }
+
+// ---- forward ----
+int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt, int grey)
+{
+  NEED_GRID(h);
+  if (w == 0 || hgt == 0) return 0;
+  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t w, uint32_t hgt, int grey)
+{
+  NEED_GRID(h);
+  if (w == 0 || hgt == 0) return 0;
+  const size_t bytes = (size_t)w * hgt * 4;
+  if (ensure_stage(h, bytes)) return 1;
+  cudaEventRecord(h->ev0, h->stream);
+  if (lrf_render_dev_async(h, (uint32_t *)h->stage, w, hgt, grey)) return 1;
+  cudaEventRecord(h->ev1, h->stream);
+  CK(cudaMemcpyAsync(out_host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->t_march, h->ev0, h->ev1);
+  return 0;
+}
+
+static int run_debug(lrf_ctx *h, bool image, uint32_t w, uint32_t hgt, size_t n, const float *o, const float *d, int grey, uint32_t *n_hit,
+                     uint32_t *n_shaded, float *rgbtc, int32_t *vox, uint32_t keep, uint8_t *touched_dev)
+{
+  const size_t rays = image ? (size_t)w * hgt : n;
+  if (rays == 0) return 0;
+  // staging layout: [o | d | n_hit | n_shaded | rgbtc | vox]
+  const size_t b_o = image ? 0 : rays * 12, b_nh = rays * 4, b_rg = rays * 20, b_vx = vox ? rays * keep * 12 : 0;
+  const size_t total = 2 * b_o + 2 * b_nh + b_rg + b_vx + 256;
+  if (ensure_stage(h, total)) return 1;
+  char *base = (char *)h->stage;
+  float *o_dev = (float *)base, *d_dev = (float *)(base + b_o);
+  DebugTaps taps{};
+  taps.n_hit = (uint32_t *)(base + 2 * b_o);
+  taps.n_shaded = (uint32_t *)(base + 2 * b_o + b_nh);
+  taps.rgbtc = (float *)(base + 2 * b_o + 2 * b_nh);
+  taps.vox_xyz = vox ? (int32_t *)(base + 2 * b_o + 2 * b_nh + b_rg) : nullptr;
+  taps.keep = vox ? keep : 0;
+  taps.touched = touched_dev;
+  if (!image) {
+    CK(cudaMemcpyAsync(o_dev, o, b_o, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_dev, d, b_o, cudaMemcpyHostToDevice, h->stream));
+    launch_debug_rays(scene_of(h), rays, o_dev, d_dev, grey, taps, h->stream);
+  } else launch_debug_image(scene_of(h), w, hgt, grey, taps, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (n_hit) CK(cudaMemcpyAsync(n_hit, taps.n_hit, b_nh, cudaMemcpyDeviceToHost, h->stream));
+  if (n_shaded) CK(cudaMemcpyAsync(n_shaded, taps.n_shaded, b_nh, cudaMemcpyDeviceToHost, h->stream));
+  if (rgbtc) CK(cudaMemcpyAsync(rgbtc, taps.rgbtc, b_rg, cudaMemcpyDeviceToHost, h->stream));
+  if (vox) CK(cudaMemcpyAsync(vox, taps.vox_xyz, b_vx, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int lrf_render_debug(lrf_ctx *h, uint32_t w, uint32_t hgt, int grey, uint32_t *n_hit, uint32_t *n_shaded, float *rgbtc, int32_t *vox, uint32_t keep)
+{
+  NEED_GRID(h);
+  return run_debug(h, true, w, hgt, 0, nullptr, nullptr, grey, n_hit, n_shaded, rgbtc, vox, keep, nullptr);
+}
+int lrf_trace_rays(lrf_ctx *h, size_t n, const float *o, const float *d, int grey, uint32_t *n_hit, uint32_t *n_shaded, float *rgbtc, int32_t *vox,
+                   uint32_t keep)
+{
+  NEED_GRID(h);
+  return run_debug(h, false, 0, 0, n, o, d, grey, n_hit, n_shaded, rgbtc, vox, keep, nullptr);
+}
+int lrf_count_touched_nodes(lrf_ctx *h, uint32_t w, uint32_t hgt, int grey, uint64_t *out)
+{
+  NEED_GRID(h);
+  uint8_t *marks = nullptr;
+  unsigned long long *cnt = nullptr;
+  CK(cudaMalloc(&marks, h->N));
+  CK(cudaMalloc(&cnt, 8));
+  CK(cudaMemsetAsync(marks, 0, h->N, h->stream));
+  CK(cudaMemsetAsync(cnt, 0, 8, h->stream));
+  int rc = run_debug(h, true, w, hgt, 0, nullptr, nullptr, grey, nullptr, nullptr, nullptr, nullptr, 0, marks);
+  if (!rc) {
+    launch_count_nonzero(marks, h->N, cnt, h->stream);
+    h->launches++;
+    unsigned long long v = 0;
+    cudaMemcpyAsync(&v, cnt, 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    *out = v;
+  }
+  cudaFree(marks); cudaFree(cnt);
+  return rc;
+}
+
+// ---- backward ----
+int lrf_render_grad_dev_async(lrf_ctx *h, uint32_t w, uint32_t hgt, const float *ref_dev, int grey)
+{
+  NEED_GRID(h);
+  if (w == 0 || hgt == 0) return 0;
+  launch_grad_image(scene_of(h), w, hgt, ref_dev, grey, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int lrf_render_grad(lrf_ctx *h, uint32_t w, uint32_t hgt, const float *ref_host, int grey)
+{
+  NEED_GRID(h);
+  if (w == 0 || hgt == 0) return 0;
+  const size_t bytes = (size_t)w * hgt * 16;
+  if (ensure_stage(h, bytes)) return 1;
+  CK(cudaMemcpyAsync(h->stage, ref_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  cudaEventRecord(h->ev0, h->stream);
+  if (lrf_render_grad_dev_async(h, w, hgt, (const float *)h->stage, grey)) return 1;
+  cudaEventRecord(h->ev1, h->stream);
+  CK(cudaStreamSynchronize(h->stream));   // ref buffer is caller-owned and freed right after L1Loss (main.cpp:118)
+  cudaEventElapsedTime(&h->t_grad, h->ev0, h->ev1);
+  return 0;
+}
+int lrf_rays_grad_dev_async(lrf_ctx *h, size_t n, const float *o, const float *d, const float *ref, int grey)
+{
+  NEED_GRID(h);
+  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int lrf_rays_grad(lrf_ctx *h, size_t n, const float *o, const float *d, const float *ref, int grey)
+{
+  NEED_GRID(h);
+  if (n == 0) return 0;
+  if (ensure_stage(h, n * 40 + 64)) return 1;
+  float *o_dev = (float *)h->stage, *d_dev = o_dev + 3 * n, *r_dev = d_dev + 3 * n;
+  // keep the float4 ref 16-byte aligned
+  r_dev = (float *)(((uintptr_t)r_dev + 15) & ~(uintptr_t)15);
+  CK(cudaMemcpyAsync(o_dev, o, n * 12, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_dev, d, n * 12, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(r_dev, ref, n * 16, cudaMemcpyHostToDevice, h->stream));
+  if (lrf_rays_grad_dev_async(h, n, o_dev, d_dev, r_dev, grey)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int lrf_gen_rays_dev_async(lrf_ctx *h, size_t n, const float *view_inv_dev, const uint32_t *picks_dev, uint32_t w, uint32_t hgt, float *o_dev,
+                           float *d_dev)
+{
+  NEED(h);
+  launch_gen_rays(h->proj_inv, n, view_inv_dev, picks_dev, w, hgt, o_dev, d_dev, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- TV / Adam ----
+static int ensure_tv_tmp(lrf_ctx *h)
+{
+  if (!h->tv_tmp) CK(cudaMalloc(&h->tv_tmp, 2 * h->N * sizeof(float)));
+  return 0;
+}
+int lrf_tv_grad(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  if (ensure_tv_tmp(h)) return 1;
+  cudaEventRecord(h->ev0, h->stream);
+  launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
+  h->launches += 3;
+  cudaEventRecord(h->ev1, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->t_tv, h->ev0, h->ev1);
+  return 0;
+}
+int lrf_adam_init(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  h->lr = 0.15f; h->beta1 = 0.9f; h->beta2 = 0.999f; h->eps = 1e-8;
+  const size_t bytes = h->N * kCell * sizeof(float);
+  CK(cudaMemsetAsync(h->V, 0, bytes, h->stream));
+  CK(cudaMemsetAsync(h->S, 0, bytes, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int lrf_set_adam_hparams(lrf_ctx *h, float lr, float b1, float b2, float eps)
+{
+  NEED(h);
+  h->lr = lr; h->beta1 = b1; h->beta2 = b2; h->eps = eps;
+  return 0;
+}
+static void adam_launch(lrf_ctx *h, int iter, int which, int zero)
+{
+  const double b1 = std::pow(h->beta1, iter + 1), b2 = std::pow(h->beta2, iter + 1);   // example_tracer.h:152-153 (double)
+  size_t off = 0, count = h->N * kCell;
+  if (which == 1) count = h->N;                            // density plane
+  else if (which == 2) { off = h->N; count = h->N * 12; }  // everything but density (i % CellSize != 0)
+  launch_adam(h->params, h->grad, h->V, h->S, off, count, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, zero, h->stream);
+  h->launches++;
+}
+int lrf_adam_step(lrf_ctx *h, int iter, int which)
+{
+  NEED_GRID(h);
+  if (which < 0 || which > 2) return fail("which must be 0 (all), 1 (density) or 2 (SH/RGB)");
+  cudaEventRecord(h->ev0, h->stream);
+  adam_launch(h, iter, which, 0);
+  cudaEventRecord(h->ev1, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->t_adam, h->ev0, h->ev1);
+  return 0;
+}
+int lrf_train_percell_async(lrf_ctx *h, int iter)
+{
+  NEED_GRID(h);
+  if (ensure_tv_tmp(h)) return 1;
+  launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
+  h->launches += 3;
+  adam_launch(h, iter, 0, 1);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- level transition ----
+int lrf_upsample_grid(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  if (h->gs * 2 > 1024) return fail("upsampled grid would exceed 1024^3");
+  const int old_gs = h->gs;
+  float *old_params = h->params;
+  const bool was_dense = h->dense;
+  int32_t *old_boxes = h->boxes;
+  const size_t old_nb = h->n_boxes;
+  // detach what must survive alloc_grid
+  h->params = nullptr; h->boxes = nullptr;
+  if (alloc_grid(h, old_gs * 2)) { cudaFree(old_params); cudaFree(old_boxes); return 1; }
+  launch_upsample_grid(old_gs, old_params, h->params, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(old_params);
+  // The reference's UpsampleGrid leaves `boxes` untouched (old-level boxes, twice the voxel size) until
+  // UpsampleOctree runs; rendering in between is not meaningful there either.  Keep the old list for
+  // lrf_upsample_boxes and mark the set as pending.
+  if (was_dense) {
+    // materialise the dense old-level list so that lrf_upsample_boxes can subdivide it
+    const int n = old_gs - 1;
+    std::vector<int32_t> xyz((size_t)n * n * n * 3);
+    size_t i = 0;
+    for (int z = 0; z < n; z++)
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++, i++) { xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z; }
+    CK(cudaMalloc(&h->boxes, (xyz.size() ? xyz.size() : 3) * sizeof(int32_t)));
+    CK(cudaMemcpy(h->boxes, xyz.data(), xyz.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->n_boxes = (size_t)n * n * n;
+  } else { h->boxes = old_boxes; h->n_boxes = old_nb; }
+  h->dense = false;  // old-level boxes: maps are rebuilt by lrf_upsample_boxes
+  return 0;
+}
+
+static int compact_boxes(lrf_ctx *h, bool children)
+{
+  const size_t n_old = h->n_boxes, n_flags = children ? n_old * 8 : n_old;
+  if (n_flags == 0) { int32_t *e = nullptr; CK(cudaMalloc(&e, 12)); return install_boxes_dev(h, e, 0); }
+  uint32_t *flags = nullptr, *offs = nullptr, *tmp = nullptr;
+  CK(cudaMalloc(&flags, n_flags * 4));
+  CK(cudaMalloc(&offs, n_flags * 4));
+  CK(cudaMalloc(&tmp, scan_tmp_elems(n_flags) * 4));
+  const SceneDev S = scene_of(h);
+  if (children) launch_box_child_flags(S, h->boxes, n_old, flags, h->stream);
+  else launch_box_keep_flags(S, h->boxes, n_old, flags, h->stream);
+  launch_exclusive_scan(flags, offs, n_flags, tmp, h->stream);
+  h->launches += 4;
+  uint32_t last_off = 0, last_flag = 0;
+  CK(cudaMemcpyAsync(&last_off, offs + n_flags - 1, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&last_flag, flags + n_flags - 1, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t n_new = (size_t)last_off + last_flag;
+  int32_t *nb = nullptr;
+  CK(cudaMalloc(&nb, (n_new ? n_new : 1) * 3 * sizeof(int32_t)));
+  if (children) launch_box_compact_children(h->boxes, n_old, flags, offs, nb, h->stream);
+  else launch_box_compact(h->boxes, n_old, flags, offs, nb, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(flags); cudaFree(offs); cudaFree(tmp);
+  return install_boxes_dev(h, nb, n_new);
+}
+int lrf_upsample_boxes(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  if (h->dense) return fail("lrf_upsample_boxes must follow lrf_upsample_grid (main.cpp:128-131)");
+  return compact_boxes(h, true);
+}
+int lrf_rebuild_boxes(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  if (h->dense) {
+    std::vector<int32_t> xyz(h->n_boxes * 3);
+    if (lrf_get_boxes(h, xyz.data())) return 1;
+    if (lrf_set_boxes(h, xyz.data(), h->n_boxes)) return 1;
+  }
+  return compact_boxes(h, false);
+}
+
+// ---- plumbing ----
+int lrf_last_time_ms(lrf_ctx *h, const char *name, float out[4])
+{
+  NEED(h);
+  const std::string s(name ? name : "");
+  if (s == "RayMarch") out[0] = h->t_march;
+  else if (s == "RayMarchGrad") out[0] = h->t_grad;
+  else if (s == "TVGrad") out[0] = h->t_tv;
+  else if (s == "Adam") out[0] = h->t_adam;
+  else return fail("unknown timer name");
+  return 0;
+}
+float *lrf_param_device_ptr(lrf_ctx *h) { return h ? h->params : nullptr; }
+float *lrf_grad_device_ptr(lrf_ctx *h) { return h ? h->grad : nullptr; }
+size_t lrf_param_count(lrf_ctx *h) { return h ? h->N * kCell : 0; }
+void *lrf_stream(lrf_ctx *h) { return h ? (void *)h->stream : nullptr; }
+int lrf_use_stream(lrf_ctx *h, void *s)
+{
+  NEED(h);
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)s;
+  h->own_stream = false;
+  return 0;
+}
+int lrf_device_alloc(lrf_ctx *h, size_t bytes, void **out) { NEED(h); CK(cudaMalloc(out, bytes)); return 0; }
+int lrf_device_free(lrf_ctx *h, void *p) { NEED(h); CK(cudaFree(p)); return 0; }
+int lrf_host_alloc_pinned(size_t bytes, void **out) { CK(cudaMallocHost(out, bytes)); return 0; }
+int lrf_host_free_pinned(void *p) { CK(cudaFreeHost(p)); return 0; }
+int lrf_memcpy_h2d_async(lrf_ctx *h, void *dst, const void *src, size_t bytes) { NEED(h); CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream)); return 0; }
+int lrf_memcpy_d2h_async(lrf_ctx *h, void *dst, const void *src, size_t bytes) { NEED(h); CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream)); return 0; }
+uint64_t lrf_launch_count(lrf_ctx *h) { return h ? h->launches : 0; }
+
+// ---- caller-side camera helpers (host arithmetic, compiled without FMA contraction) ----
+static void hm_mul_vec(float *res, const float *B, const float *V)   // LiteMath.h:1362-1368
+{
+  res[0] = V[0] * B[0] + V[1] * B[4] + V[2] * B[8] + V[3] * B[12];
+  res[1] = V[0] * B[1] + V[1] * B[5] + V[2] * B[9] + V[3] * B[13];
+  res[2] = V[0] * B[2] + V[1] * B[6] + V[2] * B[10] + V[3] * B[14];
+  res[3] = V[0] * B[3] + V[1] * B[7] + V[2] * B[11] + V[3] * B[15];
+}
+void lrf_mat4_mul(const float a[16], const float b[16], float out[16])   // LiteMath.h:1556-1569
+{
+  float tmp[16];
+  for (int c = 0; c < 4; c++) hm_mul_vec(tmp + 4 * c, a, b + 4 * c);
+  std::memcpy(out, tmp, sizeof(tmp));
+}
+void lrf_cam_perspective(float fovy, float aspect, float zNear, float zFar, float out[16])   // LiteMath.h:1797-1815
+{
+  const float ymax = zNear * tanf(fovy * 3.14159265358979323846f / 360.0f);
+  const float xmax = ymax * aspect;
+  const float left = -xmax, right = +xmax, bottom = -ymax, top = +ymax;
+  const float temp = 2.0f * zNear, temp2 = right - left, temp3 = top - bottom, temp4 = zFar - zNear;
+  const float m[16] = {temp / temp2, 0.0f, 0.0f, 0.0f, 0.0f, temp / temp3, 0.0f, 0.0f,
+                       (right + left) / temp2, (top + bottom) / temp3, (-zFar - zNear) / temp4, (float)-1.0,
+                       0.0f, 0.0f, (-temp * zFar) / temp4, 0.0f};
+  std::memcpy(out, m, sizeof(m));
+}
+static void hm_normalize3(float *v)
+{
+  const float len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const float inv = float(1) / len;
+  v[0] = v[0] * inv; v[1] = v[1] * inv; v[2] = v[2] * inv;
+}
+static void hm_cross(const float *a, const float *b, float *r)   // LiteMath.h:829-834
+{
+  const float t0 = a[0] * b[1] - a[1] * b[0], t1 = a[1] * b[2] - a[2] * b[1], t2 = a[2] * b[0] - a[0] * b[2];
+  r[0] = t1; r[1] = t2; r[2] = t0;
+}
+void lrf_cam_orbit_view(int k, int n_views, float out[16])   // main.cpp:99-102
+{
+  const float eye[3] = {0.0f, 0.0f, 1.3f}, up[3] = {0.0f, 1.0f, 0.0f};
+  float x[3], y[3], z[3] = {eye[0] - 0.0f, eye[1] - 0.0f, eye[2] - 0.0f};   // lookAt LiteMath.h:1770-1795
+  hm_normalize3(z);
+  hm_cross(up, z, x);
+  hm_cross(z, x, y);
+  hm_normalize3(x);
+  hm_normalize3(y);
+  const float la[16] = {x[0], y[0], z[0], 0.0f, x[1], y[1], z[1], 0.0f, x[2], y[2], z[2], 0.0f,
+                        -x[0] * eye[0] - x[1] * eye[1] - x[2] * eye[2], -y[0] * eye[0] - y[1] * eye[1] - y[2] * eye[2],
+                        -z[0] * eye[0] - z[1] * eye[1] - z[2] * eye[2], 1.0f};
+  const float DEG_TO_RAD = float(3.14159265358979323846f) / 180.0f;
+  const float phi = -float(360.0 / n_views * k) * DEG_TO_RAD;
+  const float rot[16] = {+cosf(phi), 0.0f, -sinf(phi), 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, +sinf(phi), 0.0f, +cosf(phi), 0.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+  const float tr[16] = {1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, -0.5f, -0.5f, -0.5f, 1.0f};
+  float tmp[16];
+  lrf_mat4_mul(la, rot, tmp);
+  lrf_mat4_mul(tmp, tr, out);
+}
+#define HM(m, r, c) (m)[(c) * 4 + (r)]
+void lrf_mat4_inverse(const float m1[16], float out[16])   // LiteMath.h:1571-1653 (cofactor expansion, same operation order)
+{
+  float t[12], m[16];
+  t[0] = HM(m1, 2, 2) * HM(m1, 3, 3); t[1] = HM(m1, 2, 3) * HM(m1, 3, 2); t[2] = HM(m1, 2, 1) * HM(m1, 3, 3);
+  t[3] = HM(m1, 2, 3) * HM(m1, 3, 1); t[4] = HM(m1, 2, 1) * HM(m1, 3, 2); t[5] = HM(m1, 2, 2) * HM(m1, 3, 1);
+  t[6] = HM(m1, 2, 0) * HM(m1, 3, 3); t[7] = HM(m1, 2, 3) * HM(m1, 3, 0); t[8] = HM(m1, 2, 0) * HM(m1, 3, 2);
+  t[9] = HM(m1, 2, 2) * HM(m1, 3, 0); t[10] = HM(m1, 2, 0) * HM(m1, 3, 1); t[11] = HM(m1, 2, 1) * HM(m1, 3, 0);
+  HM(m, 0, 0) = t[0] * HM(m1, 1, 1) + t[3] * HM(m1, 1, 2) + t[4] * HM(m1, 1, 3);
+  HM(m, 0, 0) -= t[1] * HM(m1, 1, 1) + t[2] * HM(m1, 1, 2) + t[5] * HM(m1, 1, 3);
+  HM(m, 1, 0) = t[1] * HM(m1, 1, 0) + t[6] * HM(m1, 1, 2) + t[9] * HM(m1, 1, 3);
+  HM(m, 1, 0) -= t[0] * HM(m1, 1, 0) + t[7] * HM(m1, 1, 2) + t[8] * HM(m1, 1, 3);
+  HM(m, 2, 0) = t[2] * HM(m1, 1, 0) + t[7] * HM(m1, 1, 1) + t[10] * HM(m1, 1, 3);
+  HM(m, 2, 0) -= t[3] * HM(m1, 1, 0) + t[6] * HM(m1, 1, 1) + t[11] * HM(m1, 1, 3);
+  HM(m, 3, 0) = t[5] * HM(m1, 1, 0) + t[8] * HM(m1, 1, 1) + t[11] * HM(m1, 1, 2);
+  HM(m, 3, 0) -= t[4] * HM(m1, 1, 0) + t[9] * HM(m1, 1, 1) + t[10] * HM(m1, 1, 2);
+  HM(m, 0, 1) = t[1] * HM(m1, 0, 1) + t[2] * HM(m1, 0, 2) + t[5] * HM(m1, 0, 3);
+  HM(m, 0, 1) -= t[0] * HM(m1, 0, 1) + t[3] * HM(m1, 0, 2) + t[4] * HM(m1, 0, 3);
+  HM(m, 1, 1) = t[0] * HM(m1, 0, 0) + t[7] * HM(m1, 0, 2) + t[8] * HM(m1, 0, 3);
+  HM(m, 1, 1) -= t[1] * HM(m1, 0, 0) + t[6] * HM(m1, 0, 2) + t[9] * HM(m1, 0, 3);
+  HM(m, 2, 1) = t[3] * HM(m1, 0, 0) + t[6] * HM(m1, 0, 1) + t[11] * HM(m1, 0, 3);
+  HM(m, 2, 1) -= t[2] * HM(m1, 0, 0) + t[7] * HM(m1, 0, 1) + t[10] * HM(m1, 0, 3);
+  HM(m, 3, 1) = t[4] * HM(m1, 0, 0) + t[9] * HM(m1, 0, 1) + t[10] * HM(m1, 0, 2);
+  HM(m, 3, 1) -= t[5] * HM(m1, 0, 0) + t[8] * HM(m1, 0, 1) + t[11] * HM(m1, 0, 2);
+  t[0] = HM(m1, 0, 2) * HM(m1, 1, 3); t[1] = HM(m1, 0, 3) * HM(m1, 1, 2); t[2] = HM(m1, 0, 1) * HM(m1, 1, 3);
+  t[3] = HM(m1, 0, 3) * HM(m1, 1, 1); t[4] = HM(m1, 0, 1) * HM(m1, 1, 2); t[5] = HM(m1, 0, 2) * HM(m1, 1, 1);
+  t[6] = HM(m1, 0, 0) * HM(m1, 1, 3); t[7] = HM(m1, 0, 3) * HM(m1, 1, 0); t[8] = HM(m1, 0, 0) * HM(m1, 1, 2);
+  t[9] = HM(m1, 0, 2) * HM(m1, 1, 0); t[10] = HM(m1, 0, 0) * HM(m1, 1, 1); t[11] = HM(m1, 0, 1) * HM(m1, 1, 0);
+  HM(m, 0, 2) = t[0] * HM(m1, 3, 1) + t[3] * HM(m1, 3, 2) + t[4] * HM(m1, 3, 3);
+  HM(m, 0, 2) -= t[1] * HM(m1, 3, 1) + t[2] * HM(m1, 3, 2) + t[5] * HM(m1, 3, 3);
+  HM(m, 1, 2) = t[1] * HM(m1, 3, 0) + t[6] * HM(m1, 3, 2) + t[9] * HM(m1, 3, 3);
+  HM(m, 1, 2) -= t[0] * HM(m1, 3, 0) + t[7] * HM(m1, 3, 2) + t[8] * HM(m1, 3, 3);
+  HM(m, 2, 2) = t[2] * HM(m1, 3, 0) + t[7] * HM(m1, 3, 1) + t[10] * HM(m1, 3, 3);
+  HM(m, 2, 2) -= t[3] * HM(m1, 3, 0) + t[6] * HM(m1, 3, 1) + t[11] * HM(m1, 3, 3);
+  HM(m, 3, 2) = t[5] * HM(m1, 3, 0) + t[8] * HM(m1, 3, 1) + t[11] * HM(m1, 3, 2);
+  HM(m, 3, 2) -= t[4] * HM(m1, 3, 0) + t[9] * HM(m1, 3, 1) + t[10] * HM(m1, 3, 2);
+  HM(m, 0, 3) = t[2] * HM(m1, 2, 2) + t[5] * HM(m1, 2, 3) + t[1] * HM(m1, 2, 1);
+  HM(m, 0, 3) -= t[4] * HM(m1, 2, 3) + t[0] * HM(m1, 2, 1) + t[3] * HM(m1, 2, 2);
+  HM(m, 1, 3) = t[8] * HM(m1, 2, 3) + t[0] * HM(m1, 2, 0) + t[7] * HM(m1, 2, 2);
+  HM(m, 1, 3) -= t[6] * HM(m1, 2, 2) + t[9] * HM(m1, 2, 3) + t[1] * HM(m1, 2, 0);
+  HM(m, 2, 3) = t[6] * HM(m1, 2, 1) + t[11] * HM(m1, 2, 3) + t[3] * HM(m1, 2, 0);
+  HM(m, 2, 3) -= t[10] * HM(m1, 2, 3) + t[2] * HM(m1, 2, 0) + t[7] * HM(m1, 2, 1);
+  HM(m, 3, 3) = t[10] * HM(m1, 2, 2) + t[4] * HM(m1, 2, 0) + t[9] * HM(m1, 2, 1);
+  HM(m, 3, 3) -= t[8] * HM(m1, 2, 1) + t[11] * HM(m1, 2, 2) + t[5] * HM(m1, 2, 0);
+  const float k = 1.0f / (HM(m1, 0, 0) * HM(m, 0, 0) + HM(m1, 0, 1) * HM(m, 1, 0) + HM(m1, 0, 2) * HM(m, 2, 0) + HM(m1, 0, 3) * HM(m, 3, 0));
+  for (int i = 0; i < 16; i++) out[i] = m[i] * k;
+}
+
+}  // extern "C"

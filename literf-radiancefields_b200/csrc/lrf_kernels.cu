@@ -1,0 +1,861 @@
+// lrf_kernels.cu — hand-written sm_100a kernels of the LiteRF ray-march hot path.
+//
+//   K1 render / debug   : ref kernel2D_RayMarch           example_tracer.cpp:627-663
+//   K2 grad             : ref kernel2D_RayMarchGrad       example_tracer.cpp:665-718 (+ Enzyme adjoint :270-279)
+//   K3 tv / adam / fill : ref kernel2D_TVGrad :737-749, optimizerStep example_tracer.h:128-206, zeroGrad :104-109
+//   K4 upsample / boxes : ref UpsampleGrid :281-323, UpsampleOctree :325-447, RebuildOctree :449-489
+//
+// One thread per ray; a warp covers an 8x4 pixel tile so that its 32 rays walk neighbouring voxels.
+// Built with -fmad=false (see lrf_device.cuh): decision-critical arithmetic is IEEE op-for-op the
+// reference's; explicit fmaf() only on the colour path (RGB tolerance 1e-4).
+#include "lrf_kernels.cuh"
+
+namespace lrf {
+
+namespace {
+
+constexpr int kBlock = 128;
+
+struct RayCtx
+{
+  float o[3], d[3], idir[3];
+  float Y[9];
+};
+
+__device__ __forceinline__ void ray_ctx_init(RayCtx &R, const float *o, const float *d, bool grey)
+{
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    R.o[a] = o[a];
+    R.d[a] = d[a];
+    R.idir[a] = 1.0f / d[a];  // ref: example_tracer.cpp:20-22 (recomputed per box there; same value)
+  }
+  if (!grey) sh_eval_2(R.d, R.Y);
+}
+
+struct SampleGeom
+{
+  float t, delta, lf[3];
+  uint32_t base;  // node index of the near corner
+};
+
+// ref: RayGridIntersection example_tracer.cpp:134-153 — geometry of one sample, bit-exact
+__device__ __forceinline__ void sample_geom(const SceneDev &S, const RayCtx &R, int x, int y, int z, float &tPrev, SampleGeom &g)
+{
+  const int c[3] = {x, y, z};
+  float bmin[3], bmax[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    bmin[a] = (float)c[a] * S.inv_gs_f;        // == (float)x / (float)gs for gs = 2^k  (example_tracer.h:80)
+    bmax[a] = (float)(c[a] + 1) * S.inv_gs_f;
+  }
+  // ref: RayBoxIntersection example_tracer.cpp:18-43
+  float lo = R.idir[0] * (bmin[0] - R.o[0]), hi = R.idir[0] * (bmax[0] - R.o[0]);
+  float tmin = lm_min(lo, hi), tmax = lm_max(lo, hi);
+  lo = R.idir[1] * (bmin[1] - R.o[1]); hi = R.idir[1] * (bmax[1] - R.o[1]);
+  tmin = lm_max(tmin, lm_min(lo, hi)); tmax = lm_min(tmax, lm_max(lo, hi));
+  lo = R.idir[2] * (bmin[2] - R.o[2]); hi = R.idir[2] * (bmax[2] - R.o[2]);
+  tmin = lm_max(tmin, lm_min(lo, hi)); tmax = lm_min(tmax, lm_max(lo, hi));
+  if (tPrev < 0.0f) tPrev = tmin;                            // :139
+  const float t = (tmin + tmax) * 0.5f;                      // :142  (/2.0f is exact either way)
+  float actual = t - tPrev;                                  // :144
+  if (actual > S.step_gate_f)                                // :145  actual > sqrt(3)*step, compared in double there
+    actual = (float)((double)actual - (double)((int)((double)actual / S.step) - 1) * S.step);  // :146
+  g.t = t;
+  g.delta = actual;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float p = R.o[a] + t * R.d[a];                     // :148
+    g.lf[a] = (p - bmin[a]) * S.gs_f;                        // :150  division by (bmax-bmin) = 2^-k is this exact scaling
+  }
+  g.base = (uint32_t)x + (uint32_t)y * S.gs + (uint32_t)z * S.gs * S.gs;   // :152-153 near = (x,y,z), far = near + 1
+  tPrev = t;                                                 // :190
+}
+
+// trilinear density, nested lerps in the reference's order (:155-167 via lerpCell :72-80), bit-exact
+__device__ __forceinline__ float density_at(const SceneDev &S, const SampleGeom &g)
+{
+  const float *p = S.dens + g.base;
+  const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
+  const float d000 = __ldg(p), d100 = __ldg(p + 1), d010 = __ldg(p + sy), d110 = __ldg(p + sy + 1);
+  const float d001 = __ldg(p + sz), d101 = __ldg(p + sz + 1), d011 = __ldg(p + sz + sy), d111 = __ldg(p + sz + sy + 1);
+  const float xy00 = lm_lerp(d000, d100, g.lf[0]), xy10 = lm_lerp(d010, d110, g.lf[0]);
+  const float xy01 = lm_lerp(d001, d101, g.lf[0]), xy11 = lm_lerp(d011, d111, g.lf[0]);
+  const float xyz0 = lm_lerp(xy00, xy10, g.lf[1]), xyz1 = lm_lerp(xy01, xy11, g.lf[1]);
+  return lm_lerp(xyz0, xyz1, g.lf[2]);
+}
+
+__device__ __forceinline__ void corner_weights(const SampleGeom &g, float *w)
+{
+  const float fx = g.lf[0], fy = g.lf[1], fz = g.lf[2];
+  const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+  const float w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
+  w[0] = w00 * gz; w[1] = w10 * gz; w[2] = w01 * gz; w[3] = w11 * gz;
+  w[4] = w00 * fz; w[5] = w10 * fz; w[6] = w01 * fz; w[7] = w11 * fz;
+}
+
+// trilinear colour channels {R,G,B,sh0..sh8} as a weighted sum of the 8 corners (explicit FMA: this path
+// is bounded by the 1e-4 RGB tolerance, not bit-exactness)
+__device__ __forceinline__ void colour_at(const SceneDev &S, const SampleGeom &g, const float *w, float *acc /*12*/)
+{
+  const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
+#pragma unroll
+  for (int j = 0; j < 12; j++) acc[j] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint32_t idx = g.base + (c & 1) + ((c >> 1) & 1) * sy + ((c >> 2) & 1) * sz;
+    const float4 *q = S.col + (size_t)idx * kColF4;
+    const float4 a = __ldg(q), b = __ldg(q + 1), e = __ldg(q + 2);
+    acc[0] = fmaf(w[c], a.x, acc[0]); acc[1] = fmaf(w[c], a.y, acc[1]); acc[2] = fmaf(w[c], a.z, acc[2]); acc[3] = fmaf(w[c], a.w, acc[3]);
+    acc[4] = fmaf(w[c], b.x, acc[4]); acc[5] = fmaf(w[c], b.y, acc[5]); acc[6] = fmaf(w[c], b.z, acc[6]); acc[7] = fmaf(w[c], b.w, acc[7]);
+    acc[8] = fmaf(w[c], e.x, acc[8]); acc[9] = fmaf(w[c], e.y, acc[9]); acc[10] = fmaf(w[c], e.z, acc[10]); acc[11] = fmaf(w[c], e.w, acc[11]);
+  }
+}
+
+// SH dot + clamps, ref: eval_sh :108-118 and :181-184
+__device__ __forceinline__ void colour_from(const float *acc, const float *Y, float &raw, float &s, float *c)
+{
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; i++) sum = fmaf(acc[3 + i], Y[i], sum);
+  raw = sum;
+  s = lm_clamp(sum, 0.0f, 1.0f);
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) c[ch] = lm_clamp(acc[ch] * s, 0.0f, 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward visitor.  MODE 0: render (stop at the reference's throughput break);  MODE 1: parity taps
+// (keeps marching after the break to count every hit, records voxels / cauchy / touched nodes)
+template <int MODE> struct ShadeVisitor
+{
+  const SceneDev &S;
+  const uint64_t *etab;
+  RayCtx R;
+  bool grey;
+  float thr = 1.0f, tPrev = -1.0f, cauchy = 0.0f;
+  float col[3] = {0.0f, 0.0f, 0.0f};
+  uint32_t n_hit = 0, n_shaded = 0;
+  bool alive = true;
+  // taps
+  int32_t *vox = nullptr;
+  uint32_t keep = 0;
+  uint8_t *touched = nullptr;
+
+  __device__ ShadeVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) {}
+
+  __device__ __forceinline__ bool sample(int x, int y, int z)
+  {
+    if (MODE == 1) {
+      if (vox && n_hit < keep) { vox[n_hit * 3] = x; vox[n_hit * 3 + 1] = y; vox[n_hit * 3 + 2] = z; }
+      n_hit++;
+      if (!alive) return true;
+    } else n_hit = 1;
+    SampleGeom g;
+    sample_geom(S, R, x, y, z, tPrev, g);
+    float sigma = density_at(S, g);
+    if (sigma < 0.0f) sigma = 0.0f;                          // :170-171
+    if (MODE == 1) {
+      cauchy += logf(1.0f + 2.0f * sigma * sigma);           // :173 (value only feeds the loss; tolerance-compared)
+      if (touched) {
+        const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
+#pragma unroll
+        for (int c = 0; c < 8; c++) touched[g.base + (c & 1) + ((c >> 1) & 1) * sy + ((c >> 2) & 1) * sz] = 1;
+      }
+    }
+    const float tr = expf_libm(-sigma * g.delta, etab);      // :175
+    const float wgt = thr * (1.0f - tr);                     // :187
+    if (wgt != 0.0f) {                                       // wgt == 0 adds exactly 0 to a finite colour: skip the gather
+      if (grey) { col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt; }
+      else {
+        float w[8], acc[12], raw, s, c[3];
+        corner_weights(g, w);
+        colour_at(S, g, w, acc);
+        colour_from(acc, R.Y, raw, s, c);
+        col[0] = col[0] + wgt * c[0]; col[1] = col[1] + wgt * c[1]; col[2] = col[2] + wgt * c[2];
+      }
+    }
+    thr *= tr;                                               // :189
+    n_shaded++;
+    if (thr < 0.1f) {                                        // :131  (float < 0.1 as double  <=>  float < 0.1f)
+      alive = false;
+      return MODE == 1;
+    }
+    return true;
+  }
+};
+
+__device__ __forceinline__ void load_exp_table(uint64_t *tab)
+{
+  if (threadIdx.x < 32) tab[threadIdx.x] = kExp2fTab[threadIdx.x];
+  __syncthreads();
+}
+
+// pixel of this thread: a warp covers an 8x4 tile
+__device__ __forceinline__ bool tile_pixel(uint32_t w, uint32_t h, uint32_t &px, uint32_t &py)
+{
+  const uint32_t tiles_x = (w + 7) / 8;
+  const uint32_t tile = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  px = (tile % tiles_x) * 8 + (lane & 7);
+  py = (tile / tiles_x) * 4 + (lane >> 3);
+  return px < w && py < h;
+}
+inline uint32_t tile_grid(uint32_t w, uint32_t h)
+{
+  const uint32_t tiles = ((w + 7) / 8) * ((h + 3) / 4);
+  return (tiles + (kBlock / 32) - 1) / (kBlock / 32);
+}
+
+__global__ void __launch_bounds__(kBlock) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h, int grey)
+{
+  __shared__ uint64_t etab[32];
+  load_exp_table(etab);
+  uint32_t px, py;
+  if (!tile_pixel(w, h, px, py)) return;
+  float o[3], d[3];
+  gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
+  ShadeVisitor<0> vis(S, etab, grey != 0);
+  ray_ctx_init(vis.R, o, d, grey != 0);
+  march(S, o, d, vis);
+  uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
+  if (vis.n_hit)
+    pix = pack_color(lm_clamp(vis.col[0], 0.0f, 1.0f), lm_clamp(vis.col[1], 0.0f, 1.0f), lm_clamp(vis.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
+  out[(size_t)py * w + px] = pix;
+}
+
+template <bool IMAGE>
+__global__ void __launch_bounds__(kBlock) debug_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h, size_t n_rays, const float *__restrict__ ro,
+                                                       const float *__restrict__ rd, int grey, DebugTaps taps)
+{
+  __shared__ uint64_t etab[32];
+  load_exp_table(etab);
+  size_t ray;
+  float o[3], d[3];
+  if (IMAGE) {
+    uint32_t px, py;
+    if (!tile_pixel(w, h, px, py)) return;
+    ray = (size_t)py * w + px;
+    gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
+  } else {
+    ray = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (ray >= n_rays) return;
+#pragma unroll
+    for (int a = 0; a < 3; a++) { o[a] = ro[ray * 3 + a]; d[a] = rd[ray * 3 + a]; }
+  }
+  ShadeVisitor<1> vis(S, etab, grey != 0);
+  ray_ctx_init(vis.R, o, d, grey != 0);
+  vis.keep = taps.keep;
+  vis.vox = taps.vox_xyz ? taps.vox_xyz + ray * taps.keep * 3 : nullptr;
+  vis.touched = taps.touched;
+  if (vis.vox)
+    for (uint32_t i = 0; i < taps.keep * 3; i++) vis.vox[i] = -1;
+  march(S, o, d, vis);
+  if (taps.n_hit) taps.n_hit[ray] = vis.n_hit;
+  if (taps.n_shaded) taps.n_shaded[ray] = vis.n_shaded;
+  if (taps.rgbtc) {
+    float *r = taps.rgbtc + ray * 5;
+    if (vis.n_hit) {
+      r[0] = lm_clamp(vis.col[0], 0.0f, 1.0f); r[1] = lm_clamp(vis.col[1], 0.0f, 1.0f); r[2] = lm_clamp(vis.col[2], 0.0f, 1.0f);
+      r[3] = vis.thr; r[4] = vis.cauchy;
+    } else { r[0] = r[1] = r[2] = r[3] = r[4] = 0.0f; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward.  Pass A = the forward (colour sums kept per channel in fp64 so that pass B can form the
+// exact suffix  sum_{m>k} T_m (1-tr_m) c_m  as  total - prefix  without cancellation noise);
+// pass B = forward again, emitting the adjoint of every sample in FORWARD order (no tape in HBM):
+//   a_tr_k   = -T_k (c_k . aC) + [ (suffix_k . aC) + aT_n T_n ] / tr_k           (k < n-1; tr_k >= 0.1 there)
+//   a_tr_n-1 = -T_k (c_k . aC) + aT_n T_k
+// which is the closed form of the reverse sweep  aT <- tr aT + (1-tr) (c . aC)  of SURVEY 8 a11.
+struct FwdAVisitor
+{
+  const SceneDev &S;
+  const uint64_t *etab;
+  RayCtx R;
+  bool grey;
+  float thr = 1.0f, tPrev = -1.0f;
+  double csum[3] = {0.0, 0.0, 0.0};
+  float col[3] = {0.0f, 0.0f, 0.0f};
+  uint32_t n_shaded = 0;
+  __device__ FwdAVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) {}
+  __device__ __forceinline__ bool sample(int x, int y, int z)
+  {
+    SampleGeom g;
+    sample_geom(S, R, x, y, z, tPrev, g);
+    float sigma = density_at(S, g);
+    if (sigma < 0.0f) sigma = 0.0f;
+    const float tr = expf_libm(-sigma * g.delta, etab);
+    const float wgt = thr * (1.0f - tr);
+    if (wgt != 0.0f) {
+      float c[3] = {1.0f, 1.0f, 1.0f};
+      if (!grey) {
+        float w[8], acc[12], raw, s;
+        corner_weights(g, w);
+        colour_at(S, g, w, acc);
+        colour_from(acc, R.Y, raw, s, c);
+      }
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const float term = wgt * c[ch];
+        col[ch] = col[ch] + term;
+        csum[ch] += (double)term;
+      }
+    }
+    thr *= tr;
+    n_shaded++;
+    return !(thr < 0.1f);
+  }
+};
+
+__device__ __forceinline__ void red_add(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add4(float4 *p, float a, float b, float c, float d)
+{
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct BwdVisitor
+{
+  const SceneDev &S;
+  const uint64_t *etab;
+  RayCtx R;
+  bool grey;
+  float thr = 1.0f, tPrev = -1.0f;
+  double cpre[3] = {0.0, 0.0, 0.0};
+  // from pass A
+  double ctot[3];
+  float aC[3], aTn, Tn;
+  uint32_t n_total, k = 0;
+  __device__ BwdVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) {}
+  __device__ __forceinline__ bool sample(int x, int y, int z)
+  {
+    SampleGeom g;
+    sample_geom(S, R, x, y, z, tPrev, g);
+    const float dens_raw = density_at(S, g);
+    const bool last = (k + 1 == n_total);
+    if (dens_raw < 0.0f) {  // relu closed: sigma = 0, tr = exp(-0) = 1, weight 0 -> no adjoint reaches the grid (:170-171)
+      k++;
+      return !last;
+    }
+    const float sigma = dens_raw;
+    const float tr = expf_libm(-sigma * g.delta, etab);
+    const float wgt = thr * (1.0f - tr);
+    float w[8];
+    corner_weights(g, w);
+    // the colour is needed even when wgt == 0: d colour / d tr = -T_k c_k does not vanish with (1 - tr)
+    float c[3] = {1.0f, 1.0f, 1.0f}, acc[12], raw = 0.0f, s = 0.0f;
+    if (!grey) {
+      colour_at(S, g, w, acc);
+      colour_from(acc, R.Y, raw, s, c);
+    }
+    if (wgt != 0.0f) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) cpre[ch] += (double)(wgt * c[ch]);
+    }
+    const float dot = c[0] * aC[0] + c[1] * aC[1] + c[2] * aC[2];
+    float a_tr;
+    if (last) a_tr = -thr * dot + aTn * thr;
+    else {
+      const double suffix = (ctot[0] - cpre[0]) * (double)aC[0] + (ctot[1] - cpre[1]) * (double)aC[1] + (ctot[2] - cpre[2]) * (double)aC[2];
+      a_tr = -thr * dot + (float)((suffix + (double)aTn * (double)Tn) / (double)tr);
+    }
+    // d tr / d sigma = -delta * tr ;  cauchy: d/dsigma log(1 + 2 sigma^2) = 4 sigma / (1 + 2 sigma^2), weight 0.0005 (:267)
+    const float a_sigma = -g.delta * tr * a_tr + 0.0005f * (4.0f * sigma / (1.0f + 2.0f * sigma * sigma));
+    const float a_dens = a_sigma;                              // relu passes iff density >= 0 (:170)
+    const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
+    if (a_dens != 0.0f) {
+#pragma unroll
+      for (int cn = 0; cn < 8; cn++)
+        red_add(S.gdens + g.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz, w[cn] * a_dens);
+    }
+    if (!grey && wgt != 0.0f) {
+      float a_rgb[3] = {0.0f, 0.0f, 0.0f}, a_s = 0.0f;
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const float a_c = wgt * aC[ch];
+        const float u = acc[ch] * s;
+        if (0.0f < u && u <= 1.0f) { a_rgb[ch] = s * a_c; a_s = fmaf(acc[ch], a_c, a_s); }   // clamp passes iff 0 < u <= 1
+      }
+      const float a_raw = (0.0f < raw && raw <= 1.0f) ? a_s : 0.0f;
+      if (a_raw != 0.0f || a_rgb[0] != 0.0f || a_rgb[1] != 0.0f || a_rgb[2] != 0.0f) {
+        float a_sh[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) a_sh[j] = R.Y[j] * a_raw;
+#pragma unroll
+        for (int cn = 0; cn < 8; cn++) {
+          const uint32_t idx = g.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz;
+          float4 *q = S.gcol + (size_t)idx * kColF4;
+          const float ww = w[cn];
+          red_add4(q, ww * a_rgb[0], ww * a_rgb[1], ww * a_rgb[2], ww * a_sh[0]);
+          red_add4(q + 1, ww * a_sh[1], ww * a_sh[2], ww * a_sh[3], ww * a_sh[4]);
+          red_add4(q + 2, ww * a_sh[5], ww * a_sh[6], ww * a_sh[7], ww * a_sh[8]);
+        }
+      }
+    }
+    thr *= tr;
+    k++;
+    return !last;
+  }
+};
+
+template <bool IMAGE>
+__global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h, size_t n_rays, const float *__restrict__ ro,
+                                                      const float *__restrict__ rd, const float *__restrict__ ref_rgba, int grey)
+{
+  __shared__ uint64_t etab[32];
+  load_exp_table(etab);
+  size_t ray;
+  float o[3], d[3];
+  if (IMAGE) {
+    uint32_t px, py;
+    if (!tile_pixel(w, h, px, py)) return;
+    ray = (size_t)py * w + px;
+    gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
+  } else {
+    ray = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (ray >= n_rays) return;
+#pragma unroll
+    for (int a = 0; a < 3; a++) { o[a] = ro[ray * 3 + a]; d[a] = rd[ray * 3 + a]; }
+  }
+  FwdAVisitor fa(S, etab, grey != 0);
+  ray_ctx_init(fa.R, o, d, grey != 0);
+  march(S, o, d, fa);
+  if (fa.n_shaded == 0) return;  // ref :688  empty hit list: no loss term
+  const float4 rp = __ldg(reinterpret_cast<const float4 *>(ref_rgba) + ray);
+  float ref[3] = {rp.x, rp.y, rp.z};
+  if (grey) {  // ref :696-704
+    const float gsc = 0.11f * rp.z + 0.59f * rp.y + 0.3f * rp.x;
+    ref[0] = ref[1] = ref[2] = gsc;
+  }
+  BwdVisitor bw(S, etab, grey != 0);
+  bw.R = fa.R;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const float craw = fa.col[ch];
+    const float cc = lm_clamp(craw, 0.0f, 1.0f);             // :193
+    const float diff = cc - ref[ch];                         // :266
+    const float sg = diff < 0.0f ? -1.0f : 1.0f;
+    bw.aC[ch] = (0.0f < craw && craw <= 1.0f) ? sg : 0.0f;
+    bw.ctot[ch] = fa.csum[ch];
+  }
+  // d/dT of 0.0001f * (log(T + 1e-3) + log(1 - T + 1e-3))   (:267, double arithmetic there)
+  bw.Tn = fa.thr;
+  bw.aTn = (float)((double)0.0001f * (1.0 / ((double)fa.thr + 1e-3) - 1.0 / ((double)(1.0f - fa.thr) + 1e-3)));
+  bw.n_total = fa.n_shaded;
+  march(S, o, d, bw);
+}
+
+// device-side ray generation for (view, pixel) picks — ref :635-639
+__global__ void gen_rays_kernel(size_t n, const float *__restrict__ view_inv, const uint32_t *__restrict__ picks, uint32_t w, uint32_t h,
+                                float *__restrict__ o, float *__restrict__ d, const __grid_constant__ SceneDev S)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t view = picks[2 * i], pix = picks[2 * i + 1];
+  float vi[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) vi[j] = __ldg(view_inv + (size_t)view * 16 + j);
+  float oo[3], dd[3];
+  gen_ray(vi, S.proj_inv, pix % w, pix / w, w, h, oo, dd);
+#pragma unroll
+  for (int a = 0; a < 3; a++) { o[i * 3 + a] = oo[a]; d[i * 3 + a] = dd[a]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TV (density only; ref TVRegularisation :196-239, the SH loop :241-245 is dead — SURVEY §2 defects)
+// stage 1: V_raw(a,b,c) = trilinear(0.5) of density over {a,min(a+1,gs-1)} x ... (getVoxel :203-230), pre-relu
+__global__ void tv_voxel_kernel(int gs, const float *__restrict__ dens, float *__restrict__ vraw)
+{
+  const size_t N = (size_t)gs * gs * gs, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int a = (int)(i % gs), b = (int)((i / gs) % gs), c = (int)(i / ((size_t)gs * gs));
+  const int a1 = min(a + 1, gs - 1), b1 = min(b + 1, gs - 1), c1 = min(c + 1, gs - 1);
+  auto at = [&](int x, int y, int z) { return __ldg(dens + (size_t)x + (size_t)y * gs + (size_t)z * gs * gs); };
+  const float xy00 = lm_lerp(at(a, b, c), at(a1, b, c), 0.5f), xy10 = lm_lerp(at(a, b1, c), at(a1, b1, c), 0.5f);
+  const float xy01 = lm_lerp(at(a, b, c1), at(a1, b, c1), 0.5f), xy11 = lm_lerp(at(a, b1, c1), at(a1, b1, c1), 0.5f);
+  vraw[i] = lm_lerp(lm_lerp(xy00, xy10, 0.5f), lm_lerp(xy01, xy11, 0.5f), 0.5f);
+}
+// stage 2: G(p) = d(sum tv)/dV(p) gathered from the <= 4 tv cells that reference V(p), relu-gated
+__global__ void tv_gather_kernel(int gs, const float *__restrict__ vraw, float *__restrict__ gv)
+{
+  const size_t N = (size_t)gs * gs * gs, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int a = (int)(i % gs), b = (int)((i / gs) % gs), c = (int)(i / ((size_t)gs * gs));
+  auto V = [&](int x, int y, int z) { const float v = __ldg(vraw + (size_t)x + (size_t)y * gs + (size_t)z * gs * gs); return v < 0.0f ? 0.0f : v; };
+  const float lam = 0.01f;
+  // contribution of tv cell (x,y,z) (requires x,y,z < gs-1): which = 0 centre, 1/2/3 = it references us as its +x/+y/+z neighbour
+  auto cell = [&](int x, int y, int z, int which) -> float {
+    const float v = V(x, y, z);
+    const float dx = v - V(x + 1, y, z), dy = v - V(x, y + 1, z), dz = v - V(x, y, z + 1);
+    const float sum = dx * dx + dy * dy + dz * dz;
+    if (!(sum > 0.0f)) return 0.0f;  // sqrt'(0) := 0
+    const float r = sqrtf(sum);
+    const float num = which == 0 ? (dx + dy + dz) : which == 1 ? -dx : which == 2 ? -dy : -dz;
+    return lam * num / r;
+  };
+  float g = 0.0f;
+  const int m = gs - 1;
+  if (a < m && b < m && c < m) g += cell(a, b, c, 0);
+  if (a >= 1 && b < m && c < m) g += cell(a - 1, b, c, 1);
+  if (b >= 1 && a < m && c < m) g += cell(a, b - 1, c, 2);
+  if (c >= 1 && a < m && b < m) g += cell(a, b, c - 1, 3);
+  gv[i] = (__ldg(vraw + i) < 0.0f) ? 0.0f : g;  // relu gate of getVoxel (:226-227)
+}
+// stage 3: density-node gradient += sum over the V cells having the node as a corner of (0.5 per axis, doubled where far == near)
+__global__ void tv_scatter_kernel(int gs, const float *__restrict__ gv, float *__restrict__ gdens)
+{
+  const size_t N = (size_t)gs * gs * gs, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int q[3] = {(int)(i % gs), (int)((i / gs) % gs), (int)(i / ((size_t)gs * gs))};
+  float acc = 0.0f;
+  for (int dz = -1; dz <= 0; dz++)
+    for (int dy = -1; dy <= 0; dy++)
+      for (int dx = -1; dx <= 0; dx++) {
+        const int p[3] = {q[0] + dx, q[1] + dy, q[2] + dz};
+        if (p[0] < 0 || p[1] < 0 || p[2] < 0) continue;
+        float wgt = 1.0f;
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+          const int mult = (q[ax] == p[ax] ? 1 : 0) + (q[ax] == min(p[ax] + 1, gs - 1) ? 1 : 0);
+          wgt *= 0.5f * (float)mult;
+        }
+        acc += wgt * __ldg(gv + (size_t)p[0] + (size_t)p[1] * gs + (size_t)p[2] * gs * gs);
+      }
+  gdens[i] += acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam, ref optimizerStep example_tracer.h:152-162: fp32 moments, fp64 update expression
+__global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ V, float *__restrict__ Sq,
+                                                   size_t count, float lr, float beta1, float beta2, float eps, double om_b1, double om_b2,
+                                                   int zero_grad)
+{
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= count) return;
+  const float omb1 = 1 - beta1, omb2 = 1 - beta2;  // (1 - beta_1) evaluated in float, as the reference's int - float
+#define LRF_ADAM_ONE(pp, gg, vv, ss)                                                   \
+  do {                                                                                 \
+    vv = beta1 * vv + omb1 * gg;                                                       \
+    const double Vh = (double)vv / om_b1;                                              \
+    ss = beta2 * ss + omb2 * gg * gg;                                                  \
+    const double Sh = (double)ss / om_b2;                                              \
+    pp = (float)((double)pp - (double)lr * Vh / (sqrt(Sh) + (double)eps));             \
+  } while (0)
+  if (i4 + 4 <= count) {
+    float4 pv = *reinterpret_cast<float4 *>(p + i4), gv = *reinterpret_cast<float4 *>(g + i4);
+    float4 vv = *reinterpret_cast<float4 *>(V + i4), sv = *reinterpret_cast<float4 *>(Sq + i4);
+    LRF_ADAM_ONE(pv.x, gv.x, vv.x, sv.x); LRF_ADAM_ONE(pv.y, gv.y, vv.y, sv.y);
+    LRF_ADAM_ONE(pv.z, gv.z, vv.z, sv.z); LRF_ADAM_ONE(pv.w, gv.w, vv.w, sv.w);
+    *reinterpret_cast<float4 *>(p + i4) = pv;
+    *reinterpret_cast<float4 *>(V + i4) = vv;
+    *reinterpret_cast<float4 *>(Sq + i4) = sv;
+    if (zero_grad) *reinterpret_cast<float4 *>(g + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (size_t i = i4; i < count; i++) {
+      float pp = p[i], vv = V[i], ss = Sq[i];
+      const float gg = g[i];
+      LRF_ADAM_ONE(pp, gg, vv, ss);
+      p[i] = pp; V[i] = vv; Sq[i] = ss;
+      if (zero_grad) g[i] = 0.0f;
+    }
+  }
+#undef LRF_ADAM_ONE
+}
+
+__global__ void fill_kernel(float *__restrict__ p, size_t count, float v)
+{
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 4 <= count) *reinterpret_cast<float4 *>(p + i4) = make_float4(v, v, v, v);
+  else
+    for (size_t i = i4; i < count; i++) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion between the reference's AoS Cell[13] and the device planes
+__global__ void aos_to_planes_kernel(const float *__restrict__ aos, float *__restrict__ planes, size_t N)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * kCell) return;
+  const size_t node = t / kCell;
+  const int j = (int)(t % kCell);
+  const float v = aos[t];
+  if (j == 0) planes[node] = v;
+  else planes[N + node * 12 + (j - 1)] = v;
+}
+__global__ void planes_to_aos_kernel(const float *__restrict__ planes, float *__restrict__ aos, size_t N)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * kCell) return;
+  const size_t node = t / kCell;
+  const int j = (int)(t % kCell);
+  aos[t] = (j == 0) ? planes[node] : planes[N + node * 12 + (j - 1)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// level transition
+__device__ __forceinline__ float plane_get(const float *planes, size_t N, size_t node, int j)
+{
+  return j == 0 ? __ldg(planes + node) : __ldg(planes + N + node * 12 + (j - 1));
+}
+// ref UpsampleGrid :281-323: thread per (new node, channel)
+__global__ void upsample_grid_kernel(int old_gs, const float *__restrict__ old_planes, float *__restrict__ new_planes)
+{
+  const int gs = old_gs * 2;
+  const size_t Nn = (size_t)gs * gs * gs, No = (size_t)old_gs * old_gs * old_gs;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Nn * kCell) return;
+  const size_t node = t / kCell;
+  const int j = (int)(t % kCell);
+  const int xyz[3] = {(int)(node % gs), (int)((node / gs) % gs), (int)(node / ((size_t)gs * gs))};
+  const float step = 1.0f / (float)gs;
+  int nc[3], fc[3];
+  float lf[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float coord = (0.0f + step * ((float)xyz[a] + 0.5f)) * (float)old_gs;  // :294
+    nc[a] = max(0, min(old_gs - 1, (int)coord));
+    fc[a] = max(0, min(old_gs - 1, (int)coord + 1));
+    lf[a] = coord - (float)nc[a];
+  }
+  auto at = [&](int x, int y, int z) { return plane_get(old_planes, No, (size_t)x + (size_t)y * old_gs + (size_t)z * old_gs * old_gs, j); };
+  const float xy00 = lm_lerp(at(nc[0], nc[1], nc[2]), at(fc[0], nc[1], nc[2]), lf[0]);
+  const float xy10 = lm_lerp(at(nc[0], fc[1], nc[2]), at(fc[0], fc[1], nc[2]), lf[0]);
+  const float xy01 = lm_lerp(at(nc[0], nc[1], fc[2]), at(fc[0], nc[1], fc[2]), lf[0]);
+  const float xy11 = lm_lerp(at(nc[0], fc[1], fc[2]), at(fc[0], fc[1], fc[2]), lf[0]);
+  float v = lm_lerp(lm_lerp(xy00, xy10, lf[1]), lm_lerp(xy01, xy11, lf[1]), lf[2]);
+  if (j == 0 && v < 0.0f) v = 0.0f;  // :316-317
+  if (j == 0) new_planes[node] = v;
+  else new_planes[Nn + node * 12 + (j - 1)] = v;
+}
+
+// un-relu'd trilinear density at the centre of lattice box (x,y,z): getDensity lambda :331-357 / RebuildOctree :459-483
+__device__ __forceinline__ float box_centre_density(const SceneDev &S, int x, int y, int z)
+{
+  const int c[3] = {x, y, z};
+  float lf[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float bmin = (float)c[a] * S.inv_gs_f, bmax = (float)(c[a] + 1) * S.inv_gs_f;
+    const float p = (bmin + bmax) / 2.0f;
+    lf[a] = (p - bmin) / (bmax - bmin);
+  }
+  SampleGeom g;
+  g.lf[0] = lf[0]; g.lf[1] = lf[1]; g.lf[2] = lf[2];
+  g.base = (uint32_t)x + (uint32_t)y * S.gs + (uint32_t)z * S.gs * S.gs;
+  return density_at(S, g);
+}
+__constant__ int kChildOrder[8][3] = {{0, 0, 0}, {1, 1, 1}, {1, 0, 0}, {0, 1, 0}, {1, 1, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};  // :363-441
+__global__ void box_child_flags_kernel(const __grid_constant__ SceneDev S, const int32_t *__restrict__ old_xyz, size_t n_old, uint32_t *__restrict__ flags)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_old * 8) return;
+  const size_t b = t >> 3;
+  const int c = (int)(t & 7);
+  const int x = 2 * old_xyz[3 * b] + kChildOrder[c][0], y = 2 * old_xyz[3 * b + 1] + kChildOrder[c][1], z = 2 * old_xyz[3 * b + 2] + kChildOrder[c][2];
+  flags[t] = box_centre_density(S, x, y, z) > 0.0f ? 1u : 0u;  // :369
+}
+__global__ void box_keep_flags_kernel(const __grid_constant__ SceneDev S, const int32_t *__restrict__ xyz, size_t n, uint32_t *__restrict__ flags)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  flags[t] = box_centre_density(S, xyz[3 * t], xyz[3 * t + 1], xyz[3 * t + 2]) > 0.0f ? 1u : 0u;  // :483
+}
+__global__ void box_compact_children_kernel(const int32_t *__restrict__ old_xyz, size_t n_old, const uint32_t *__restrict__ flags,
+                                            const uint32_t *__restrict__ offs, int32_t *__restrict__ new_xyz)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_old * 8 || !flags[t]) return;
+  const size_t b = t >> 3;
+  const int c = (int)(t & 7);
+  const size_t o = offs[t];
+  new_xyz[3 * o] = 2 * old_xyz[3 * b] + kChildOrder[c][0];
+  new_xyz[3 * o + 1] = 2 * old_xyz[3 * b + 1] + kChildOrder[c][1];
+  new_xyz[3 * o + 2] = 2 * old_xyz[3 * b + 2] + kChildOrder[c][2];
+}
+__global__ void box_compact_kernel(const int32_t *__restrict__ xyz, size_t n, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ offs,
+                                   int32_t *__restrict__ new_xyz)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n || !flags[t]) return;
+  const size_t o = offs[t];
+  new_xyz[3 * o] = xyz[3 * t]; new_xyz[3 * o + 1] = xyz[3 * t + 1]; new_xyz[3 * o + 2] = xyz[3 * t + 2];
+}
+__global__ void build_box_maps_kernel(int nv, const int32_t *__restrict__ xyz, size_t n, uint32_t *__restrict__ occ, uint32_t *__restrict__ vox2id)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t lin = (uint32_t)xyz[3 * t] + (uint32_t)xyz[3 * t + 1] * nv + (uint32_t)xyz[3 * t + 2] * nv * nv;
+  atomicOr(occ + (lin >> 5), 1u << (lin & 31));
+  vox2id[lin] = (uint32_t)t;
+}
+__global__ void count_nonzero_kernel(const uint8_t *__restrict__ marks, size_t n, unsigned long long *out)
+{
+  unsigned long long local = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) local += marks[i] ? 1 : 0;
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+// two-level exclusive scan of uint32 flags (order-preserving box compaction)
+constexpr int kScanBlock = 1024;
+__global__ void scan_block_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n, uint32_t *__restrict__ block_sums)
+{
+  __shared__ uint32_t warp_sums[32];
+  const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const uint32_t v = i < n ? in[i] : 0u;
+  uint32_t x = v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = warp_sums[lane];
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t incl = x + (wid ? warp_sums[wid - 1] : 0u);
+  if (i < n) out[i] = incl - v;
+  if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = incl;
+}
+__global__ void scan_sums_kernel(uint32_t *block_sums, size_t nb)  // single block, serial over chunks
+{
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < nb; base += kScanBlock) {
+    const size_t i = base + threadIdx.x;
+    const uint32_t v = i < nb ? block_sums[i] : 0u;
+    uint32_t x = v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t s = warp_sums[lane];
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t incl = x + (wid ? warp_sums[wid - 1] : 0u) + carry;
+    if (i < nb) block_sums[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == kScanBlock - 1) carry = incl;
+    __syncthreads();
+  }
+}
+__global__ void scan_add_kernel(uint32_t *__restrict__ out, size_t n, const uint32_t *__restrict__ block_sums)
+{
+  const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;
+  if (i < n) out[i] += block_sums[blockIdx.x];
+}
+
+inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, cudaStream_t st)
+{
+  render_image_kernel<<<tile_grid(w, h), kBlock, 0, st>>>(S, out_dev, w, h, grey);
+}
+void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, const DebugTaps &taps, cudaStream_t st)
+{
+  debug_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, grey, taps);
+}
+void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float *d, int grey, const DebugTaps &taps, cudaStream_t st)
+{
+  if (n == 0) return;
+  debug_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, grey, taps);
+}
+void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st)
+{
+  grad_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, ref_rgba, grey);
+}
+void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, cudaStream_t st)
+{
+  if (n == 0) return;
+  grad_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, ref_rgba, grey);
+}
+void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_inv_dev, const uint32_t *picks, uint32_t w, uint32_t h, float *o,
+                     float *d, cudaStream_t st)
+{
+  if (n == 0) return;
+  SceneDev S{};
+  for (int i = 0; i < 16; i++) S.proj_inv[i] = proj_inv_host16[i];
+  gen_rays_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, view_inv_dev, picks, w, h, o, d, S);
+}
+void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float *tmp_g, cudaStream_t st)
+{
+  const size_t N = (size_t)gs * gs * gs;
+  tv_voxel_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, dens, tmp_v);
+  tv_gather_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, tmp_v, tmp_g);
+  tv_scatter_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, tmp_g, gdens);
+}
+void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t count, float lr, float beta1, float beta2, float eps, double om_b1,
+                 double om_b2, int zero_grad, cudaStream_t st)
+{
+  if (count == 0) return;
+  adam_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(p + off, g + off, V + off, S + off, count, lr, beta1, beta2, eps, om_b1, om_b2,
+                                                                zero_grad);
+}
+void launch_fill(float *p, size_t count, float v, cudaStream_t st)
+{
+  if (count == 0) return;
+  fill_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(p, count, v);
+}
+void launch_aos_to_planes(const float *aos, float *planes, size_t N, cudaStream_t st)
+{
+  aos_to_planes_kernel<<<blocks_for(N * kCell, 256), 256, 0, st>>>(aos, planes, N);
+}
+void launch_planes_to_aos(const float *planes, float *aos, size_t N, cudaStream_t st)
+{
+  planes_to_aos_kernel<<<blocks_for(N * kCell, 256), 256, 0, st>>>(planes, aos, N);
+}
+void launch_upsample_grid(int old_gs, const float *old_planes, float *new_planes, cudaStream_t st)
+{
+  const size_t Nn = (size_t)old_gs * old_gs * old_gs * 8;
+  upsample_grid_kernel<<<blocks_for(Nn * kCell, 256), 256, 0, st>>>(old_gs, old_planes, new_planes);
+}
+void launch_box_child_flags(const SceneDev &S_new, const int32_t *old_xyz, size_t n_old, uint32_t *flags, cudaStream_t st)
+{
+  if (n_old == 0) return;
+  box_child_flags_kernel<<<blocks_for(n_old * 8, 256), 256, 0, st>>>(S_new, old_xyz, n_old, flags);
+}
+void launch_box_keep_flags(const SceneDev &S, const int32_t *xyz, size_t n, uint32_t *flags, cudaStream_t st)
+{
+  if (n == 0) return;
+  box_keep_flags_kernel<<<blocks_for(n, 256), 256, 0, st>>>(S, xyz, n, flags);
+}
+void launch_box_compact_children(const int32_t *old_xyz, size_t n_old, const uint32_t *flags, const uint32_t *offsets, int32_t *new_xyz,
+                                 cudaStream_t st)
+{
+  if (n_old == 0) return;
+  box_compact_children_kernel<<<blocks_for(n_old * 8, 256), 256, 0, st>>>(old_xyz, n_old, flags, offsets, new_xyz);
+}
+void launch_box_compact(const int32_t *xyz, size_t n, const uint32_t *flags, const uint32_t *offsets, int32_t *new_xyz, cudaStream_t st)
+{
+  if (n == 0) return;
+  box_compact_kernel<<<blocks_for(n, 256), 256, 0, st>>>(xyz, n, flags, offsets, new_xyz);
+}
+void launch_build_box_maps(int nv, const int32_t *xyz, size_t n, uint32_t *occ, uint32_t *vox2id, cudaStream_t st)
+{
+  if (n == 0) return;
+  build_box_maps_kernel<<<blocks_for(n, 256), 256, 0, st>>>(nv, xyz, n, occ, vox2id);
+}
+void launch_count_nonzero(const uint8_t *marks, size_t n, unsigned long long *out, cudaStream_t st)
+{
+  count_nonzero_kernel<<<148 * 8, 256, 0, st>>>(marks, n, out);
+}
+size_t scan_tmp_elems(size_t n) { return (n + kScanBlock - 1) / kScanBlock + 1; }
+void launch_exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *block_tmp, cudaStream_t st)
+{
+  if (n == 0) return;
+  const size_t nb = (n + kScanBlock - 1) / kScanBlock;
+  scan_block_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(in, out, n, block_tmp);
+  scan_sums_kernel<<<1, kScanBlock, 0, st>>>(block_tmp, nb);
+  scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(out, n, block_tmp);
+}
+
+}  // namespace lrf

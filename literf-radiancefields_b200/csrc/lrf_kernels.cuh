@@ -1,0 +1,50 @@
+// lrf_kernels.cuh — launch interface between the C-ABI layer (lrf_capi.cu) and the sm_100a
+// kernels (lrf_kernels.cu).  Plain pointers and sizes only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lrf_device.cuh"
+
+namespace lrf {
+
+struct DebugTaps  // device pointers, any may be null
+{
+  uint32_t *n_hit;
+  uint32_t *n_shaded;
+  float *rgbtc;      // 5 per ray
+  int32_t *vox_xyz;  // keep*3 per ray
+  uint32_t keep;
+  uint8_t *touched;  // [gs^3] node-read marks (lrf_count_touched_nodes)
+};
+
+// forward
+void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, cudaStream_t st);
+void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, const DebugTaps &taps, cudaStream_t st);
+void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float *d, int grey, const DebugTaps &taps, cudaStream_t st);
+// backward
+void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st);
+void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, cudaStream_t st);
+void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_inv_dev, const uint32_t *picks, uint32_t w, uint32_t h,
+                     float *o, float *d, cudaStream_t st);
+// per-cell
+void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float *tmp_g, cudaStream_t st);
+void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t count, float lr, float beta1, float beta2, float eps,
+                 double om_b1, double om_b2, int zero_grad, cudaStream_t st);
+void launch_fill(float *p, size_t count, float v, cudaStream_t st);
+// layout conversion: host AoS [N][13]  <->  device planes dens[N] + col[N][12]
+void launch_aos_to_planes(const float *aos, float *planes, size_t N, cudaStream_t st);
+void launch_planes_to_aos(const float *planes, float *aos, size_t N, cudaStream_t st);
+// level transition
+void launch_upsample_grid(int old_gs, const float *old_planes, float *new_planes, cudaStream_t st);
+void launch_box_child_flags(const SceneDev &S_new, const int32_t *old_xyz, size_t n_old, uint32_t *flags, cudaStream_t st);   // 8 per box
+void launch_box_keep_flags(const SceneDev &S, const int32_t *xyz, size_t n, uint32_t *flags, cudaStream_t st);                // 1 per box
+void launch_box_compact_children(const int32_t *old_xyz, size_t n_old, const uint32_t *flags, const uint32_t *offsets, int32_t *new_xyz,
+                                 cudaStream_t st);
+void launch_box_compact(const int32_t *xyz, size_t n, const uint32_t *flags, const uint32_t *offsets, int32_t *new_xyz, cudaStream_t st);
+void launch_build_box_maps(int n_vox_axis, const int32_t *xyz, size_t n, uint32_t *occ, uint32_t *vox2id, cudaStream_t st);
+void launch_count_nonzero(const uint8_t *marks, size_t n, unsigned long long *out, cudaStream_t st);
+// exclusive prefix sum of uint32 flags (single-pass decoupled look-back is overkill here; two-level scan)
+void launch_exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *block_tmp, cudaStream_t st);
+size_t scan_tmp_elems(size_t n);
+
+}  // namespace lrf

@@ -1,0 +1,150 @@
+"""GPU parity, forward: the CUDA path through the C-ABI vs the CPU oracle on identical seeded inputs.
+Bar (BASELINE.json north_star): bit-exact per-ray hit counts, shaded-sample counts and voxel indices;
+RGB within 1e-4 absolute (PSNR > 60 dB); packed pixels equal up to the 1e-4 tolerance."""
+import numpy as np
+import pytest
+
+import libs
+from scenes import OracleScene, cameras, sphere_boxes
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 1e-4  # north_star: rendered RGB within 1e-4 absolute
+
+
+def _check_view(t, S, w, h, grey, keep):
+    nh_o, ns_o, rg_o, vox_o = S.render_debug(w, h, grey, keep)
+    nh_g, ns_g, rg_g, vox_g = t.render_debug(w, h, grey, keep)
+    assert np.array_equal(nh_o, nh_g), "hit counts differ on %d rays" % (nh_o != nh_g).sum()
+    assert np.array_equal(ns_o, ns_g), "shaded counts differ on %d rays" % (ns_o != ns_g).sum()
+    assert np.array_equal(vox_o, vox_g), "voxel lists differ"
+    assert np.abs(rg_o[:, :3] - rg_g[:, :3]).max() <= RGB_TOL
+    assert np.array_equal(rg_o[:, 3].view(np.uint32), rg_g[:, 3].view(np.uint32)), "transmittance not bit-exact"
+    assert np.allclose(rg_o[:, 4], rg_g[:, 4], rtol=1e-5, atol=1e-6)  # cauchy: logf is tolerance-compared
+    mse = np.mean((rg_o[:, :3].astype(np.float64) - rg_g[:, :3]) ** 2)
+    assert mse == 0 or 10 * np.log10(1.0 / mse) > 60.0
+    img_o = S.render(w, h, grey)
+    img_g = np.zeros(w * h, np.uint32)
+    t.kernel2D_RayMarch(img_g, w, h, grey)
+    ch_o = np.stack([(img_o >> s) & 255 for s in (0, 8, 16, 24)]).astype(np.int32)
+    ch_g = np.stack([(img_g >> s) & 255 for s in (0, 8, 16, 24)]).astype(np.int32)
+    assert np.abs(ch_o - ch_g).max() <= 1  # (uint)(c*255) of colours within 1e-4
+    assert np.array_equal(ch_o[3], ch_g[3])
+    assert (ch_o != ch_g).mean() < 1e-3
+    return nh_o, ns_o
+
+
+@pytest.mark.parametrize("gs,D,wh", [(16, 20.0, 64), (16, 2.0, 64), (32, 20.0, 64), (64, 20.0, 48)])
+def test_dense_orbit_views(pkg, gs, D, wh):
+    grid = libs.lcg_grid(gs, D)
+    S = OracleScene(gs, grid)
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.SetBoundingBox([0, 0, 0], [1, 1, 1])
+    t.set_grid(grid)
+    total_hits = 0
+    for k in range(7):
+        vi, pi = cameras(pkg, k, 7)
+        S.set_cam(vi, pi)
+        t.set_view_inv(vi)
+        t.set_proj_inv(pi)
+        nh, ns = _check_view(t, S, wh, wh, False, keep=min(3 * gs, 96))
+        total_hits += int(nh.sum())
+    assert total_hits > 0
+    t.close()
+    S.close()
+
+
+def test_init_grid_contents_and_greyscale(pkg):
+    gs = 16
+    S = OracleScene(gs)
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    assert np.array_equal(t.get_grid(), S.grid)  # InitGrid contents, example_tracer.h:65-67
+    vi, pi = cameras(pkg, 3, 7)
+    S.set_cam(vi, pi)
+    t.set_view_inv(vi)
+    t.set_proj_inv(pi)
+    _check_view(t, S, 32, 32, True, keep=40)
+    _check_view(t, S, 33, 17, False, keep=40)  # ragged image size: partial tiles
+    t.close()
+    S.close()
+
+
+def test_sparse_box_set(pkg):
+    gs = 32
+    grid = libs.lcg_grid(gs, 20.0)
+    boxes = sphere_boxes(gs)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(boxes.shape[0])  # ids in a non-lattice order, like the reference's after UpsampleOctree
+    for bx in (boxes, boxes[perm]):
+        S = OracleScene(gs, grid)
+        S.set_boxes(bx)
+        t = pkg.RayMarcherExample()
+        t.InitGrid(gs)
+        t.set_grid(grid)
+        t.set_boxes(bx)
+        assert t.box_count() == bx.shape[0]
+        assert np.array_equal(t.get_boxes(), bx)
+        for k in (0, 2, 5):
+            vi, pi = cameras(pkg, k, 7)
+            S.set_cam(vi, pi)
+            t.set_view_inv(vi)
+            t.set_proj_inv(pi)
+            _check_view(t, S, 48, 48, False, keep=64)
+        t.close()
+        S.close()
+
+
+def test_crafted_rays_ties_and_static_axes(pkg):
+    """axis-aligned and lattice-grazing rays: exact edge/corner ties, zero direction components, origin on a
+    plane, origin inside the lattice, rays that miss — the cases a plain DDA gets wrong"""
+    gs = 16
+    grid = libs.lcg_grid(gs, 2.0)
+    S = OracleScene(gs, grid)
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.set_grid(grid)
+    o, d = [], []
+    g = 1.0 / gs
+    for oo, dd in [
+        ((-0.5, 0.5 * g * 5, 0.5 * g * 7), (1, 0, 0)),          # two static axes, inside a cell
+        ((-0.5, 4 * g, 0.5 * g * 7), (1, 0, 0)),                # static axis exactly on a plane
+        ((-0.5, 4 * g, 6 * g), (1, 0, 0)),                      # two static axes on planes: 4 cells per step
+        ((-0.25, -0.25, 0.5 * g), (1, 1, 0)),                   # exact diagonal through lattice edges
+        ((-0.25, -0.25, -0.25), (1, 1, 1)),                     # exact diagonal through lattice corners
+        ((1.25, 1.25, 1.25), (-1, -1, -1)),                     # same, negative travel
+        ((0.5, 0.5, 0.5), (0.3, 0.5, 0.81)),                    # origin inside the lattice
+        ((4 * g, 4 * g, 4 * g), (1, 0.5, 0.25)),                # origin on a lattice corner
+        ((4 * g, 4 * g, 4 * g), (-1, 0.5, 0.25)),
+        ((0.5, 0.5, 2.0), (0, 0, 1)),                           # pointing away: miss
+        ((0.5, 0.5, 2.0), (0, 0, -1)),
+        ((-1, 15 * g, 0.5), (1, 0, 0)),                         # static axis on the last plane of the lattice
+        ((-1, 0.0, 0.5), (1, 0, 0)),                            # static axis on the first plane
+        ((-1, 15.5 * g, 0.5), (1, 0, 0)),                       # beyond the lattice (node row without boxes): miss
+        ((2.0, 0.5 * g, 0.5 * g), (-1, 1e-30, 0)),              # denormal-scale direction component
+    ]:
+        dd = np.array(dd, np.float64)
+        dd = dd / np.linalg.norm(dd)
+        o.append(oo)
+        d.append(dd)
+    rng = np.random.default_rng(11)
+    for _ in range(400):  # random rays from lattice-aligned origins along rational directions: many exact ties
+        oo = rng.integers(-8, 24, 3) * g * 0.5
+        dd = rng.integers(-3, 4, 3).astype(np.float64)
+        if not dd.any():
+            dd[0] = 1
+        o.append(oo)
+        d.append(dd / 4.0)
+    o, d = np.array(o, np.float32), np.array(d, np.float32)
+    keep = 64
+    nh_o, ns_o, rg_o, vox_o = S.trace_rays(o, d, False, keep)
+    nh_g, ns_g, rg_g, vox_g = t.trace_rays(o, d, False, keep)
+    bad = np.nonzero(nh_o != nh_g)[0]
+    assert bad.size == 0, "hit counts differ on rays %s: oracle %s gpu %s" % (bad[:8], nh_o[bad[:8]], nh_g[bad[:8]])
+    assert np.array_equal(vox_o, vox_g)
+    assert np.array_equal(ns_o, ns_g)
+    assert np.abs(rg_o[:, :3] - rg_g[:, :3]).max() <= RGB_TOL
+    assert nh_o.max() > 0 and (nh_o == 0).any()
+    t.close()
+    S.close()
