@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — the hot-path benchmark (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W              # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's own CPU code (oracle/_ref)
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): forward render of a
+256^3 SH-degree-2 dense grid (synthetic LCG grid of SURVEY 8d, density scale D=20), 800x800, 100 orbit
+views of main.cpp:99-102 (360/100 degrees apart).  One STEP = one pass over the 100 views = 64 M rays.
+With N GPUs each rank holds a grid replica and renders its own 100 views of a 100*N-view orbit (views
+interleaved over ranks): per-GPU work fixed => "scaling": "weak", no data-path collective.
+
+  value     Mrays/s with everything resident in HBM (grid, output frames), CUDA events on the launching
+            stream, max over ranks.
+  e2e       same metric through the public host API (RayMarcherExample.kernel2D_RayMarch == lrf_render):
+            per view the camera goes host->device and the finished frame device->pinned host, inside the
+            timed region.
+  roofline  dominant kernel render_image_kernel: algorithmic bytes per launch = 52 B x (distinct grid nodes
+            read by shaded samples of the view, counted on the device) + 4 B x rays, / mean launch time.
+  cpu_baseline  the reference's kernel2D_RayMarch compiled from /root/reference (oracle/_ref/libref_O3.so,
+            -O3 -fopenmp -ffp-contract=off) on the same grid + camera, bounded sample (a 96x96 frame of view 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GS = 256
+W = H = 800
+VIEWS = 100
+DENSITY_SCALE = 20.0
+CPU_SAMPLE = 96          # cpu_baseline / reference arm: one CPU_SAMPLE x CPU_SAMPLE frame per step
+METRIC = "forward_render_Mrays_per_s"
+
+
+def lcg_grid(gs, D):
+    import libs  # numpy generator only (no oracle code is executed by it)
+    return libs.lcg_grid(gs, D)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows]
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, or None"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("render_image_kernel", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+def cameras(pkg, rank, world):
+    proj_inv = pkg.inverse4x4(pkg.perspective(45.0, 1.0, 0.1, 100.0))
+    views = [pkg.inverse4x4(pkg.orbit_view(k * world + rank, VIEWS * world)) for k in range(VIEWS)]
+    return proj_inv, views
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(grid, steps, warmup, quiet=False):
+    """times the reference's own kernel2D_RayMarch (oracle/_ref) — or the oracle port if the reference build is
+    absent — on a CPU_SAMPLE^2 frame of view 0 of the same workload.  Returns (rays_per_s list, info)."""
+    import libs
+    from libs import fp, u32p, np_view
+    n = CPU_SAMPLE * CPU_SAMPLE
+    out = np.zeros(n, np.uint32)
+    rates = []
+    if libs.have_ref("O3"):
+        R = libs.ref("O3")
+        kind, cores = "reference", R.ref_omp_threads()
+        h = R.ref_create()
+        R.ref_init_grid(h, GS)   # builds the 255^3-box octree (~15 s, not timed: setup, like InitGrid in main.cpp)
+        np_view(R.ref_grid_ptr(h), GS ** 3 * 13)[:] = grid.ravel()
+        proj, view = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        R.ref_make_perspective(45.0, 1.0, 0.1, 100.0, fp(proj))
+        R.ref_make_orbit_view(0, VIEWS, fp(view))
+        R.ref_set_proj_matrix(h, fp(proj))
+        R.ref_set_view_matrix(h, fp(view))
+        run = lambda: R.ref_render(h, u32p(out), CPU_SAMPLE, CPU_SAMPLE, 0)
+        what = "oracle/_ref/libref_O3.so: reference example_tracer.cpp compiled -O3 -fopenmp -ffp-contract=off"
+    else:
+        O = libs.oracle()
+        kind, cores = "port", O.orc_omp_threads()
+        h = O.orc_create(GS)
+        np_view(O.orc_grid_ptr(h), GS ** 3 * 13)[:] = grid.ravel()
+        proj, view, vi, pi = (np.zeros(16, np.float32) for _ in range(4))
+        O.orc_perspective(45.0, 1.0, 0.1, 100.0, fp(proj))
+        O.orc_orbit_view(0, VIEWS, fp(view))
+        O.orc_inverse4x4(fp(view), fp(vi))
+        O.orc_inverse4x4(fp(proj), fp(pi))
+        O.orc_set_view_inv(h, fp(vi))
+        O.orc_set_proj_inv(h, fp(pi))
+        run = lambda: O.orc_render(h, u32p(out), CPU_SAMPLE, CPU_SAMPLE, 0)
+        what = "oracle/_build/liblrf_oracle.so: CPU restatement (reference build absent)"
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            rates.append(n / dt)
+    info = {"kind": kind, "cores": int(cores),
+            "sample": "%dx%d frame of orbit view 0 (%d rays) per step on the %d^3 D=%g grid, %d timed step(s); %s" % (CPU_SAMPLE, CPU_SAMPLE, n, GS, DENSITY_SCALE, steps, what)}
+    return rates, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    grid = lcg_grid(GS, DENSITY_SCALE)
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    rates, info = cpu_reference_rate(grid, steps, warmup)
+    n = CPU_SAMPLE * CPU_SAMPLE
+    total_t = sum(n / r for r in rates)
+    value = n * len(rates) / total_t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * total_t / len(rates), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(1),
+        "cpu_baseline": dict(info, value=value, unit="Mrays/s"),
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(world):
+    return {"workload": "forward render, dense %d^3 SH-degree-2 grid (13 fp32/node, synthetic LCG, density scale %g), %dx%d, %d orbit views per GPU (BASELINE.json configs[1])"
+            % (GS, DENSITY_SCALE, W, H, VIEWS),
+            "grid": GS, "width": W, "height": H, "views_per_gpu": VIEWS, "rays_per_step_per_gpu": W * H * VIEWS,
+            "density_scale": DENSITY_SCALE, "parallelism": "views sharded over %d GPU(s), grid replica per GPU, no collective" % world,
+            "l2": "inputs exceed L2: the 872 MB grid is re-read by every view (L2 = 126 MB); no explicit flush needed"}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the (extra) training-iteration measurement")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import __graft_entry__ as ge
+    pkg = ge.package()
+    t = pkg.RayMarcherExample(local)          # raises if the CUDA library / a B200 is missing: no fallback
+    t.InitGrid(GS)
+    t.SetBoundingBox([0, 0, 0], [1, 1, 1])
+    grid = lcg_grid(GS, DENSITY_SCALE)
+    t.set_grid(grid)
+    proj_inv, views = cameras(pkg, rank, world)
+    t.set_proj_inv(proj_inv)
+    frame = pkg.DeviceBuffer(t, W * H * 4)
+
+    def barrier():
+        t.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        v = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    # ---- value: device-resident ----
+    def step_resident():
+        for vi in views:
+            t.set_view_inv(vi)
+            t.render_dev_async(frame.ptr, W, H)
+
+    for _ in range(warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    time.sleep(0.3)
+    l0 = t.launch_count()
+    tc0 = time.perf_counter()
+    t.timer_start()
+    for _ in range(steps):
+        step_resident()
+    ms = t.timer_stop_ms()
+    tc1 = time.perf_counter()
+    barrier()
+    launches = t.launch_count() - l0
+    clocks = sampler.stop(tc0, tc1)
+    ms = max_over_ranks(ms)
+    rays_per_step = W * H * VIEWS * world
+    value = rays_per_step * steps / (ms * 1e-3) / 1e6
+
+    # ---- e2e: host API, camera h2d + frame d2h per view inside the timed region ----
+    pinned = pkg.PinnedBuffer(W * H, np.uint32)
+    e2e_steps = max(1, min(steps, 2))
+
+    def step_host():
+        for vi in views:
+            t.set_view_inv(vi)                       # host matrices travel as kernel arguments
+            t.kernel2D_RayMarch(pinned.array, W, H)  # kernel + D2H of the frame into pinned host memory, synchronous
+
+    step_host()
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    t.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - te0)
+    checksum = int(pinned.array.astype(np.uint64).sum())
+    e2e_value = rays_per_step * e2e_steps / e2e_s / 1e6
+
+    # ---- roofline of the dominant kernel ----
+    sel = list(range(0, VIEWS, 10))
+    touched = []
+    for k in sel:
+        t.set_view_inv(views[k])
+        touched.append(t.count_touched_nodes(W, H))
+    n_touched = float(np.mean(touched))
+    alg_bytes = 52.0 * n_touched + 4.0 * W * H
+    kernel_ms = ms / (steps * VIEWS)               # launches are back to back on one stream: mean launch duration
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                "kernel": "render_image_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "n_touched_nodes_mean": n_touched, "n_touched_sampled_views": len(sel), "peak_source": peak_src}
+
+    extra = {"e2e_checksum": checksum}
+    if not args.no_train:
+        try:
+            extra["train"] = train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier)
+        except Exception as e:  # the headline line must still be printed
+            extra["train"] = {"error": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": VIEWS * 2 * 64, "d2h_bytes_per_step": VIEWS * W * H * 4, "steps": e2e_steps},
+        "gpu_launches": int(launches), "roofline": roofline, "extra": extra,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rates, info = cpu_reference_rate(grid, 2, 1)
+            line["cpu_baseline"] = dict(info, value=float(np.mean(rates)) / 1e6, unit="Mrays/s")
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier, iters=20, batch=4096):
+    """BASELINE.json configs[2]: grid optimisation on the 256^3 grid, 4096-ray batches per GPU against synthetic targets:
+    one iteration = ray generation + backward(4096 rays) [+ NCCL all-reduce of the 13*N-float gradient] + TV + Adam + zero."""
+    import ctypes as C
+    n_views = len(views)
+    rng = np.random.default_rng(1234 + rank)
+    vi_dev = pkg.DeviceBuffer(t, n_views * 64)
+    vi_dev.upload(np.stack(views).astype(np.float32))
+    picks = np.stack([rng.integers(0, n_views, (iters + 3) * batch), rng.integers(0, W * H, (iters + 3) * batch)], axis=1).astype(np.uint32)
+    picks_dev = pkg.DeviceBuffer(t, picks.nbytes)
+    picks_dev.upload(picks)
+    ref = rng.random(((iters + 3) * batch, 4)).astype(np.float32)   # synthetic target colours
+    ref_dev = pkg.DeviceBuffer(t, ref.nbytes)
+    ref_dev.upload(ref)
+    o_dev, d_dev = pkg.DeviceBuffer(t, batch * 12), pkg.DeviceBuffer(t, batch * 12)
+    t.optimizerInit()
+    t.zeroGrad()
+    grad_tensor = None
+    if dist is not None:
+        import torch
+        n = t.lib.lrf_param_count(t.h)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (t.lib.lrf_grad_device_ptr(t.h), False), "version": 2}
+        grad_tensor = torch.as_tensor(_Arr(), device="cuda")
+        ext = torch.cuda.ExternalStream(t.lib.lrf_stream(t.h))
+
+    def one(it):
+        off = it * batch
+        t._ck(t.lib.lrf_gen_rays_dev_async(t.h, batch, vi_dev.ptr, picks_dev.ptr + off * 8, W, H, o_dev.ptr, d_dev.ptr))
+        t._ck(t.lib.lrf_rays_grad_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
+        if grad_tensor is not None:
+            import torch
+            with torch.cuda.stream(ext):
+                dist.all_reduce(grad_tensor)
+        t._ck(t.lib.lrf_train_percell_async(t.h, it))
+
+    for it in range(3):
+        one(it)
+    barrier()
+    t.timer_start()
+    for it in range(3, 3 + iters):
+        one(it)
+    ms = max_over_ranks(t.timer_stop_ms())
+    barrier()
+    # break-down: backward alone / per-cell alone
+    t.timer_start()
+    for it in range(5):
+        t._ck(t.lib.lrf_rays_grad_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr, 0))
+    ms_bwd = t.timer_stop_ms() / 5
+    t.timer_start()
+    for it in range(5):
+        t._ck(t.lib.lrf_train_percell_async(t.h, 100 + it))
+    ms_cell = t.timer_stop_ms() / 5
+    N = GS ** 3
+    peak, _ = measured_peak()
+    out = {"metric": "train_iters_per_s", "value": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "rays_per_iter": batch * world, "n_gpus": world,
+           "ms_backward_4096_rays": ms_bwd, "ms_percell_tv_adam_zero": ms_cell,
+           "percell_algorithmic_bytes": 416.0 * N + 12.0 * N, "percell_frac_of_hbm_peak": (428.0 * N / (ms_cell * 1e-3) / 1e9) / peak,
+           "allreduce": "NCCL all_reduce of 13*N fp32 gradient (%d MB) per iteration" % (52 * N // 2 ** 20) if world > 1 else "none (1 GPU)"}
+    for b in (vi_dev, picks_dev, ref_dev, o_dev, d_dev):
+        b.free()
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -134,6 +134,11 @@ int lrf_rebuild_boxes(lrf_ctx *h);
 /* ref: GetExecutionTime(const char*, float[4]), example_tracer.cpp:759-763.  name in {"RayMarch",
  * "RayMarchGrad","TVGrad","Adam"}: out[0] = device ms of the last such call (CUDA events). */
 int lrf_last_time_ms(lrf_ctx *h, const char *name, float out[4]);
+/* CUDA-event stopwatch on the context stream (the stream every kernel of this context is launched on):
+ * lrf_timer_start records an event; lrf_timer_stop_ms records a second one, waits for it and returns the
+ * elapsed device time in milliseconds. */
+int lrf_timer_start(lrf_ctx *h);
+int lrf_timer_stop_ms(lrf_ctx *h, float *ms);
 /* device pointers of the parameter / gradient storage in DEVICE layout (density plane [gs^3] followed by
  * colour plane [gs^3 x 12]) for NCCL all-reduce by the multi-GPU harness; n_floats = 13*gs^3 */
 float *lrf_param_device_ptr(lrf_ctx *h);

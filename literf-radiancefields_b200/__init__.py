@@ -65,6 +65,8 @@ SIGNATURES = {
     "lrf_upsample_boxes": (C.c_int, [_vp]),
     "lrf_rebuild_boxes": (C.c_int, [_vp]),
     "lrf_last_time_ms": (C.c_int, [_vp, C.c_char_p, _c_fp]),
+    "lrf_timer_start": (C.c_int, [_vp]),
+    "lrf_timer_stop_ms": (C.c_int, [_vp, _c_fp]),
     "lrf_param_device_ptr": (_vp, [_vp]),
     "lrf_grad_device_ptr": (_vp, [_vp]),
     "lrf_param_count": (C.c_size_t, [_vp]),
@@ -386,6 +388,14 @@ class RayMarcherExample:
 
     def RebuildOctree(self):
         self._ck(self.lib.lrf_rebuild_boxes(self.h))
+
+    def timer_start(self):
+        self._ck(self.lib.lrf_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.lrf_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return self.lib.lrf_launch_count(self.h)

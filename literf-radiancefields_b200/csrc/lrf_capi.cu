@@ -33,7 +33,7 @@ struct lrf_ctx
   float lr = 0.15f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8;   // example_tracer.h:120-123
   cudaStream_t stream = nullptr;
   bool own_stream = true;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
   float t_march = 0, t_grad = 0, t_tv = 0, t_adam = 0;
   uint64_t launches = 0;
   // staging
@@ -133,6 +133,8 @@ int lrf_create(int device, lrf_ctx **out)
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  CK(cudaEventCreate(&h->tm0));
+  CK(cudaEventCreate(&h->tm1));
   // defaults of the reference constructor (example_tracer.h:43-49): caller overrides through the setters
   for (int i = 0; i < 16; i++) h->view_inv[i] = h->proj_inv[i] = (i % 5 == 0) ? 1.0f : 0.0f;
   *out = h;
@@ -146,7 +148,7 @@ int lrf_destroy(lrf_ctx *h)
   cudaStreamSynchronize(h->stream);
   free_grid(h);
   cudaFree(h->stage);
-  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -575,6 +577,15 @@ int lrf_last_time_ms(lrf_ctx *h, const char *name, float out[4])
   else if (s == "TVGrad") out[0] = h->t_tv;
   else if (s == "Adam") out[0] = h->t_adam;
   else return fail("unknown timer name");
+  return 0;
+}
+int lrf_timer_start(lrf_ctx *h) { NEED(h); CK(cudaEventRecord(h->tm0, h->stream)); return 0; }
+int lrf_timer_stop_ms(lrf_ctx *h, float *ms)
+{
+  NEED(h);
+  CK(cudaEventRecord(h->tm1, h->stream));
+  CK(cudaEventSynchronize(h->tm1));
+  CK(cudaEventElapsedTime(ms, h->tm0, h->tm1));
   return 0;
 }
 float *lrf_param_device_ptr(lrf_ctx *h) { return h ? h->params : nullptr; }

@@ -125,6 +125,144 @@ __device__ __forceinline__ void colour_from(const float *acc, const float *Y, fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Register window over the 2x2x2 nodes of the current voxel.
+//
+// Consecutive samples of a ray sit in face-adjacent voxels and share 4 of their 8 nodes, so re-gathering
+// all 8 x 52 B per sample doubles the L1 traffic — and the first ncu capture of this kernel shows the L1
+// data pipe (l1tex__data_pipe_lsu_wavefronts) at 88 % with DRAM at 1 %: the gather, not HBM, is the bound.
+// The window keeps, per node, the density and the colour contracted with this ray's SH basis
+// {R, G, B, q = sum_j sh_j Y_j(d)} in registers.  A node lives in the slot given by the PARITY of its
+// coordinates (slot = x&1 | (y&1)<<1 | (z&1)<<2): when the ray moves to a face-adjacent voxel the 4 nodes
+// that stay keep their slots and the 4 new ones have exactly the parities of the 4 that leave, so nothing
+// is ever moved between registers — only (predicated) loads into the slots whose coordinates changed, and
+// the interpolation weights are permuted instead of the values.  Any transition (first sample, the 3/7-voxel
+// tie events, gaps of a sparse box set) is handled by the same compare-and-reload.
+struct Window
+{
+  float d[8];
+  float r[8], g[8], b[8], q[8];
+  int cd[3][2];   // node coordinate currently held by parity 0 / 1 along each axis (density part)
+  int cc[3][2];   // same for the colour part (loaded lazily: only samples with a non-zero weight need it)
+  __device__ __forceinline__ void reset()
+  {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { cd[a][0] = cd[a][1] = cc[a][0] = cc[a][1] = -4; }
+  }
+};
+
+// coordinates of the voxel's two nodes along one axis, by parity: parity-0 slot holds v + (v&1), parity-1 slot v + 1 - (v&1)
+__device__ __forceinline__ void window_density(const SceneDev &S, Window &W, int x, int y, int z)
+{
+  const int v[3] = {x, y, z};
+  int req[3][2];
+  bool chg[3][2];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    req[a][0] = v[a] + (v[a] & 1);
+    req[a][1] = v[a] + 1 - (v[a] & 1);
+    chg[a][0] = W.cd[a][0] != req[a][0];
+    chg[a][1] = W.cd[a][1] != req[a][1];
+    W.cd[a][0] = req[a][0];
+    W.cd[a][1] = req[a][1];
+  }
+  const uint32_t gs = S.gs, gs2 = (uint32_t)S.gs * S.gs;
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
+    if (chg[0][sx] | chg[1][sy] | chg[2][sz])
+      W.d[s] = __ldg(S.dens + (uint32_t)req[0][sx] + (uint32_t)req[1][sy] * gs + (uint32_t)req[2][sz] * gs2);
+  }
+}
+
+// trilinear density from the window: nested lerps in the reference's order (:155-167 via lerpCell :72-80), bit-exact.
+// near/far along an axis = parity slot (v&1) / the other one.
+__device__ __forceinline__ float window_density_lerp(const Window &W, const SampleGeom &g, int x, int y, int z)
+{
+  const bool ox = x & 1, oy = y & 1, oz = z & 1;
+  float A[4];  // x-lerped, indexed by (sy, sz) parity
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float p0 = W.d[2 * j], p1 = W.d[2 * j + 1];
+    A[j] = lm_lerp(ox ? p1 : p0, ox ? p0 : p1, g.lf[0]);
+  }
+  float B[2];  // y-lerped, indexed by sz parity
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const float p0 = A[2 * j], p1 = A[2 * j + 1];
+    B[j] = lm_lerp(oy ? p1 : p0, oy ? p0 : p1, g.lf[1]);
+  }
+  return lm_lerp(oz ? B[1] : B[0], oz ? B[0] : B[1], g.lf[2]);
+}
+
+// interpolation weight of each parity slot (explicit-FMA colour path; also the scatter weights of the backward)
+__device__ __forceinline__ void window_weights(const SampleGeom &g, int x, int y, int z, float *w)
+{
+  const float fx = g.lf[0], fy = g.lf[1], fz = g.lf[2];
+  const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+  const bool ox = x & 1, oy = y & 1, oz = z & 1;
+  const float wx0 = ox ? fx : gx, wx1 = ox ? gx : fx;
+  const float wy0 = oy ? fy : gy, wy1 = oy ? gy : fy;
+  const float wz0 = oz ? fz : gz, wz1 = oz ? gz : fz;
+  const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+  w[0] = w00 * wz0; w[1] = w10 * wz0; w[2] = w01 * wz0; w[3] = w11 * wz0;
+  w[4] = w00 * wz1; w[5] = w10 * wz1; w[6] = w01 * wz1; w[7] = w11 * wz1;
+}
+
+// node index held by parity slot s for voxel (x,y,z)
+__device__ __forceinline__ uint32_t window_node(const SceneDev &S, int s, int x, int y, int z)
+{
+  const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
+  const int cx = sx ? x + 1 - (x & 1) : x + (x & 1), cy = sy ? y + 1 - (y & 1) : y + (y & 1), cz = sz ? z + 1 - (z & 1) : z + (z & 1);
+  return (uint32_t)cx + (uint32_t)cy * S.gs + (uint32_t)cz * S.gs * S.gs;
+}
+
+// bring the colour part of the window to voxel (x,y,z): load the nodes whose coordinates changed, contracting the 9 SH
+// coefficients with this ray's basis on the fly
+__device__ __forceinline__ void window_colour(const SceneDev &S, Window &W, const float *Y, int x, int y, int z)
+{
+  const int v[3] = {x, y, z};
+  int req[3][2];
+  bool chg[3][2];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    req[a][0] = v[a] + (v[a] & 1);
+    req[a][1] = v[a] + 1 - (v[a] & 1);
+    chg[a][0] = W.cc[a][0] != req[a][0];
+    chg[a][1] = W.cc[a][1] != req[a][1];
+    W.cc[a][0] = req[a][0];
+    W.cc[a][1] = req[a][1];
+  }
+  const uint32_t gs = S.gs, gs2 = (uint32_t)S.gs * S.gs;
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
+    if (chg[0][sx] | chg[1][sy] | chg[2][sz]) {
+      const uint32_t idx = (uint32_t)req[0][sx] + (uint32_t)req[1][sy] * gs + (uint32_t)req[2][sz] * gs2;
+      const float4 *p = S.col + (size_t)idx * kColF4;
+      const float4 a = __ldg(p), b = __ldg(p + 1), e = __ldg(p + 2);
+      float qq = a.w * Y[0];
+      qq = fmaf(b.x, Y[1], qq); qq = fmaf(b.y, Y[2], qq); qq = fmaf(b.z, Y[3], qq); qq = fmaf(b.w, Y[4], qq);
+      qq = fmaf(e.x, Y[5], qq); qq = fmaf(e.y, Y[6], qq); qq = fmaf(e.z, Y[7], qq); qq = fmaf(e.w, Y[8], qq);
+      W.r[s] = a.x; W.g[s] = a.y; W.b[s] = a.z; W.q[s] = qq;
+    }
+  }
+}
+
+// weighted sums over the window + clamps (ref :181-184): rgbi = interpolated RGB, raw = interpolated sh . Y
+__device__ __forceinline__ void window_colour_eval(const Window &W, const float *w, float *rgbi, float &raw, float &s, float *c)
+{
+  float R = 0.0f, G = 0.0f, B = 0.0f, Q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    R = fmaf(w[k], W.r[k], R); G = fmaf(w[k], W.g[k], G); B = fmaf(w[k], W.b[k], B); Q = fmaf(w[k], W.q[k], Q);
+  }
+  rgbi[0] = R; rgbi[1] = G; rgbi[2] = B;
+  raw = Q;
+  s = lm_clamp(Q, 0.0f, 1.0f);
+  c[0] = lm_clamp(R * s, 0.0f, 1.0f); c[1] = lm_clamp(G * s, 0.0f, 1.0f); c[2] = lm_clamp(B * s, 0.0f, 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward visitor.  MODE 0: render (stop at the reference's throughput break);  MODE 1: parity taps
 // (keeps marching after the break to count every hit, records voxels / cauchy / touched nodes)
 template <int MODE> struct ShadeVisitor
@@ -141,8 +279,9 @@ template <int MODE> struct ShadeVisitor
   int32_t *vox = nullptr;
   uint32_t keep = 0;
   uint8_t *touched = nullptr;
+  Window W;
 
-  __device__ ShadeVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) {}
+  __device__ ShadeVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) { W.reset(); }
 
   __device__ __forceinline__ bool sample(int x, int y, int z)
   {
@@ -153,7 +292,8 @@ template <int MODE> struct ShadeVisitor
     } else n_hit = 1;
     SampleGeom g;
     sample_geom(S, R, x, y, z, tPrev, g);
-    float sigma = density_at(S, g);
+    window_density(S, W, x, y, z);
+    float sigma = window_density_lerp(W, g, x, y, z);
     if (sigma < 0.0f) sigma = 0.0f;                          // :170-171
     if (MODE == 1) {
       cauchy += logf(1.0f + 2.0f * sigma * sigma);           // :173 (value only feeds the loss; tolerance-compared)
@@ -168,10 +308,10 @@ template <int MODE> struct ShadeVisitor
     if (wgt != 0.0f) {                                       // wgt == 0 adds exactly 0 to a finite colour: skip the gather
       if (grey) { col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt; }
       else {
-        float w[8], acc[12], raw, s, c[3];
-        corner_weights(g, w);
-        colour_at(S, g, w, acc);
-        colour_from(acc, R.Y, raw, s, c);
+        float w[8], rgbi[3], raw, s, c[3];
+        window_colour(S, W, R.Y, x, y, z);
+        window_weights(g, x, y, z, w);
+        window_colour_eval(W, w, rgbi, raw, s, c);
         col[0] = col[0] + wgt * c[0]; col[1] = col[1] + wgt * c[1]; col[2] = col[2] + wgt * c[2];
       }
     }
@@ -278,22 +418,24 @@ struct FwdAVisitor
   double csum[3] = {0.0, 0.0, 0.0};
   float col[3] = {0.0f, 0.0f, 0.0f};
   uint32_t n_shaded = 0;
-  __device__ FwdAVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) {}
+  Window W;
+  __device__ FwdAVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) { W.reset(); }
   __device__ __forceinline__ bool sample(int x, int y, int z)
   {
     SampleGeom g;
     sample_geom(S, R, x, y, z, tPrev, g);
-    float sigma = density_at(S, g);
+    window_density(S, W, x, y, z);
+    float sigma = window_density_lerp(W, g, x, y, z);
     if (sigma < 0.0f) sigma = 0.0f;
     const float tr = expf_libm(-sigma * g.delta, etab);
     const float wgt = thr * (1.0f - tr);
     if (wgt != 0.0f) {
       float c[3] = {1.0f, 1.0f, 1.0f};
       if (!grey) {
-        float w[8], acc[12], raw, s;
-        corner_weights(g, w);
-        colour_at(S, g, w, acc);
-        colour_from(acc, R.Y, raw, s, c);
+        float w[8], rgbi[3], raw, s;
+        window_colour(S, W, R.Y, x, y, z);
+        window_weights(g, x, y, z, w);
+        window_colour_eval(W, w, rgbi, raw, s, c);
       }
 #pragma unroll
       for (int ch = 0; ch < 3; ch++) {
@@ -326,12 +468,14 @@ struct BwdVisitor
   double ctot[3];
   float aC[3], aTn, Tn;
   uint32_t n_total, k = 0;
-  __device__ BwdVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) {}
+  Window W;
+  __device__ BwdVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) { W.reset(); }
   __device__ __forceinline__ bool sample(int x, int y, int z)
   {
     SampleGeom g;
     sample_geom(S, R, x, y, z, tPrev, g);
-    const float dens_raw = density_at(S, g);
+    window_density(S, W, x, y, z);
+    const float dens_raw = window_density_lerp(W, g, x, y, z);
     const bool last = (k + 1 == n_total);
     if (dens_raw < 0.0f) {  // relu closed: sigma = 0, tr = exp(-0) = 1, weight 0 -> no adjoint reaches the grid (:170-171)
       k++;
@@ -341,12 +485,12 @@ struct BwdVisitor
     const float tr = expf_libm(-sigma * g.delta, etab);
     const float wgt = thr * (1.0f - tr);
     float w[8];
-    corner_weights(g, w);
+    window_weights(g, x, y, z, w);
     // the colour is needed even when wgt == 0: d colour / d tr = -T_k c_k does not vanish with (1 - tr)
-    float c[3] = {1.0f, 1.0f, 1.0f}, acc[12], raw = 0.0f, s = 0.0f;
+    float c[3] = {1.0f, 1.0f, 1.0f}, acc[3] = {0.0f, 0.0f, 0.0f}, raw = 0.0f, s = 0.0f;
     if (!grey) {
-      colour_at(S, g, w, acc);
-      colour_from(acc, R.Y, raw, s, c);
+      window_colour(S, W, R.Y, x, y, z);
+      window_colour_eval(W, w, acc, raw, s, c);
     }
     if (wgt != 0.0f) {
 #pragma unroll
@@ -362,11 +506,9 @@ struct BwdVisitor
     // d tr / d sigma = -delta * tr ;  cauchy: d/dsigma log(1 + 2 sigma^2) = 4 sigma / (1 + 2 sigma^2), weight 0.0005 (:267)
     const float a_sigma = -g.delta * tr * a_tr + 0.0005f * (4.0f * sigma / (1.0f + 2.0f * sigma * sigma));
     const float a_dens = a_sigma;                              // relu passes iff density >= 0 (:170)
-    const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
     if (a_dens != 0.0f) {
 #pragma unroll
-      for (int cn = 0; cn < 8; cn++)
-        red_add(S.gdens + g.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz, w[cn] * a_dens);
+      for (int cn = 0; cn < 8; cn++) red_add(S.gdens + window_node(S, cn, x, y, z), w[cn] * a_dens);
     }
     if (!grey && wgt != 0.0f) {
       float a_rgb[3] = {0.0f, 0.0f, 0.0f}, a_s = 0.0f;
@@ -383,8 +525,7 @@ struct BwdVisitor
         for (int j = 0; j < 9; j++) a_sh[j] = R.Y[j] * a_raw;
 #pragma unroll
         for (int cn = 0; cn < 8; cn++) {
-          const uint32_t idx = g.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz;
-          float4 *q = S.gcol + (size_t)idx * kColF4;
+          float4 *q = S.gcol + (size_t)window_node(S, cn, x, y, z) * kColF4;
           const float ww = w[cn];
           red_add4(q, ww * a_rgb[0], ww * a_rgb[1], ww * a_rgb[2], ww * a_sh[0]);
           red_add4(q + 1, ww * a_sh[1], ww * a_sh[2], ww * a_sh[3], ww * a_sh[4]);

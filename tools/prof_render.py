@@ -1,0 +1,30 @@
+"""Small driver for ncu captures: renders a few 800x800 views of the bench workload (256^3, D=20) and,
+optionally, one training iteration.  Usage: python tools/prof_render.py [n_views] [--train]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as ge
+import bench
+
+pkg = ge.package()
+n_views = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4
+t = pkg.RayMarcherExample(0)
+t.InitGrid(bench.GS)
+grid = bench.lcg_grid(bench.GS, bench.DENSITY_SCALE)
+t.set_grid(grid)
+proj_inv, views = bench.cameras(pkg, 0, 1)
+t.set_proj_inv(proj_inv)
+frame = pkg.DeviceBuffer(t, bench.W * bench.H * 4)
+for k in range(n_views):
+    t.set_view_inv(views[(k * 13) % len(views)])
+    t.render_dev_async(frame.ptr, bench.W, bench.H)
+t.sync()
+if "--train" in sys.argv:
+    r = bench.train_bench(pkg, t, grid, views, proj_inv, 0, 1, None, lambda x: x, t.sync, iters=2)
+    print(r)
+print("done")
