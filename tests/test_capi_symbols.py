@@ -1,0 +1,47 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/lrf.h declares (no compute calls here);
+the ctypes binding table covers the same set; constructing a tracer without a CUDA device fails loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "lrf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lrf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound(pkg):
+    import __graft_entry__ as ge
+    ge.build()
+    syms = declared_symbols()
+    assert len(syms) >= 50
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(pkg.SIGNATURES) == syms, set(pkg.SIGNATURES) ^ set(syms)
+    pkg.load_library()
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.LrfError, match="no CUDA device|CPU fallback"):
+        pkg.RayMarcherExample(0)
+
+
+def test_product_never_touches_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use oracle/"""
+    pkg_dir = os.path.join(ROOT, "literf-radiancefields_b200")
+    for dp_, _, files in os.walk(pkg_dir):
+        if "_build" in dp_:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp_, f)).read()
+                assert "lrf_oracle" not in txt and "oracle/" not in txt.replace("no oracle", ""), os.path.join(dp_, f)
