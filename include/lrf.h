@@ -155,6 +155,9 @@ int lrf_memcpy_d2h_async(lrf_ctx *h, void *dst_host, const void *src_dev, size_t
 /* counters the benchmark reports: kernels launched by this context since creation; distinct nodes
  * read by the last lrf_count_touched call */
 uint64_t lrf_launch_count(lrf_ctx *h);
+/* test / diagnostic switches.  "force_generic_march" = 1: the parity taps (lrf_render_debug, lrf_trace_rays) send every
+ * ray down the generic exact march instead of the streamlined one, so that tests can compare the two. */
+int lrf_set_option(lrf_ctx *h, const char *name, int value);
 int lrf_count_touched_nodes(lrf_ctx *h, uint32_t width, uint32_t height, int greyscale, uint64_t *out);
 
 #ifdef __cplusplus

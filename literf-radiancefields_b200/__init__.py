@@ -79,6 +79,7 @@ SIGNATURES = {
     "lrf_memcpy_h2d_async": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "lrf_memcpy_d2h_async": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "lrf_launch_count": (C.c_uint64, [_vp]),
+    "lrf_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lrf_count_touched_nodes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
 }
 
@@ -396,6 +397,9 @@ class RayMarcherExample:
         ms = C.c_float(0)
         self._ck(self.lib.lrf_timer_stop_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def set_option(self, name, value):
+        self._ck(self.lib.lrf_set_option(self.h, name.encode(), int(value)))
 
     def launch_count(self):
         return self.lib.lrf_launch_count(self.h)

@@ -39,6 +39,10 @@ struct lrf_ctx
   // staging
   void *stage = nullptr;
   size_t stage_bytes = 0;
+  // fallback queue of the forward render (rays that need the generic march): [0] = count, [1..] = pixel indices
+  uint32_t *fb = nullptr;
+  size_t fb_cap = 0;
+  int force_generic = 0;   // parity taps: 1 = generic march for every ray (tests compare both paths)
 };
 
 static thread_local std::string g_err;
@@ -58,6 +62,16 @@ static int ensure_stage(lrf_ctx *h, size_t bytes)
   h->stage = nullptr; h->stage_bytes = 0;
   CK(cudaMalloc(&h->stage, bytes));
   h->stage_bytes = bytes;
+  return 0;
+}
+
+static int ensure_fb(lrf_ctx *h, size_t rays)
+{
+  if (h->fb_cap >= rays) return 0;
+  if (h->fb) cudaFree(h->fb);
+  h->fb = nullptr; h->fb_cap = 0;
+  CK(cudaMalloc(&h->fb, (rays + 4) * sizeof(uint32_t)));
+  h->fb_cap = rays;
   return 0;
 }
 
@@ -148,6 +162,7 @@ int lrf_destroy(lrf_ctx *h)
   cudaStreamSynchronize(h->stream);
   free_grid(h);
   cudaFree(h->stage);
+  cudaFree(h->fb);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -280,8 +295,9 @@ int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt
 {
   NEED_GRID(h);
   if (w == 0 || hgt == 0) return 0;
-  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->stream);
-  h->launches++;
+  if (ensure_fb(h, (size_t)w * hgt)) return 1;
+  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + 4, h->stream);
+  h->launches += 2;   // render_image_kernel + render_fallback_kernel
   CK(cudaGetLastError());
   return 0;
 }
@@ -321,8 +337,8 @@ static int run_debug(lrf_ctx *h, bool image, uint32_t w, uint32_t hgt, size_t n,
   if (!image) {
     CK(cudaMemcpyAsync(o_dev, o, b_o, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_dev, d, b_o, cudaMemcpyHostToDevice, h->stream));
-    launch_debug_rays(scene_of(h), rays, o_dev, d_dev, grey, taps, h->stream);
-  } else launch_debug_image(scene_of(h), w, hgt, grey, taps, h->stream);
+    launch_debug_rays(scene_of(h), rays, o_dev, d_dev, grey, taps, h->force_generic, h->stream);
+  } else launch_debug_image(scene_of(h), w, hgt, grey, taps, h->force_generic, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   if (n_hit) CK(cudaMemcpyAsync(n_hit, taps.n_hit, b_nh, cudaMemcpyDeviceToHost, h->stream));
@@ -608,6 +624,14 @@ int lrf_host_free_pinned(void *p) { CK(cudaFreeHost(p)); return 0; }
 int lrf_memcpy_h2d_async(lrf_ctx *h, void *dst, const void *src, size_t bytes) { NEED(h); CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream)); return 0; }
 int lrf_memcpy_d2h_async(lrf_ctx *h, void *dst, const void *src, size_t bytes) { NEED(h); CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream)); return 0; }
 uint64_t lrf_launch_count(lrf_ctx *h) { return h ? h->launches : 0; }
+int lrf_set_option(lrf_ctx *h, const char *name, int value)
+{
+  NEED(h);
+  const std::string s(name ? name : "");
+  if (s == "force_generic_march") h->force_generic = value ? 1 : 0;
+  else return fail("unknown option: " + s);
+  return 0;
+}
 
 // ---- caller-side camera helpers (host arithmetic, compiled without FMA contraction) ----
 static void hm_mul_vec(float *res, const float *B, const float *V)   // LiteMath.h:1362-1368

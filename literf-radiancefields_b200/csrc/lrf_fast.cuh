@@ -1,0 +1,493 @@
+// lrf_fast.cuh — the streamlined forward ray march (render + parity taps) for rays whose three direction
+// components are all non-zero with a finite reciprocal (every ray of a perspective image except, at most, a
+// centre row/column; the rest take the generic path of lrf_device.cuh through a fallback queue).
+//
+// Same results as the generic march (bit-exact hit set, order, shaded-sample count, transmittance; RGB to the
+// 1e-4 tolerance), about a third of the instructions per sample.  What changed, and why it is still exact:
+//
+//  * Traversal decisions are taken on the fp32 slab times the shading needs anyway.  The reference shades
+//    box (x,y,z) with  t_a(j) = (1.0f/d_a) * (j/gs - o_a)  for its two planes per axis (RayBoxIntersection,
+//    ref example_tracer.cpp:18-43); it ORDERS boxes by the fp64 quotients  T_a(j) = (j/gs - o_a) / d_a
+//    (IsRayHit, ref external/Octree/octree.h:449-488).  t_a(j) carries at most 3 roundings of 2^-24 relative
+//    to T_a(j), so whenever the smallest exit time leads the other two by more than 2^-20 relative, the fp32
+//    order IS the fp64 order and the ray crosses exactly one face: one new box.  Otherwise (about 1 step in
+//    1000) the exact fp64 quotients are formed and compared — the reference's own comparison — and a true tie
+//    (edge / corner grazing: 3 or 7 boxes, ordered by id) is expanded by build_event_cells like in the generic march.
+//  * Per-axis slab times, plane coordinates and the 8 node offsets are carried incrementally: a step along axis a
+//    touches only axis a's entry/exit time and the 4 nodes of the face that leaves.
+//  * The 2x2x2 node window lives in registers, one slot per PARITY of the node coordinates (a face-adjacent
+//    step replaces 4 nodes by 4 nodes of the same parities, so nothing moves between registers); stale slots
+//    are tracked in an 8-bit mask and refilled by predicated loads.  The colour part keeps, per node,
+//    {R, G, B, q = sum_j sh_j Y_j(d)} as two packed fp32 pairs and is contracted / interpolated with the
+//    sm_100 packed-pair FMA (fma.rn.f32x2 -> FFMA2): this is the 1e-4-tolerance path, fused arithmetic is fine.
+//    Everything that feeds a decision (density interpolation, expf, throughput product) stays op-for-op the
+//    reference's unfused fp32 / fp64 sequence.
+#pragma once
+#include "lrf_device.cuh"
+
+namespace lrf {
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// packed-pair fp32 (tolerance path only: ptxas is free to contract mul2 + add2 into FFMA2 even under -fmad=false)
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+struct FastOut
+{
+  float col[3], thr, cauchy;
+  uint32_t n_hit, n_shaded;
+};
+
+// true when the ray can take the fast path
+__device__ __forceinline__ bool fast_path_ok(const float *d)
+{
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float inv = 1.0f / d[a];
+    ok = ok && (d[a] != 0.0f) && (fabsf(inv) < __int_as_float(0x7f800000)) && (d[a] == d[a]);
+  }
+  return ok;
+}
+
+// MODE 0: render (stops at the reference's throughput break, ref example_tracer.cpp:131)
+// MODE 1: parity taps (keeps traversing after the break to count every hit; records voxels, cauchy, touched nodes)
+constexpr int kFastBlock = 128;   // threads per block of the kernels that use FastMarch (shared-memory stride)
+
+template <int MODE, bool SPARSE, bool GREY> struct FastMarch
+{
+  const SceneDev &S;
+  const uint64_t *etab;
+  // ray
+  float o_[3], d_[3], idir_[3];
+  float4 *csm;       // this thread's colour window in shared memory: csm[slot * kFastBlock] = {R, G, B, q = sum_j sh_j Y_j(d)}
+  float *ysm;        // this thread's SH basis in shared memory: ysm[j * kFastBlock], j = 0..8 (frees 9 registers)
+  // traversal state of the CURRENT cell
+  int cell[3];
+  int sgn[3];
+  float pa[3];       // coordinate of the plane through which the ray leaves the current cell
+  float tn[3], tf[3];  // fp32 slab times of the entry / exit plane  ==  min(lo,hi) / max(lo,hi) of RayBoxIntersection
+  // register window: slot s = (x parity) | (y parity) << 1 | (z parity) << 2 of the node coordinates
+  uint32_t nx[2], ny[2], nz[2];   // node index contribution held by parity p of each axis: x, y*gs, z*gs^2
+  float dn[8];
+  uint32_t dirty;    // slots whose registers are stale
+  uint32_t odd;      // parity bits of the cell coordinates
+  // compositing
+  float thr = 1.0f, tPrev = -1.0f, cauchy = 0.0f;
+  float col[3] = {0.0f, 0.0f, 0.0f};
+  uint32_t n_hit = 0, n_shaded = 0;
+  bool alive = true;
+  // taps
+  int32_t *vox = nullptr;
+  uint32_t keep = 0;
+  uint8_t *touched = nullptr;
+
+  __device__ FastMarch(const SceneDev &s, const uint64_t *t, float *ysm_, float4 *csm_) : S(s), etab(t), csm(csm_), ysm(ysm_) {}
+  __device__ __forceinline__ float o(int a) const { return o_[a]; }
+  __device__ __forceinline__ float d(int a) const { return d_[a]; }
+  __device__ __forceinline__ float idir(int a) const { return idir_[a]; }
+
+  __device__ __forceinline__ void init_ray(const float *of, const float *df)
+  {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      o_[a] = of[a];
+      d_[a] = df[a];
+      idir_[a] = 1.0f / df[a];                      // ref example_tracer.cpp:20-22
+      sgn[a] = df[a] > 0.0f ? 1 : -1;
+    }
+    if (!GREY) {
+      float Y[9];
+      sh_eval_2(df, Y);
+#pragma unroll
+      for (int j = 0; j < 9; j++) ysm[j * kFastBlock] = Y[j];
+    }
+  }
+
+  __device__ __forceinline__ uint32_t slot_node(int s) const { return nx[s & 1] + ny[(s >> 1) & 1] + nz[s >> 2]; }
+
+  // bring every piece of per-cell state to cell (x,y,z) from scratch (first cell, tie events, resync after them)
+  __device__ __forceinline__ void set_cell(int x, int y, int z)
+  {
+    const int v[3] = {x, y, z};
+    uint32_t nd[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      cell[a] = v[a];
+      const int ex = v[a] + (sgn[a] > 0 ? 1 : 0), en = v[a] + (sgn[a] > 0 ? 0 : 1);
+      pa[a] = (float)ex * S.inv_gs_f;
+      tf[a] = idir(a) * (pa[a] - o(a));
+      tn[a] = idir(a) * ((float)en * S.inv_gs_f - o(a));
+      nd[a][0] = (uint32_t)(v[a] + (v[a] & 1));
+      nd[a][1] = (uint32_t)(v[a] + 1 - (v[a] & 1));
+    }
+    const uint32_t gs = S.gs, gs2 = (uint32_t)S.gs * S.gs;
+    nx[0] = nd[0][0]; nx[1] = nd[0][1];
+    ny[0] = nd[1][0] * gs; ny[1] = nd[1][1] * gs;
+    nz[0] = nd[2][0] * gs2; nz[1] = nd[2][1] * gs2;
+    dirty = 0xffu;
+    odd = (uint32_t)(x & 1) | ((uint32_t)(y & 1) << 1) | ((uint32_t)(z & 1) << 2);
+  }
+
+  // one face crossing along axis ax (select form: branch-free, the three axes' candidates are computed and the
+  // crossed one is kept); returns the new cell index along that axis
+  __device__ __forceinline__ int advance(int ax)
+  {
+    const bool m0 = ax == 0, m1 = ax == 1, m2 = ax == 2;
+    const bool mm[3] = {m0, m1, m2};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float pan = pa[a] + (sgn[a] > 0 ? S.inv_gs_f : -S.inv_gs_f);   // exact: multiples of 2^-k
+      const float tfn = idir(a) * (pan - o(a));
+      tn[a] = mm[a] ? tf[a] : tn[a];
+      tf[a] = mm[a] ? tfn : tf[a];
+      pa[a] = mm[a] ? pan : pa[a];
+      cell[a] = mm[a] ? cell[a] + sgn[a] : cell[a];
+    }
+    odd ^= 1u << ax;
+    const int csel = m0 ? cell[0] : (m1 ? cell[1] : cell[2]);
+    const int ssel = m0 ? sgn[0] : (m1 ? sgn[1] : sgn[2]);
+    // the node that enters lies on the new exit plane (coordinate csel + [ssel > 0]); it takes the slot of its parity
+    const bool p1 = ((csel + (ssel > 0 ? 1 : 0)) & 1) != 0;
+    const int stride2 = m0 ? 2 : (m1 ? 2 * S.gs : 2 * S.gs * S.gs);
+    const uint32_t delta = (uint32_t)(ssel * stride2);
+    nx[0] += (m0 && !p1) ? delta : 0u; nx[1] += (m0 && p1) ? delta : 0u;
+    ny[0] += (m1 && !p1) ? delta : 0u; ny[1] += (m1 && p1) ? delta : 0u;
+    nz[0] += (m2 && !p1) ? delta : 0u; nz[1] += (m2 && p1) ? delta : 0u;
+    const uint32_t f0 = m0 ? 0x55u : (m1 ? 0x33u : 0x0fu);
+    dirty |= p1 ? (f0 ^ 0xffu) : f0;
+    return csel;
+  }
+
+  // Refill of the stale slots.  A face-adjacent step leaves exactly 4 stale slots and they never include both members
+  // of an antipodal pair (s, 7 - s): a cube face contains one vertex of each of the 4 space diagonals.  So a refill
+  // round runs over the 4 pairs: per pair ONE unconditional node load + SH contraction (no predicated-off work, no
+  // divergent branches), written back into whichever member is stale.  After a full reset (both members stale) a
+  // second round picks up the other members.
+  // The round is split in two halves so that independent work sits between them: issue() starts the loads of the
+  // cell about to be shaded, the march then does that cell's geometry and the whole traversal step to the NEXT cell
+  // (~90 instructions that need no memory), and only then commit() consumes the loads.  That hides most of the
+  // L2 latency of the gathers — the first thing the ncu stall breakdown of the unpipelined version pointed at —
+  // at no cost in registers beyond the in-flight node data.
+  struct NodeLoad
+  {
+    float td;
+    float4 a, b, e;   // {R,G,B,sh0}, {sh1..sh4}, {sh5..sh8}
+  };
+  // bit J of the result: member 7-J of pair J is stale
+  static __device__ __forceinline__ uint32_t high_members(uint32_t stale) { return __brev(stale) >> 24; }
+
+  template <int J> __device__ __forceinline__ void issue_pair(uint32_t stale, NodeLoad &L) const
+  {
+    const bool wA = (stale >> J) & 1u;
+    const uint32_t node = wA ? slot_node(J) : slot_node(7 - J);
+    L.td = __ldg(S.dens + node);
+    if (!GREY) {
+      const float4 *pc = S.col + (size_t)node * kColF4;
+      L.a = __ldg(pc); L.b = __ldg(pc + 1); L.e = __ldg(pc + 2);
+    }
+  }
+  struct Basis
+  {
+    float Y0;
+    u64 Y12, Y34, Y56, Y78;
+  };
+  __device__ __forceinline__ void load_basis(Basis &Y) const
+  {
+    Y.Y0 = ysm[0];
+    Y.Y12 = pk2(ysm[1 * kFastBlock], ysm[2 * kFastBlock]); Y.Y34 = pk2(ysm[3 * kFastBlock], ysm[4 * kFastBlock]);
+    Y.Y56 = pk2(ysm[5 * kFastBlock], ysm[6 * kFastBlock]); Y.Y78 = pk2(ysm[7 * kFastBlock], ysm[8 * kFastBlock]);
+  }
+  // density goes to its register slot; the colour, contracted with this ray's SH basis, to the slot's shared-memory
+  // cell — the slot index is an address there, so no selects and no predicates are needed (a clean pair just rewrites
+  // member 7-J with its own data)
+  template <int J> __device__ __forceinline__ void commit_pair(uint32_t stale, uint32_t hi, const NodeLoad &L, const Basis &Y)
+  {
+    const bool wA = (stale >> J) & 1u, wB = ((hi & ~stale) >> J) & 1u;
+    dn[J] = wA ? L.td : dn[J];
+    dn[7 - J] = wB ? L.td : dn[7 - J];
+    if (GREY) return;
+    u64 q2 = mul2(pk2(L.b.x, L.b.y), Y.Y12);
+    q2 = fma2(pk2(L.b.z, L.b.w), Y.Y34, q2);
+    q2 = fma2(pk2(L.e.x, L.e.y), Y.Y56, q2);
+    q2 = fma2(pk2(L.e.z, L.e.w), Y.Y78, q2);
+    float ql, qh;
+    upk2(q2, ql, qh);
+    const float q = fmaf(L.a.w, Y.Y0, ql + qh);
+    csm[(wA ? J : 7 - J) * kFastBlock] = make_float4(L.a.x, L.a.y, L.a.z, q);
+  }
+  __device__ __forceinline__ void refill_blocking(uint32_t stale)
+  {
+    while (stale) {
+      const uint32_t hi = high_members(stale);
+      NodeLoad L0, L1, L2, L3;
+      issue_pair<0>(stale, L0); issue_pair<1>(stale, L1); issue_pair<2>(stale, L2); issue_pair<3>(stale, L3);
+      Basis Y;
+      if (!GREY) load_basis(Y);
+      commit_pair<0>(stale, hi, L0, Y); commit_pair<1>(stale, hi, L1, Y); commit_pair<2>(stale, hi, L2, Y); commit_pair<3>(stale, hi, L3, Y);
+      // served this round: the low member of each pair if stale, else the high member
+      const uint32_t lowm = stale & 0x0fu;
+      stale &= ~(lowm | (__brev((hi & ~lowm & 0x0fu)) >> 24));
+    }
+  }
+
+  // geometry of the sample in the current cell, ref RayGridIntersection example_tracer.cpp:134-153 (bit-exact)
+  struct Geom
+  {
+    float delta, lf[3];
+    uint32_t odd;   // parity bits of the cell coordinates
+  };
+  __device__ __forceinline__ void geometry(Geom &g)
+  {
+    const float tmin = fmaxf(fmaxf(tn[0], tn[1]), tn[2]);      // all finite: == the std::max / std::min chains of :18-43
+    const float tmax = fminf(fminf(tf[0], tf[1]), tf[2]);
+    if (tPrev < 0.0f) tPrev = tmin;                            // :139
+    const float t = (tmin + tmax) * 0.5f;                      // :142
+    float delta = t - tPrev;                                   // :144
+    if (delta > S.step_gate_f)                                 // :145-146
+      delta = (float)((double)delta - (double)((int)((double)delta / S.step) - 1) * S.step);
+    tPrev = t;                                                 // :190
+    g.delta = delta;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float bmin = sgn[a] > 0 ? pa[a] - S.inv_gs_f : pa[a];   // == (float)cell / (float)gs, exact
+      const float p = o(a) + t * d(a);                         // :148
+      g.lf[a] = (p - bmin) * S.gs_f;                           // :150
+    }
+    g.odd = odd;
+  }
+
+  // shade one sample from the window; false = the reference's throughput break fired
+  __device__ __forceinline__ bool shade(const Geom &g)
+  {
+    const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
+    const float *lf = g.lf;
+    // ---- density: nested lerps in the reference's order (:155-167 via lerpCell :72-80), bit-exact ----
+    float A[4], B[2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float p0 = dn[2 * j], p1 = dn[2 * j + 1];
+      A[j] = lm_lerp(od[0] ? p1 : p0, od[0] ? p0 : p1, lf[0]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const float p0 = A[2 * j], p1 = A[2 * j + 1];
+      B[j] = lm_lerp(od[1] ? p1 : p0, od[1] ? p0 : p1, lf[1]);
+    }
+    float sigma = lm_lerp(od[2] ? B[1] : B[0], od[2] ? B[0] : B[1], lf[2]);
+    if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
+    if (MODE == 1) cauchy += logf(1.0f + 2.0f * sigma * sigma);  // :173
+    const float tr = expf_libm(-sigma * g.delta, etab);        // :175
+    const float wgt = thr * (1.0f - tr);                       // :187
+    if (wgt != 0.0f) {
+      if (GREY) { col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt; }
+      else {
+        // ---- colour: 1e-4-tolerance path, packed-pair FMAs ----
+        const float gx = 1.0f - lf[0], gy = 1.0f - lf[1], gz = 1.0f - lf[2];
+        const float wx0 = od[0] ? lf[0] : gx, wx1 = od[0] ? gx : lf[0];
+        const float wy0 = od[1] ? lf[1] : gy, wy1 = od[1] ? gy : lf[1];
+        const float wz0 = od[2] ? lf[2] : gz, wz1 = od[2] ? gz : lf[2];
+        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+        const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
+        // two independent accumulation chains per pair of channels (latency), merged at the end
+        const float4 c0 = csm[0], c1 = csm[kFastBlock];
+        u64 RG0 = mul2(pk2(w[0], w[0]), pk2(c0.x, c0.y)), BQ0 = mul2(pk2(w[0], w[0]), pk2(c0.z, c0.w));
+        u64 RG1 = mul2(pk2(w[1], w[1]), pk2(c1.x, c1.y)), BQ1 = mul2(pk2(w[1], w[1]), pk2(c1.z, c1.w));
+#pragma unroll
+        for (int k = 2; k < 8; k += 2) {
+          const float4 ca = csm[k * kFastBlock], cb = csm[(k + 1) * kFastBlock];
+          const u64 wk = pk2(w[k], w[k]), wk1 = pk2(w[k + 1], w[k + 1]);
+          RG0 = fma2(wk, pk2(ca.x, ca.y), RG0);
+          BQ0 = fma2(wk, pk2(ca.z, ca.w), BQ0);
+          RG1 = fma2(wk1, pk2(cb.x, cb.y), RG1);
+          BQ1 = fma2(wk1, pk2(cb.z, cb.w), BQ1);
+        }
+        float R, G, Bc, Q, R1, G1, B1, Q1;
+        upk2(RG0, R, G); upk2(BQ0, Bc, Q); upk2(RG1, R1, G1); upk2(BQ1, B1, Q1);
+        R += R1; G += G1; Bc += B1; Q += Q1;
+        const float s = lm_clamp(Q, 0.0f, 1.0f);               // :181
+        col[0] = fmaf(wgt, lm_clamp(R * s, 0.0f, 1.0f), col[0]);  // :182-187
+        col[1] = fmaf(wgt, lm_clamp(G * s, 0.0f, 1.0f), col[1]);
+        col[2] = fmaf(wgt, lm_clamp(Bc * s, 0.0f, 1.0f), col[2]);
+      }
+    }
+    thr *= tr;                                                 // :189
+    n_shaded++;
+    return !(thr < 0.1f);                                      // :131
+  }
+
+  // fp32 filter on the three exit times: the axis whose plane comes first, or -1 when two of them are within the
+  // rounding bound of each other (then the exact fp64 quotients decide)
+  __device__ __forceinline__ int decide_fast() const
+  {
+    const float m = fminf(fminf(tf[0], tf[1]), tf[2]);
+    const float gate = fmaf(fabsf(m), 0x1p-20f, 0x1p-100f);
+    const bool c0 = tf[0] - m <= gate, c1 = tf[1] - m <= gate, c2 = tf[2] - m <= gate;
+    const int ax = c0 ? 0 : (c1 ? 1 : 2);
+    return ((c0 && c1) || (c0 && c2) || (c1 && c2)) ? -1 : ax;
+  }
+
+  // exact comparison of the three exit-plane times (the reference's own fp64 quotients); returns the crossing mask
+  __device__ __forceinline__ int exact_cross() const
+  {
+    double te[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) te[a] = ((double)pa[a] - (double)o(a)) / (double)d(a);
+    const double em = fmin(te[0], fmin(te[1], te[2]));
+    return (te[0] == em ? 1 : 0) | (te[1] == em ? 2 : 0) | (te[2] == em ? 4 : 0);
+  }
+
+  __device__ void run(const float *of, const float *df)
+  {
+    init_ray(of, df);
+    const int n = S.n;
+    // ---- entry: exact fp64, once per ray (same construction as the generic march) ----
+    uint32_t queue[8];
+    int nq = 0;
+    int cur[3];
+    bool leaving_after = false;
+    {
+      const double INF = __longlong_as_double(0x7ff0000000000000LL);
+      double t_enter = -INF, t_exit = INF, od[3], hd[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        od[a] = (double)of[a];
+        hd[a] = (double)df[a];
+        const double T0 = (0.0 - od[a]) / hd[a], Tn = ((double)n * S.inv_gs - od[a]) / hd[a];
+        t_enter = fmax(t_enter, sgn[a] > 0 ? T0 : Tn);
+        t_exit = fmin(t_exit, sgn[a] > 0 ? Tn : T0);
+      }
+      const double t_start = fmax(t_enter, 0.0);
+      if (!(t_exit >= t_start)) return;                        // ref octree.h:483 for the whole lattice
+      int lo[3], two_mask = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const int s = sgn[a];
+        auto Tex = [&](int j) { return ((double)j * S.inv_gs - od[a]) / hd[a]; };
+        int i = (int)floor((od[a] + t_start * hd[a]) * (double)S.gs);
+        i = max(0, min(n - 1, i));
+        for (int it = 0; it < 4; it++) {
+          if (Tex(i + (s > 0 ? 0 : 1)) > t_start && (unsigned)(i - s) < (unsigned)n) { i -= s; continue; }
+          if (Tex(i + (s > 0 ? 1 : 0)) < t_start && (unsigned)(i + s) < (unsigned)n) { i += s; continue; }
+          break;
+        }
+        cur[a] = i;
+        lo[a] = i;
+        if (Tex(i + (s > 0 ? 0 : 1)) == t_start && (unsigned)(i - s) < (unsigned)n) {
+          two_mask |= 1 << a;
+          lo[a] = min(i, i - s);
+        } else if (Tex(i + (s > 0 ? 1 : 0)) == t_start && (unsigned)(i + s) < (unsigned)n) {
+          two_mask |= 1 << a;
+          lo[a] = min(i, i + s);
+          cur[a] = i + s;
+        }
+      }
+      if (two_mask == 0) {
+        if (cell_present(S, lo[0], lo[1], lo[2])) queue[nq++] = pack_cell(lo[0], lo[1], lo[2]);
+      } else {
+        uint32_t cells[8];
+        const int m = build_event_cells(S, lo[0], lo[1], lo[2], two_mask, 0, 0, cells);
+        for (int j = 0; j < m; j++) queue[j] = cells[m - 1 - j];   // popped from the back
+        nq = m;
+      }
+    }
+    const int pos_mask = (sgn[0] > 0 ? 1 : 0) | (sgn[1] > 0 ? 2 : 0) | (sgn[2] > 0 ? 4 : 0);
+    bool resync = true;
+    cell[0] = cell[1] = cell[2] = -8;
+    dirty = 0;
+
+    // moves the traversal to the next cell to be shaded; false = the ray is done
+    auto next_cell = [&]() -> bool {
+      for (;;) {
+        if (nq > 0) {
+          int x, y, z;
+          unpack_cell(queue[--nq], x, y, z);
+          set_cell(x, y, z);
+          return true;
+        }
+        if (resync) {
+          if (leaving_after) return false;
+          if (cell[0] != cur[0] || cell[1] != cur[1] || cell[2] != cur[2]) set_cell(cur[0], cur[1], cur[2]);
+          resync = false;
+        }
+        // ---- which face does the ray leave through?  fp32 filter, exact fp64 when close ----
+        int ax = decide_fast();
+        if (ax < 0) {
+          const int cross = exact_cross();
+          if (cross & (cross - 1)) {
+            // true tie: the ray passes through a lattice edge / corner — 3 or 7 boxes at the same distance
+            int lo[3];
+            leaving_after = false;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+              lo[a] = cell[a];
+              cur[a] = cell[a];
+              if (cross & (1 << a)) {
+                const int nw = cell[a] + sgn[a];
+                lo[a] = min(cell[a], nw);
+                cur[a] = nw;
+                if ((unsigned)nw >= (unsigned)n) leaving_after = true;
+              }
+            }
+            uint32_t cells[8];
+            const int mm = build_event_cells(S, lo[0], lo[1], lo[2], cross, cross, pos_mask, cells);
+            for (int j = 0; j < mm; j++) queue[j] = cells[mm - 1 - j];
+            nq = mm;
+            resync = true;
+            continue;
+          }
+          ax = (cross & 1) ? 0 : ((cross & 2) ? 1 : 2);
+        }
+        const int moved = advance(ax);
+        if ((unsigned)moved >= (unsigned)n) return false;      // left the lattice
+        if (SPARSE && !cell_present(S, cell[0], cell[1], cell[2])) continue;
+        return true;
+      }
+    };
+
+    if (!next_cell()) return;
+    for (;;) {
+      // ---- the current cell is a hit ----
+      if (MODE == 1) {
+        if (vox && n_hit < keep) { vox[n_hit * 3] = cell[0]; vox[n_hit * 3 + 1] = cell[1]; vox[n_hit * 3 + 2] = cell[2]; }
+        n_hit++;
+        if (!alive) {                                          // past the break: only count the remaining hits
+          if (!next_cell()) return;
+          continue;
+        }
+        if (touched) {
+#pragma unroll
+          for (int s = 0; s < 8; s++) touched[slot_node(s)] = 1;
+        }
+      } else n_hit = 1;
+      // 1. start the gathers of this cell's stale nodes
+      uint32_t stale = dirty;
+      uint32_t hi = high_members(stale);
+      if (stale & hi & 0x0fu) {                                // both members of a pair stale (after a full reset): rare
+        refill_blocking(stale);
+        stale = 0;
+        hi = 0;
+      }
+      NodeLoad L0, L1, L2, L3;
+      issue_pair<0>(stale, L0); issue_pair<1>(stale, L1); issue_pair<2>(stale, L2); issue_pair<3>(stale, L3);
+      dirty = 0;
+      // 2. this cell's geometry, then the whole traversal step to the next cell — no memory needed
+      Geom g;
+      geometry(g);
+      const bool more = next_cell();
+      // 3. consume the gathers (second round only after a full reset), shade
+      Basis Y;
+      if (!GREY) load_basis(Y);
+      commit_pair<0>(stale, hi, L0, Y); commit_pair<1>(stale, hi, L1, Y); commit_pair<2>(stale, hi, L2, Y); commit_pair<3>(stale, hi, L3, Y);
+      if (!shade(g)) {
+        alive = false;
+        if (MODE == 0) return;
+      }
+      if (!more) return;
+    }
+  }
+};
+
+}  // namespace lrf

@@ -9,12 +9,14 @@
 // Built with -fmad=false (see lrf_device.cuh): decision-critical arithmetic is IEEE op-for-op the
 // reference's; explicit fmaf() only on the colour path (RGB tolerance 1e-4).
 #include "lrf_kernels.cuh"
+#include "lrf_fast.cuh"
 
 namespace lrf {
 
 namespace {
 
 constexpr int kBlock = 128;
+static_assert(kBlock == kFastBlock, "FastMarch's shared-memory stride assumes the forward kernels' block size");
 
 struct RayCtx
 {
@@ -331,13 +333,17 @@ __device__ __forceinline__ void load_exp_table(uint64_t *tab)
   __syncthreads();
 }
 
-// pixel of this thread: a warp covers an 8x4 tile
+// pixel of this thread: a warp covers an 8x4 pixel tile, each quarter-warp a 4x2 block of it.  The L1 data pipe serves
+// a 128-bit warp load one quarter-warp at a time and spends one wavefront per distinct 128-byte line in it, so the
+// more compact the quarter's footprint on the grid, the fewer wavefronts a gather costs (ncu: 8.3 per LDG.128 with
+// 8x1 quarters; the pipe was 88 % busy).
 __device__ __forceinline__ bool tile_pixel(uint32_t w, uint32_t h, uint32_t &px, uint32_t &py)
 {
   const uint32_t tiles_x = (w + 7) / 8;
   const uint32_t tile = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  px = (tile % tiles_x) * 8 + (lane & 7);
-  py = (tile / tiles_x) * 4 + (lane >> 3);
+  const uint32_t q = lane >> 3, sub = lane & 7;
+  px = (tile % tiles_x) * 8 + (q & 1) * 4 + (sub & 3);
+  py = (tile / tiles_x) * 4 + (q >> 1) * 2 + (sub >> 2);
   return px < w && py < h;
 }
 inline uint32_t tile_grid(uint32_t w, uint32_t h)
@@ -346,7 +352,11 @@ inline uint32_t tile_grid(uint32_t w, uint32_t h)
   return (tiles + (kBlock / 32) - 1) / (kBlock / 32);
 }
 
-__global__ void __launch_bounds__(kBlock) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h, int grey)
+// Forward render, one thread per pixel.  Rays that cannot take the fast path (a zero / non-finite reciprocal direction
+// component) are appended to a fallback list and rendered by render_fallback_kernel with the generic march.
+template <bool SPARSE, bool GREY>
+__global__ void __launch_bounds__(kBlock, 4) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
+                                                                 uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list)
 {
   __shared__ uint64_t etab[32];
   load_exp_table(etab);
@@ -354,20 +364,48 @@ __global__ void __launch_bounds__(kBlock) render_image_kernel(const __grid_const
   if (!tile_pixel(w, h, px, py)) return;
   float o[3], d[3];
   gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
-  ShadeVisitor<0> vis(S, etab, grey != 0);
-  ray_ctx_init(vis.R, o, d, grey != 0);
-  march(S, o, d, vis);
+  if (!fast_path_ok(d)) {
+    fb_list[atomicAdd(fb_count, 1u)] = py * w + px;
+    return;
+  }
+  __shared__ float ysm[9 * kFastBlock];
+  __shared__ float4 csm[8 * kFastBlock];
+  FastMarch<0, SPARSE, GREY> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
+  fm.run(o, d);
   uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
-  if (vis.n_hit)
-    pix = pack_color(lm_clamp(vis.col[0], 0.0f, 1.0f), lm_clamp(vis.col[1], 0.0f, 1.0f), lm_clamp(vis.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
+  if (fm.n_hit)
+    pix = pack_color(lm_clamp(fm.col[0], 0.0f, 1.0f), lm_clamp(fm.col[1], 0.0f, 1.0f), lm_clamp(fm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
   out[(size_t)py * w + px] = pix;
 }
 
-template <bool IMAGE>
-__global__ void __launch_bounds__(kBlock) debug_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h, size_t n_rays, const float *__restrict__ ro,
-                                                       const float *__restrict__ rd, int grey, DebugTaps taps)
+__global__ void __launch_bounds__(kBlock) render_fallback_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h, int grey,
+                                                                 const uint32_t *__restrict__ fb_count, const uint32_t *__restrict__ fb_list)
 {
   __shared__ uint64_t etab[32];
+  load_exp_table(etab);
+  const uint32_t n = *fb_count;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const uint32_t pixel = fb_list[i], px = pixel % w, py = pixel / w;
+    float o[3], d[3];
+    gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
+    ShadeVisitor<0> vis(S, etab, grey != 0);
+    ray_ctx_init(vis.R, o, d, grey != 0);
+    march(S, o, d, vis);
+    uint32_t pix = 0;
+    if (vis.n_hit)
+      pix = pack_color(lm_clamp(vis.col[0], 0.0f, 1.0f), lm_clamp(vis.col[1], 0.0f, 1.0f), lm_clamp(vis.col[2], 0.0f, 1.0f), 1.0f);
+    out[pixel] = pix;
+  }
+}
+
+// parity taps.  force_generic = 1 sends every ray down the generic march (tests compare both paths)
+template <bool IMAGE>
+__global__ void __launch_bounds__(kBlock) debug_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h, size_t n_rays, const float *__restrict__ ro,
+                                                       const float *__restrict__ rd, int grey, DebugTaps taps, int force_generic)
+{
+  __shared__ uint64_t etab[32];
+  __shared__ float ysm[9 * kFastBlock];
+  __shared__ float4 csm[8 * kFastBlock];
   load_exp_table(etab);
   size_t ray;
   float o[3], d[3];
@@ -382,21 +420,39 @@ __global__ void __launch_bounds__(kBlock) debug_kernel(const __grid_constant__ S
 #pragma unroll
     for (int a = 0; a < 3; a++) { o[a] = ro[ray * 3 + a]; d[a] = rd[ray * 3 + a]; }
   }
-  ShadeVisitor<1> vis(S, etab, grey != 0);
-  ray_ctx_init(vis.R, o, d, grey != 0);
-  vis.keep = taps.keep;
-  vis.vox = taps.vox_xyz ? taps.vox_xyz + ray * taps.keep * 3 : nullptr;
-  vis.touched = taps.touched;
-  if (vis.vox)
-    for (uint32_t i = 0; i < taps.keep * 3; i++) vis.vox[i] = -1;
-  march(S, o, d, vis);
-  if (taps.n_hit) taps.n_hit[ray] = vis.n_hit;
-  if (taps.n_shaded) taps.n_shaded[ray] = vis.n_shaded;
+  int32_t *vox = taps.vox_xyz ? taps.vox_xyz + ray * taps.keep * 3 : nullptr;
+  if (vox)
+    for (uint32_t i = 0; i < taps.keep * 3; i++) vox[i] = -1;
+  uint32_t n_hit, n_shaded;
+  float col[3], thr, cauchy;
+  if (!force_generic && fast_path_ok(d)) {
+    auto run_fast = [&](auto &fm) {
+      fm.keep = taps.keep;
+      fm.vox = vox;
+      fm.touched = taps.touched;
+      fm.run(o, d);
+      n_hit = fm.n_hit; n_shaded = fm.n_shaded; thr = fm.thr; cauchy = fm.cauchy;
+      col[0] = fm.col[0]; col[1] = fm.col[1]; col[2] = fm.col[2];
+    };
+    if (grey) { FastMarch<1, true, true> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x); run_fast(fm); }
+    else { FastMarch<1, true, false> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x); run_fast(fm); }
+  } else {
+    ShadeVisitor<1> vis(S, etab, grey != 0);
+    ray_ctx_init(vis.R, o, d, grey != 0);
+    vis.keep = taps.keep;
+    vis.vox = vox;
+    vis.touched = taps.touched;
+    march(S, o, d, vis);
+    n_hit = vis.n_hit; n_shaded = vis.n_shaded; thr = vis.thr; cauchy = vis.cauchy;
+    col[0] = vis.col[0]; col[1] = vis.col[1]; col[2] = vis.col[2];
+  }
+  if (taps.n_hit) taps.n_hit[ray] = n_hit;
+  if (taps.n_shaded) taps.n_shaded[ray] = n_shaded;
   if (taps.rgbtc) {
     float *r = taps.rgbtc + ray * 5;
-    if (vis.n_hit) {
-      r[0] = lm_clamp(vis.col[0], 0.0f, 1.0f); r[1] = lm_clamp(vis.col[1], 0.0f, 1.0f); r[2] = lm_clamp(vis.col[2], 0.0f, 1.0f);
-      r[3] = vis.thr; r[4] = vis.cauchy;
+    if (n_hit) {
+      r[0] = lm_clamp(col[0], 0.0f, 1.0f); r[1] = lm_clamp(col[1], 0.0f, 1.0f); r[2] = lm_clamp(col[2], 0.0f, 1.0f);
+      r[3] = thr; r[4] = cauchy;
     } else { r[0] = r[1] = r[2] = r[3] = r[4] = 0.0f; }
   }
 }
@@ -897,18 +953,29 @@ inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, cudaStream_t st)
+void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, uint32_t *fb_count, uint32_t *fb_list,
+                         cudaStream_t st)
 {
-  render_image_kernel<<<tile_grid(w, h), kBlock, 0, st>>>(S, out_dev, w, h, grey);
+  cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
+  const dim3 g(tile_grid(w, h));
+  if (S.occ) {
+    if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+    else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+  } else {
+    if (grey) render_image_kernel<false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+    else render_image_kernel<false, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+  }
+  render_fallback_kernel<<<148, kBlock, 0, st>>>(S, out_dev, w, h, grey, fb_count, fb_list);
 }
-void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, const DebugTaps &taps, cudaStream_t st)
+void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, const DebugTaps &taps, int force_generic, cudaStream_t st)
 {
-  debug_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, grey, taps);
+  debug_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, grey, taps, force_generic);
 }
-void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float *d, int grey, const DebugTaps &taps, cudaStream_t st)
+void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float *d, int grey, const DebugTaps &taps, int force_generic,
+                       cudaStream_t st)
 {
   if (n == 0) return;
-  debug_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, grey, taps);
+  debug_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, grey, taps, force_generic);
 }
 void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st)
 {

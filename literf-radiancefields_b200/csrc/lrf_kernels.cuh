@@ -18,9 +18,12 @@ struct DebugTaps  // device pointers, any may be null
 };
 
 // forward
-void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, cudaStream_t st);
-void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, const DebugTaps &taps, cudaStream_t st);
-void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float *d, int grey, const DebugTaps &taps, cudaStream_t st);
+// fb_count (1 uint32) / fb_list (w*h uint32): fallback queue for rays that need the generic march; 2 kernel launches
+void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, uint32_t *fb_count, uint32_t *fb_list,
+                         cudaStream_t st);
+void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, const DebugTaps &taps, int force_generic, cudaStream_t st);
+void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float *d, int grey, const DebugTaps &taps, int force_generic,
+                       cudaStream_t st);
 // backward
 void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st);
 void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, cudaStream_t st);

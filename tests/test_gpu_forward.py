@@ -152,3 +152,28 @@ def test_crafted_rays_ties_and_static_axes(pkg):
     assert nh_o.max() > 0 and (nh_o == 0).any()
     t.close()
     S.close()
+
+
+def test_fast_and_generic_march_agree(pkg):
+    """the streamlined march (lrf_fast.cuh) and the generic exact march (lrf_device.cuh) give identical taps"""
+    gs = 32
+    grid = libs.lcg_grid(gs, 20.0)
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.set_grid(grid)
+    for boxes in (None, sphere_boxes(gs)):
+        if boxes is not None:
+            t.set_boxes(boxes)
+        for k in (1, 4):
+            vi, pi = cameras(pkg, k, 7)
+            t.set_view_inv(vi)
+            t.set_proj_inv(pi)
+            t.set_option("force_generic_march", 0)
+            a = t.render_debug(56, 56, False, 80)
+            t.set_option("force_generic_march", 1)
+            b = t.render_debug(56, 56, False, 80)
+            t.set_option("force_generic_march", 0)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+            assert np.array_equal(a[2][:, 3].view(np.uint32), b[2][:, 3].view(np.uint32))
+            assert np.abs(a[2][:, :3] - b[2][:, :3]).max() <= 2e-6
+    t.close()

@@ -12,7 +12,7 @@ import sys
 import tempfile
 
 rep, kname = sys.argv[1], sys.argv[2]
-topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+topn = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "literf-radiancefields_b200", "_build", "liblrf_b200.so")], cwd=tmp, capture_output=True)
@@ -36,7 +36,7 @@ rows = list(csv.reader(io.StringIO(sass)))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hdr]
 ie, ist = h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
-body = [r for r in rows[hdr + 1:] if r and r[ie].isdigit()]
+body = [r for r in rows[hdr + 1:] if r and len(r) > max(ie, ist) and r[ie].isdigit()]
 base = int(body[0][0], 16) if body[0][0].startswith("0x") else int(body[0][0])
 cnt, st = collections.Counter(), collections.Counter()
 tot = 0
@@ -47,10 +47,12 @@ for r in body:
     st[key] += int(r[ist]) if r[ist].isdigit() else 0
     tot += int(r[ie])
 src = {}
-for f in ("lrf_kernels.cu", "lrf_device.cuh"):
+for f in ("lrf_kernels.cu", "lrf_device.cuh", "lrf_fast.cuh"):
     src[f] = open(os.path.join(ROOT, "literf-radiancefields_b200", "csrc", f)).read().splitlines()
 ts = max(1, sum(st.values()))
 print("total dynamic warp-instr", tot)
-for (f, ln), v in cnt.most_common(topn):
+order = st.most_common(topn) if "--by-stall" in sys.argv else cnt.most_common(topn)
+for (f, ln), _v in order:
+    v = cnt[(f, ln)]
     text = src.get(f, [""] * (ln + 1))[ln - 1].strip()[:110] if f in src and ln - 1 < len(src[f]) else ""
     print("%5.2f%% instr %5.2f%% stall  %s:%d  %s" % (100 * v / tot, 100 * st[(f, ln)] / ts, f, ln, text))
