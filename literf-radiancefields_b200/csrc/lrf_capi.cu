@@ -408,8 +408,10 @@ int lrf_render_grad(lrf_ctx *h, uint32_t w, uint32_t hgt, const float *ref_host,
 int lrf_rays_grad_dev_async(lrf_ctx *h, size_t n, const float *o, const float *d, const float *ref, int grey)
 {
   NEED_GRID(h);
-  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->stream);
-  h->launches++;
+  if (n == 0) return 0;
+  if (ensure_fb(h, n)) return 1;
+  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->fb, h->fb + 4, h->stream);
+  h->launches += 2;   // grad_rays_warp_kernel + the generic fallback over its queue
   CK(cudaGetLastError());
   return 0;
 }
@@ -450,7 +452,7 @@ int lrf_tv_grad(lrf_ctx *h)
   if (ensure_tv_tmp(h)) return 1;
   cudaEventRecord(h->ev0, h->stream);
   launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
-  h->launches += 3;
+  h->launches += (h->gs >= 8) ? 1 : 3;   // fused TV kernel (8^3 tiles), stage-by-stage below that
   cudaEventRecord(h->ev1, h->stream);
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->t_tv, h->ev0, h->ev1);
@@ -497,7 +499,7 @@ int lrf_train_percell_async(lrf_ctx *h, int iter)
   NEED_GRID(h);
   if (ensure_tv_tmp(h)) return 1;
   launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
-  h->launches += 3;
+  h->launches += (h->gs >= 8) ? 1 : 3;   // fused TV kernel (8^3 tiles), stage-by-stage below that
   adam_launch(h, iter, 0, 1);
   CK(cudaGetLastError());
   return 0;

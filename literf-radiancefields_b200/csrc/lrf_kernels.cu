@@ -10,6 +10,7 @@
 // reference's; explicit fmaf() only on the colour path (RGB tolerance 1e-4).
 #include "lrf_kernels.cuh"
 #include "lrf_fast.cuh"
+#include "lrf_wray.cuh"
 
 namespace lrf {
 
@@ -595,9 +596,12 @@ struct BwdVisitor
   }
 };
 
+// idx_list / idx_count (packed-ray form only): when given, thread i handles ray idx_list[i] for i < *idx_count — the
+// fallback queue of the warp-per-ray kernel (rays with a zero / non-finite reciprocal direction component)
 template <bool IMAGE>
 __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h, size_t n_rays, const float *__restrict__ ro,
-                                                      const float *__restrict__ rd, const float *__restrict__ ref_rgba, int grey)
+                                                      const float *__restrict__ rd, const float *__restrict__ ref_rgba, int grey,
+                                                      const uint32_t *__restrict__ idx_list, const uint32_t *__restrict__ idx_count)
 {
   __shared__ uint64_t etab[32];
   load_exp_table(etab);
@@ -610,6 +614,10 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
     gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
   } else {
     ray = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (idx_list) {
+      if (ray >= *idx_count) return;
+      ray = idx_list[ray];
+    }
     if (ray >= n_rays) return;
 #pragma unroll
     for (int a = 0; a < 3; a++) { o[a] = ro[ray * 3 + a]; d[a] = rd[ray * 3 + a]; }
@@ -640,6 +648,32 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
   bw.aTn = (float)((double)0.0001f * (1.0 / ((double)fa.thr + 1e-3) - 1.0 / ((double)(1.0f - fa.thr) + 1e-3)));
   bw.n_total = fa.n_shaded;
   march(S, o, d, bw);
+}
+
+// packed ray batch, one WARP per ray (lrf_wray.cuh)
+template <bool SPARSE, bool GREY>
+__global__ void __launch_bounds__(kBlock, 3) grad_rays_warp_kernel(const __grid_constant__ SceneDev S, size_t n_rays, const float *__restrict__ ro,
+                                                                const float *__restrict__ rd, const float *__restrict__ ref_rgba,
+                                                                uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list)
+{
+  __shared__ uint64_t etab[32];
+  load_exp_table(etab);
+  const size_t ray = ((size_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+  if (ray >= n_rays) return;
+  float o[3], d[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) { o[a] = __ldg(ro + ray * 3 + a); d[a] = __ldg(rd + ray * 3 + a); }
+  if (!fast_path_ok(d)) {
+    if ((threadIdx.x & 31) == 0) fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)ray;
+    return;
+  }
+  const float4 rp = __ldg(reinterpret_cast<const float4 *>(ref_rgba) + ray);
+  float ref[3] = {rp.x, rp.y, rp.z};
+  if (GREY) {  // ref :696-704
+    const float gsc = 0.11f * rp.z + 0.59f * rp.y + 0.3f * rp.x;
+    ref[0] = ref[1] = ref[2] = gsc;
+  }
+  warp_ray_backward<SPARSE, GREY>(S, etab, o, d, ref);
 }
 
 // device-side ray generation for (view, pixel) picks — ref :635-639
@@ -721,28 +755,135 @@ __global__ void tv_scatter_kernel(int gs, const float *__restrict__ gv, float *_
   gdens[i] += acc;
 }
 
+// Fused TV gradient: the three stages above in ONE kernel over 8^3 output tiles staged through shared memory
+// (12^3 densities -> 11^3 V -> 9^3 G -> 8^3 node gradients).  The stage-by-stage version moves the V and G
+// planes through L2 twice and evaluates every tv cell four times from global memory; here the only global
+// traffic is the density halo in and the density-gradient tile in/out.
+constexpr int kTvT = 8;
+__global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens)
+{
+  __shared__ float sD[12 * 12 * 12], sV[11 * 11 * 11], sG[9 * 9 * 9];
+  const int tiles = gs / kTvT;
+  const int bx = blockIdx.x % tiles, by = (blockIdx.x / tiles) % tiles, bz = blockIdx.x / (tiles * tiles);
+  const int q0[3] = {bx * kTvT, by * kTvT, bz * kTvT};
+  const int m = gs - 1;
+  for (int i = threadIdx.x; i < 12 * 12 * 12; i += blockDim.x) {
+    const int lx = i % 12, ly = (i / 12) % 12, lz = i / 144;
+    const int x = min(max(q0[0] - 2 + lx, 0), m), y = min(max(q0[1] - 2 + ly, 0), m), z = min(max(q0[2] - 2 + lz, 0), m);
+    sD[i] = __ldg(dens + (size_t)x + (size_t)y * gs + (size_t)z * gs * gs);
+  }
+  __syncthreads();
+  // V_raw at local (lx,ly,lz) <-> coordinate q0 - 2 + l: trilinear(0.5) over {a, min(a+1, gs-1)}^3 (getVoxel :203-230)
+  for (int i = threadIdx.x; i < 11 * 11 * 11; i += blockDim.x) {
+    const int lx = i % 11, ly = (i / 11) % 11, lz = i / 121;
+    auto at = [&](int dx, int dy, int dz) { return sD[(lx + dx) + (ly + dy) * 12 + (lz + dz) * 144]; };
+    const float xy00 = lm_lerp(at(0, 0, 0), at(1, 0, 0), 0.5f), xy10 = lm_lerp(at(0, 1, 0), at(1, 1, 0), 0.5f);
+    const float xy01 = lm_lerp(at(0, 0, 1), at(1, 0, 1), 0.5f), xy11 = lm_lerp(at(0, 1, 1), at(1, 1, 1), 0.5f);
+    sV[i] = lm_lerp(lm_lerp(xy00, xy10, 0.5f), lm_lerp(xy01, xy11, 0.5f), 0.5f);
+  }
+  __syncthreads();
+  // G at local (lx,ly,lz) <-> coordinate p = q0 - 1 + l  (V index of p is l + 1)
+  for (int i = threadIdx.x; i < 9 * 9 * 9; i += blockDim.x) {
+    const int lx = i % 9, ly = (i / 9) % 9, lz = i / 81;
+    const int a = q0[0] - 1 + lx, b = q0[1] - 1 + ly, c = q0[2] - 1 + lz;
+    float g = 0.0f;
+    if (a >= 0 && b >= 0 && c >= 0) {   // a, b, c <= gs - 1 always
+      auto V = [&](int x, int y, int z) { const float v = sV[(x - q0[0] + 2) + (y - q0[1] + 2) * 11 + (z - q0[2] + 2) * 121]; return v < 0.0f ? 0.0f : v; };
+      const float lam = 0.01f;
+      auto cell = [&](int x, int y, int z, int which) -> float {
+        const float v = V(x, y, z);
+        const float dx = v - V(x + 1, y, z), dy = v - V(x, y + 1, z), dz = v - V(x, y, z + 1);
+        const float sum = dx * dx + dy * dy + dz * dz;
+        if (!(sum > 0.0f)) return 0.0f;  // sqrt'(0) := 0
+        const float r = sqrtf(sum);
+        const float num = which == 0 ? (dx + dy + dz) : which == 1 ? -dx : which == 2 ? -dy : -dz;
+        return lam * num / r;
+      };
+      if (a < m && b < m && c < m) g += cell(a, b, c, 0);
+      if (a >= 1 && b < m && c < m) g += cell(a - 1, b, c, 1);
+      if (b >= 1 && a < m && c < m) g += cell(a, b - 1, c, 2);
+      if (c >= 1 && a < m && b < m) g += cell(a, b, c - 1, 3);
+      if (sV[(lx + 1) + (ly + 1) * 11 + (lz + 1) * 121] < 0.0f) g = 0.0f;  // relu gate of getVoxel (:226-227)
+    }
+    sG[i] = g;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kTvT * kTvT * kTvT; i += blockDim.x) {
+    const int lx = i % kTvT, ly = (i / kTvT) % kTvT, lz = i / (kTvT * kTvT);
+    const int q[3] = {q0[0] + lx, q0[1] + ly, q0[2] + lz};
+    float acc = 0.0f;
+    for (int dz = -1; dz <= 0; dz++)
+      for (int dy = -1; dy <= 0; dy++)
+        for (int dx = -1; dx <= 0; dx++) {
+          const int pp[3] = {q[0] + dx, q[1] + dy, q[2] + dz};
+          if (pp[0] < 0 || pp[1] < 0 || pp[2] < 0) continue;
+          float wgt = 1.0f;
+#pragma unroll
+          for (int ax = 0; ax < 3; ax++) {
+            const int mult = (q[ax] == pp[ax] ? 1 : 0) + (q[ax] == min(pp[ax] + 1, m) ? 1 : 0);
+            wgt *= 0.5f * (float)mult;
+          }
+          acc += wgt * sG[(lx + 1 + dx) + (ly + 1 + dy) * 9 + (lz + 1 + dz) * 81];
+        }
+    const size_t o = (size_t)q[0] + (size_t)q[1] * gs + (size_t)q[2] * gs * gs;
+    gdens[o] += acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Adam, ref optimizerStep example_tracer.h:152-162: fp32 moments, fp64 update expression
+//     V = b1 V + (1-b1) g;  Vh = V / (1 - b1^t);  S = b2 S + (1-b2) g g;  Sh = S / (1 - b2^t);  p -= lr Vh / (sqrt(Sh) + eps)
+// with Vh, Sh and the whole update in double, the result narrowed to float.  Evaluated literally that is 3 IEEE fp64
+// divisions and an fp64 sqrt per element (~120 fp64-pipe instructions): the first version of this kernel ran at 50 %
+// of the HBM roofline, bound by the fp64 pipe.  The result is a FLOAT, though, so the double value only has to be known
+// well enough to round it: update() evaluates the expression with reciprocal / rsqrt seeds + one Newton step each
+// (relative error < 2^-40, ~30 instructions) and accepts the float only if the whole error interval rounds to the same
+// float; otherwise (about one element in 10^5) the literal IEEE sequence decides.  Bit-exact either way.
+struct AdamConst
+{
+  float lr, beta1, beta2, eps, omb1f, omb2f;
+  double om_b1, om_b2, inv_om_b1, inv_om_b2;
+};
+__device__ __forceinline__ float adam_param_exact(float p, float v, float s, const AdamConst &C)
+{
+  const double Vh = (double)v / C.om_b1;
+  const double Sh = (double)s / C.om_b2;
+  return (float)((double)p - (double)C.lr * Vh / (sqrt(Sh) + (double)C.eps));
+}
+__device__ __forceinline__ void adam_update(float &p, float g, float &v, float &s, const AdamConst &C)
+{
+  v = C.beta1 * v + C.omb1f * g;
+  s = C.beta2 * s + C.omb2f * g * g;
+  if (v == 0.0f && s == 0.0f) return;   // never touched by a gradient: lr * 0 / (0 + eps) = 0, p - 0 = p exactly (most of the grid early on)
+  // fast evaluation: every approximate step carries a relative error far below 2^-40
+  const double Sh = (double)s * C.inv_om_b2;
+  const float shf = (float)Sh;
+  bool ok = (shf > 1e-30f) && (shf < 1e30f);
+  const double y0 = (double)rsqrtf(shf);                       // 2^-22
+  const double y1 = y0 * fma(-0.5 * Sh, y0 * y0, 1.5);         // one Newton step on 1/sqrt: ~2^-43
+  const double D = fma(Sh, y1, (double)C.eps);                 // sqrt(Sh) + eps
+  const float df = (float)D;
+  ok = ok && (df > 1e-30f) && (df < 1e30f);
+  const double r0 = (double)__fdividef(1.0f, df);              // rcp.approx: 2^-23
+  const double r1 = r0 * fma(-D, r0, 2.0);                     // one Newton step on 1/D: ~2^-46
+  const double x = ((double)C.lr * ((double)v * C.inv_om_b1)) * r1;
+  const double r = (double)p - x;
+  const double e = fabs(x) * 0x1p-38 + fabs(r) * 0x1p-50;      // generous bound on |r - r_reference|
+  const float lo = (float)(r - e), hi = (float)(r + e);
+  if (ok && lo == hi) p = lo;
+  else p = adam_param_exact(p, v, s, C);
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ V, float *__restrict__ Sq,
-                                                   size_t count, float lr, float beta1, float beta2, float eps, double om_b1, double om_b2,
-                                                   int zero_grad)
+                                                   size_t count, const AdamConst C, int zero_grad)
 {
   const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= count) return;
-  const float omb1 = 1 - beta1, omb2 = 1 - beta2;  // (1 - beta_1) evaluated in float, as the reference's int - float
-#define LRF_ADAM_ONE(pp, gg, vv, ss)                                                   \
-  do {                                                                                 \
-    vv = beta1 * vv + omb1 * gg;                                                       \
-    const double Vh = (double)vv / om_b1;                                              \
-    ss = beta2 * ss + omb2 * gg * gg;                                                  \
-    const double Sh = (double)ss / om_b2;                                              \
-    pp = (float)((double)pp - (double)lr * Vh / (sqrt(Sh) + (double)eps));             \
-  } while (0)
   if (i4 + 4 <= count) {
     float4 pv = *reinterpret_cast<float4 *>(p + i4), gv = *reinterpret_cast<float4 *>(g + i4);
     float4 vv = *reinterpret_cast<float4 *>(V + i4), sv = *reinterpret_cast<float4 *>(Sq + i4);
-    LRF_ADAM_ONE(pv.x, gv.x, vv.x, sv.x); LRF_ADAM_ONE(pv.y, gv.y, vv.y, sv.y);
-    LRF_ADAM_ONE(pv.z, gv.z, vv.z, sv.z); LRF_ADAM_ONE(pv.w, gv.w, vv.w, sv.w);
+    adam_update(pv.x, gv.x, vv.x, sv.x, C); adam_update(pv.y, gv.y, vv.y, sv.y, C);
+    adam_update(pv.z, gv.z, vv.z, sv.z, C); adam_update(pv.w, gv.w, vv.w, sv.w, C);
     *reinterpret_cast<float4 *>(p + i4) = pv;
     *reinterpret_cast<float4 *>(V + i4) = vv;
     *reinterpret_cast<float4 *>(Sq + i4) = sv;
@@ -750,13 +891,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, float 
   } else {
     for (size_t i = i4; i < count; i++) {
       float pp = p[i], vv = V[i], ss = Sq[i];
-      const float gg = g[i];
-      LRF_ADAM_ONE(pp, gg, vv, ss);
+      adam_update(pp, g[i], vv, ss, C);
       p[i] = pp; V[i] = vv; Sq[i] = ss;
       if (zero_grad) g[i] = 0.0f;
     }
   }
-#undef LRF_ADAM_ONE
 }
 
 __global__ void fill_kernel(float *__restrict__ p, size_t count, float v)
@@ -979,12 +1118,23 @@ void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float 
 }
 void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st)
 {
-  grad_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, ref_rgba, grey);
+  grad_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, ref_rgba, grey, nullptr, nullptr);
 }
-void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, cudaStream_t st)
+void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, uint32_t *fb_count,
+                      uint32_t *fb_list, cudaStream_t st)
 {
   if (n == 0) return;
-  grad_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, ref_rgba, grey);
+  cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
+  const unsigned g = blocks_for(n * 32, kBlock);
+  if (S.occ) {
+    if (grey) grad_rays_warp_kernel<true, true><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
+    else grad_rays_warp_kernel<true, false><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
+  } else {
+    if (grey) grad_rays_warp_kernel<false, true><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
+    else grad_rays_warp_kernel<false, false><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
+  }
+  // rays the warp kernel cannot take (axis-aligned): the generic thread-per-ray march, usually an empty launch
+  grad_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, ref_rgba, grey, fb_list, fb_count);
 }
 void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_inv_dev, const uint32_t *picks, uint32_t w, uint32_t h, float *o,
                      float *d, cudaStream_t st)
@@ -997,6 +1147,11 @@ void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_i
 void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float *tmp_g, cudaStream_t st)
 {
   const size_t N = (size_t)gs * gs * gs;
+  if (gs >= kTvT) {
+    const int tiles = gs / kTvT;
+    tv_fused_kernel<<<tiles * tiles * tiles, 256, 0, st>>>(gs, dens, gdens);
+    return;
+  }
   tv_voxel_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, dens, tmp_v);
   tv_gather_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, tmp_v, tmp_g);
   tv_scatter_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, tmp_g, gdens);
@@ -1005,8 +1160,11 @@ void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t coun
                  double om_b2, int zero_grad, cudaStream_t st)
 {
   if (count == 0) return;
-  adam_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(p + off, g + off, V + off, S + off, count, lr, beta1, beta2, eps, om_b1, om_b2,
-                                                                zero_grad);
+  AdamConst C;
+  C.lr = lr; C.beta1 = beta1; C.beta2 = beta2; C.eps = eps;
+  C.omb1f = 1 - beta1; C.omb2f = 1 - beta2;   // (1 - beta) evaluated in float, as the reference's int - float
+  C.om_b1 = om_b1; C.om_b2 = om_b2; C.inv_om_b1 = 1.0 / om_b1; C.inv_om_b2 = 1.0 / om_b2;
+  adam_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(p + off, g + off, V + off, S + off, count, C, zero_grad);
 }
 void launch_fill(float *p, size_t count, float v, cudaStream_t st)
 {

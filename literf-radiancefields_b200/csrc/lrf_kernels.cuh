@@ -26,7 +26,9 @@ void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float 
                        cudaStream_t st);
 // backward
 void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st);
-void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, cudaStream_t st);
+// packed rays: warp-per-ray kernel + generic fallback over the queue (fb_count: 1 uint32, fb_list: n uint32); 2 launches
+void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, uint32_t *fb_count,
+                      uint32_t *fb_list, cudaStream_t st);
 void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_inv_dev, const uint32_t *picks, uint32_t w, uint32_t h,
                      float *o, float *d, cudaStream_t st);
 // per-cell

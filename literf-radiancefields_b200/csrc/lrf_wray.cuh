@@ -1,0 +1,453 @@
+// lrf_wray.cuh — warp-per-ray, sample-parallel backward for packed ray batches (BASELINE config 3: 4096 random rays
+// per optimisation step).
+//
+// With a few thousand incoherent rays there are fewer rays than the GPU has warp slots (148 SMs x 64), and a
+// thread-per-ray kernel leaves each ray on one lane with ~500 dependent steps of gathers: the first version ran the
+// 4096-ray batch in 1.8 ms at 6 % warp occupancy and 10 % issue utilisation.  Here one WARP takes one ray:
+//   * the exact traversal (same fp32-filtered DDA as lrf_fast.cuh) runs in lock-step on all lanes — it is the only
+//     serial part — and lane k latches the k-th box of each group of 32 hits;
+//   * every lane then shades ITS sample (8-corner gathers, trilinear density, libm-exact expf, SH colour) in parallel;
+//   * the throughput product — which must be the reference's left-to-right fp32 product, because the break at
+//     `throughput < 0.1` (ref example_tracer.cpp:131) decides how many samples exist — is formed by a 32-step
+//     shuffle loop, a few instructions per sample;
+//   * the adjoint of sample k needs only prefix/suffix sums of the composited colour (closed form of the reverse sweep,
+//     see grad_kernel), so the backward is sample-parallel too: a warp scan, then each lane scatters its 8 x 13 values
+//     with red.global.add.{f32,v4.f32}.
+// Pass A (forward) and pass B (adjoint + scatter) both walk the ray; nothing per-sample is kept in memory.
+#pragma once
+#include "lrf_fast.cuh"
+
+namespace lrf {
+
+// Exact hit enumeration without any node window: the traversal half of FastMarch.
+template <bool SPARSE> struct RayWalker
+{
+  const SceneDev &S;
+  float o[3], d[3], idir[3];
+  int cell[3], sgn[3];
+  float pa[3], tn[3], tf[3];
+  uint32_t queue[8];
+  int nq = 0, cur[3], pos_mask = 0;
+  bool leaving_after = false, resync = true;
+
+  __device__ RayWalker(const SceneDev &s) : S(s) {}
+
+  __device__ __forceinline__ void set_cell(int x, int y, int z)
+  {
+    const int v[3] = {x, y, z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      cell[a] = v[a];
+      const int ex = v[a] + (sgn[a] > 0 ? 1 : 0), en = v[a] + (sgn[a] > 0 ? 0 : 1);
+      pa[a] = (float)ex * S.inv_gs_f;
+      tf[a] = idir[a] * (pa[a] - o[a]);
+      tn[a] = idir[a] * ((float)en * S.inv_gs_f - o[a]);
+    }
+  }
+  __device__ __forceinline__ int advance(int ax)
+  {
+    const bool mm[3] = {ax == 0, ax == 1, ax == 2};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float pan = pa[a] + (sgn[a] > 0 ? S.inv_gs_f : -S.inv_gs_f);
+      const float tfn = idir[a] * (pan - o[a]);
+      tn[a] = mm[a] ? tf[a] : tn[a];
+      tf[a] = mm[a] ? tfn : tf[a];
+      pa[a] = mm[a] ? pan : pa[a];
+      cell[a] = mm[a] ? cell[a] + sgn[a] : cell[a];
+    }
+    return mm[0] ? cell[0] : (mm[1] ? cell[1] : cell[2]);
+  }
+  __device__ __forceinline__ int decide_fast() const
+  {
+    const float m = fminf(fminf(tf[0], tf[1]), tf[2]);
+    const float gate = fmaf(fabsf(m), 0x1p-20f, 0x1p-100f);
+    const bool c0 = tf[0] - m <= gate, c1 = tf[1] - m <= gate, c2 = tf[2] - m <= gate;
+    const int ax = c0 ? 0 : (c1 ? 1 : 2);
+    return ((c0 && c1) || (c0 && c2) || (c1 && c2)) ? -1 : ax;
+  }
+  __device__ __forceinline__ int exact_cross() const
+  {
+    double te[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) te[a] = ((double)pa[a] - (double)o[a]) / (double)d[a];
+    const double em = fmin(te[0], fmin(te[1], te[2]));
+    return (te[0] == em ? 1 : 0) | (te[1] == em ? 2 : 0) | (te[2] == em ? 4 : 0);
+  }
+
+  // entry into the lattice (exact fp64, same construction as the generic march); false = the ray misses it
+  __device__ __forceinline__ bool start(const float *of, const float *df)
+  {
+    const int n = S.n;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      o[a] = of[a];
+      d[a] = df[a];
+      idir[a] = 1.0f / df[a];
+      sgn[a] = df[a] > 0.0f ? 1 : -1;
+    }
+    nq = 0;
+    leaving_after = false;
+    resync = true;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double t_enter = -INF, t_exit = INF, od[3], hd[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      od[a] = (double)of[a];
+      hd[a] = (double)df[a];
+      const double T0 = (0.0 - od[a]) / hd[a], Tn = ((double)n * S.inv_gs - od[a]) / hd[a];
+      t_enter = fmax(t_enter, sgn[a] > 0 ? T0 : Tn);
+      t_exit = fmin(t_exit, sgn[a] > 0 ? Tn : T0);
+    }
+    const double t_start = fmax(t_enter, 0.0);
+    if (!(t_exit >= t_start)) return false;
+    int lo[3], two_mask = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int s = sgn[a];
+      auto Tex = [&](int j) { return ((double)j * S.inv_gs - od[a]) / hd[a]; };
+      int i = (int)floor((od[a] + t_start * hd[a]) * (double)S.gs);
+      i = max(0, min(n - 1, i));
+      for (int it = 0; it < 4; it++) {
+        if (Tex(i + (s > 0 ? 0 : 1)) > t_start && (unsigned)(i - s) < (unsigned)n) { i -= s; continue; }
+        if (Tex(i + (s > 0 ? 1 : 0)) < t_start && (unsigned)(i + s) < (unsigned)n) { i += s; continue; }
+        break;
+      }
+      cur[a] = i;
+      lo[a] = i;
+      if (Tex(i + (s > 0 ? 0 : 1)) == t_start && (unsigned)(i - s) < (unsigned)n) {
+        two_mask |= 1 << a;
+        lo[a] = min(i, i - s);
+      } else if (Tex(i + (s > 0 ? 1 : 0)) == t_start && (unsigned)(i + s) < (unsigned)n) {
+        two_mask |= 1 << a;
+        lo[a] = min(i, i + s);
+        cur[a] = i + s;
+      }
+    }
+    if (two_mask == 0) {
+      if (cell_present(S, lo[0], lo[1], lo[2])) queue[nq++] = pack_cell(lo[0], lo[1], lo[2]);
+    } else {
+      uint32_t cells[8];
+      const int m = build_event_cells(S, lo[0], lo[1], lo[2], two_mask, 0, 0, cells);
+      for (int j = 0; j < m; j++) queue[j] = cells[m - 1 - j];
+      nq = m;
+    }
+    pos_mask = (sgn[0] > 0 ? 1 : 0) | (sgn[1] > 0 ? 2 : 0) | (sgn[2] > 0 ? 4 : 0);
+    cell[0] = cell[1] = cell[2] = -8;
+    return true;
+  }
+
+  // moves to the next hit; false = no more hits
+  __device__ __forceinline__ bool next()
+  {
+    const int n = S.n;
+    for (;;) {
+      if (nq > 0) {
+        int x, y, z;
+        unpack_cell(queue[--nq], x, y, z);
+        set_cell(x, y, z);
+        return true;
+      }
+      if (resync) {
+        if (leaving_after) return false;
+        if (cell[0] != cur[0] || cell[1] != cur[1] || cell[2] != cur[2]) set_cell(cur[0], cur[1], cur[2]);
+        resync = false;
+      }
+      int ax = decide_fast();
+      if (ax < 0) {
+        const int cross = exact_cross();
+        if (cross & (cross - 1)) {
+          int lo[3];
+          leaving_after = false;
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            lo[a] = cell[a];
+            cur[a] = cell[a];
+            if (cross & (1 << a)) {
+              const int nw = cell[a] + sgn[a];
+              lo[a] = min(cell[a], nw);
+              cur[a] = nw;
+              if ((unsigned)nw >= (unsigned)n) leaving_after = true;
+            }
+          }
+          uint32_t cells[8];
+          const int mm = build_event_cells(S, lo[0], lo[1], lo[2], cross, cross, pos_mask, cells);
+          for (int j = 0; j < mm; j++) queue[j] = cells[mm - 1 - j];
+          nq = mm;
+          resync = true;
+          continue;
+        }
+        ax = (cross & 1) ? 0 : ((cross & 2) ? 1 : 2);
+      }
+      const int moved = advance(ax);
+      if ((unsigned)moved >= (unsigned)n) return false;
+      if (SPARSE && !cell_present(S, cell[0], cell[1], cell[2])) continue;
+      return true;
+    }
+  }
+};
+
+__device__ __forceinline__ void red_add_f32(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_v4(float4 *p, float a, float b, float c, float d)
+{
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_incl_scan(double v, int lane)
+{
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += y;
+  }
+  return v;
+}
+
+// one lane's sample of a 32-hit group
+struct LaneSample
+{
+  int x, y, z;
+  float tmin, tmax;
+  // derived
+  float delta, lf[3], w[8];
+  uint32_t base;
+  float dens_raw, sigma, tr, T;   // T = throughput BEFORE this sample
+  float rgb[3], raw, s, c[3];     // interpolated RGB, sh . Y, clamped s, clamped colour
+};
+
+template <bool SPARSE, bool GREY> struct WarpRay
+{
+  const SceneDev &S;
+  const uint64_t *etab;
+  const int lane;
+  RayWalker<SPARSE> W;
+  float Y[9];
+  bool more = false;     // the walker currently stands on an unconsumed hit
+
+  __device__ WarpRay(const SceneDev &s, const uint64_t *t) : S(s), etab(t), lane(threadIdx.x & 31), W(s) {}
+
+  __device__ __forceinline__ bool begin(const float *o, const float *d)
+  {
+    if (!W.start(o, d)) return false;
+    more = W.next();
+    return more;
+  }
+  // latch up to `want` (<= 32) hits, lane k taking the k-th; returns the number latched
+  __device__ __forceinline__ int gather(LaneSample &L, int want)
+  {
+    int m = 0;
+    while (m < want && more) {
+      if (lane == m) {
+        L.x = W.cell[0]; L.y = W.cell[1]; L.z = W.cell[2];
+        L.tmin = fmaxf(fmaxf(W.tn[0], W.tn[1]), W.tn[2]);
+        L.tmax = fminf(fminf(W.tf[0], W.tf[1]), W.tf[2]);
+      }
+      m++;
+      more = W.next();
+    }
+    return m;
+  }
+  // geometry + density + transmittance of this lane's sample (lanes >= m get tr = 1); carry_t = t of the previous
+  // group's last sample (-1 before the first sample of the ray), updated
+  __device__ __forceinline__ void shade_density(LaneSample &L, int m, float &carry_t)
+  {
+    const bool act = lane < m;
+    const float t = (L.tmin + L.tmax) * 0.5f;                  // ref :142
+    float tp = __shfl_up_sync(0xffffffffu, t, 1);
+    if (lane == 0) tp = carry_t;
+    if (tp < 0.0f) tp = L.tmin;                                // :139
+    float delta = t - tp;                                      // :144
+    if (delta > S.step_gate_f)                                 // :145-146
+      delta = (float)((double)delta - (double)((int)((double)delta / S.step) - 1) * S.step);
+    carry_t = __shfl_sync(0xffffffffu, t, max(m - 1, 0));
+    L.delta = delta;
+    L.tr = 1.0f;
+    L.dens_raw = -1.0f;
+    L.sigma = 0.0f;
+    if (!act) return;
+    const int c[3] = {L.x, L.y, L.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float bmin = (float)c[a] * S.inv_gs_f;
+      const float p = W.o[a] + t * W.d[a];                     // :148
+      L.lf[a] = (p - bmin) * S.gs_f;                           // :150
+    }
+    L.base = (uint32_t)L.x + (uint32_t)L.y * S.gs + (uint32_t)L.z * S.gs * S.gs;
+    const float *p = S.dens + L.base;
+    const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
+    const float d000 = __ldg(p), d100 = __ldg(p + 1), d010 = __ldg(p + sy), d110 = __ldg(p + sy + 1);
+    const float d001 = __ldg(p + sz), d101 = __ldg(p + sz + 1), d011 = __ldg(p + sz + sy), d111 = __ldg(p + sz + sy + 1);
+    const float xy00 = lm_lerp(d000, d100, L.lf[0]), xy10 = lm_lerp(d010, d110, L.lf[0]);
+    const float xy01 = lm_lerp(d001, d101, L.lf[0]), xy11 = lm_lerp(d011, d111, L.lf[0]);
+    const float xyz0 = lm_lerp(xy00, xy10, L.lf[1]), xyz1 = lm_lerp(xy01, xy11, L.lf[1]);
+    L.dens_raw = lm_lerp(xyz0, xyz1, L.lf[2]);                 // :155-167, bit-exact
+    L.sigma = L.dens_raw < 0.0f ? 0.0f : L.dens_raw;           // :170-171
+    L.tr = expf_libm(-L.sigma * delta, etab);                  // :175
+  }
+  // the reference's left-to-right throughput product over the group; T_run = throughput entering the group, updated.
+  // Returns the number of samples of this group that are shaded (the break at :131 may cut it short; *broke says so).
+  __device__ __forceinline__ int throughput(LaneSample &L, int m, float &T_run, bool &broke)
+  {
+    broke = false;
+    int n_valid = m;
+    float run = T_run;
+    L.T = run;
+    for (int j = 0; j < m; j++) {
+      const float trj = __shfl_sync(0xffffffffu, L.tr, j);
+      if (lane == j) L.T = run;
+      run = run * trj;                                         // :189
+      if (run < 0.1f) {                                        // :131 — checked before the NEXT sample
+        n_valid = j + 1;
+        broke = true;
+        break;
+      }
+    }
+    T_run = run;
+    return n_valid;
+  }
+  // colour of this lane's sample (lanes < n_valid with a non-zero weight); fills rgb / raw / s / c and the corner weights
+  __device__ __forceinline__ void shade_colour(LaneSample &L)
+  {
+    const float fx = L.lf[0], fy = L.lf[1], fz = L.lf[2];
+    const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+    const float w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
+    L.w[0] = w00 * gz; L.w[1] = w10 * gz; L.w[2] = w01 * gz; L.w[3] = w11 * gz;
+    L.w[4] = w00 * fz; L.w[5] = w10 * fz; L.w[6] = w01 * fz; L.w[7] = w11 * fz;
+    if (GREY) { L.c[0] = L.c[1] = L.c[2] = 1.0f; L.rgb[0] = L.rgb[1] = L.rgb[2] = 0.0f; L.raw = 0.0f; L.s = 0.0f; return; }
+    const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
+    float R = 0.0f, G = 0.0f, B = 0.0f, Q = 0.0f;
+#pragma unroll
+    for (int cn = 0; cn < 8; cn++) {
+      const uint32_t idx = L.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz;
+      const float4 *q = S.col + (size_t)idx * kColF4;
+      const float4 a = __ldg(q), b = __ldg(q + 1), e = __ldg(q + 2);
+      float qq = a.w * Y[0];
+      qq = fmaf(b.x, Y[1], qq); qq = fmaf(b.y, Y[2], qq); qq = fmaf(b.z, Y[3], qq); qq = fmaf(b.w, Y[4], qq);
+      qq = fmaf(e.x, Y[5], qq); qq = fmaf(e.y, Y[6], qq); qq = fmaf(e.z, Y[7], qq); qq = fmaf(e.w, Y[8], qq);
+      R = fmaf(L.w[cn], a.x, R); G = fmaf(L.w[cn], a.y, G); B = fmaf(L.w[cn], a.z, B); Q = fmaf(L.w[cn], qq, Q);
+    }
+    L.rgb[0] = R; L.rgb[1] = G; L.rgb[2] = B;
+    L.raw = Q;
+    L.s = lm_clamp(Q, 0.0f, 1.0f);                             // :181
+    L.c[0] = lm_clamp(R * L.s, 0.0f, 1.0f); L.c[1] = lm_clamp(G * L.s, 0.0f, 1.0f); L.c[2] = lm_clamp(B * L.s, 0.0f, 1.0f);
+  }
+};
+
+// the whole backward of one ray by one warp; ref = {r,g,b} target (already grey-mixed by the caller if GREY).
+// pass 0 = forward (sample count, final throughput, per-channel colour totals in fp64), pass 1 = the adjoint of every
+// sample in forward order:  a_tr_k = -T_k (c_k . aC) + [ (suffix_k . aC) + aT_n T_n ] / tr_k  (last sample: aT_n T_k),
+// the closed form of the reverse sweep  aT <- tr aT + (1 - tr)(c . aC);  suffix_k = total - prefix_k.
+template <bool SPARSE, bool GREY>
+__device__ void warp_ray_backward(const SceneDev &S, const uint64_t *etab, const float *o, const float *d, const float *ref)
+{
+  const int lane = threadIdx.x & 31;
+  WarpRay<SPARSE, GREY> R(S, etab);
+  if (!GREY) sh_eval_2(d, R.Y);
+  double ctot[3] = {0.0, 0.0, 0.0};
+  float aC[3] = {0.0f, 0.0f, 0.0f}, Tn = 0.0f, aTn = 0.0f;
+  uint32_t n_shaded = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    if (!R.begin(o, d)) return;                                // ref :688: empty hit list, no loss term
+    float T_run = 1.0f, carry_t = -1.0f;
+    double cpre[3] = {0.0, 0.0, 0.0};
+    uint32_t left = pass ? n_shaded : 0xffffffffu, count = 0;
+    while (left) {
+      LaneSample L;
+      const int m = R.gather(L, (int)min(left, 32u));
+      if (m == 0) break;
+      R.shade_density(L, m, carry_t);
+      bool broke;
+      const int nv = R.throughput(L, m, T_run, broke);
+      const bool act = lane < nv;
+      const bool open = act && !(L.dens_raw < 0.0f);           // relu closed: sigma = 0, tr = 1, weight 0, no adjoint (:170-171)
+      const float wgt = open ? L.T * (1.0f - L.tr) : 0.0f;     // :187
+      double term[3] = {0.0, 0.0, 0.0};
+      // the colour is needed by the adjoint even when wgt == 0: d colour / d tr = -T c does not vanish with (1 - tr)
+      if (pass ? open : (wgt != 0.0f)) {
+        R.shade_colour(L);
+        if (wgt != 0.0f) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) term[ch] = (double)(wgt * L.c[ch]);
+        }
+      }
+      if (pass == 0) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) ctot[ch] += warp_sum(term[ch]);
+        count += (uint32_t)nv;
+        if (broke || !R.more) break;
+        continue;
+      }
+      double pre[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        pre[ch] = cpre[ch] + warp_incl_scan(term[ch], lane);   // prefix INCLUDING this sample
+        cpre[ch] = __shfl_sync(0xffffffffu, pre[ch], 31);
+      }
+      const bool last = (left <= 32u) && (lane == m - 1);
+      if (open) {
+        const float dot = L.c[0] * aC[0] + L.c[1] * aC[1] + L.c[2] * aC[2];
+        float a_tr;
+        if (last) a_tr = -L.T * dot + aTn * L.T;
+        else {
+          const double suffix = (ctot[0] - pre[0]) * (double)aC[0] + (ctot[1] - pre[1]) * (double)aC[1] + (ctot[2] - pre[2]) * (double)aC[2];
+          a_tr = -L.T * dot + (float)((suffix + (double)aTn * (double)Tn) / (double)L.tr);
+        }
+        const float sigma = L.sigma;
+        // d tr / d sigma = -delta tr;  cauchy: d/dsigma log(1 + 2 sigma^2) = 4 sigma / (1 + 2 sigma^2), weight 0.0005 (:267)
+        const float a_dens = -L.delta * L.tr * a_tr + 0.0005f * (4.0f * sigma / (1.0f + 2.0f * sigma * sigma));
+        const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
+        if (a_dens != 0.0f) {
+#pragma unroll
+          for (int cn = 0; cn < 8; cn++)
+            red_add_f32(S.gdens + L.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz, L.w[cn] * a_dens);
+        }
+        if (!GREY && wgt != 0.0f) {
+          float a_rgb[3] = {0.0f, 0.0f, 0.0f}, a_s = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            const float a_c = wgt * aC[ch];
+            const float u = L.rgb[ch] * L.s;
+            if (0.0f < u && u <= 1.0f) { a_rgb[ch] = L.s * a_c; a_s = fmaf(L.rgb[ch], a_c, a_s); }   // clamp passes iff 0 < u <= 1
+          }
+          const float a_raw = (0.0f < L.raw && L.raw <= 1.0f) ? a_s : 0.0f;
+          if (a_raw != 0.0f || a_rgb[0] != 0.0f || a_rgb[1] != 0.0f || a_rgb[2] != 0.0f) {
+            float a_sh[9];
+#pragma unroll
+            for (int j = 0; j < 9; j++) a_sh[j] = R.Y[j] * a_raw;
+#pragma unroll
+            for (int cn = 0; cn < 8; cn++) {
+              float4 *q = S.gcol + (size_t)(L.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz) * kColF4;
+              const float ww = L.w[cn];
+              red_add_v4(q, ww * a_rgb[0], ww * a_rgb[1], ww * a_rgb[2], ww * a_sh[0]);
+              red_add_v4(q + 1, ww * a_sh[1], ww * a_sh[2], ww * a_sh[3], ww * a_sh[4]);
+              red_add_v4(q + 2, ww * a_sh[5], ww * a_sh[6], ww * a_sh[7], ww * a_sh[8]);
+            }
+          }
+        }
+      }
+      left -= (uint32_t)m;
+    }
+    if (pass == 0) {
+      n_shaded = count;
+      if (n_shaded == 0) return;
+      Tn = T_run;
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const float craw = (float)ctot[ch];
+        const float cc = lm_clamp(craw, 0.0f, 1.0f);           // :193
+        const float diff = cc - ref[ch];                       // :266
+        const float sg = diff < 0.0f ? -1.0f : 1.0f;
+        aC[ch] = (0.0f < craw && craw <= 1.0f) ? sg : 0.0f;
+      }
+      // d/dT of 0.0001f * (log(T + 1e-3) + log(1 - T + 1e-3))   (:267, double arithmetic there)
+      aTn = (float)((double)0.0001f * (1.0 / ((double)Tn + 1e-3) - 1.0 / ((double)(1.0f - Tn) + 1e-3)));
+    }
+  }
+}
+
+}  // namespace lrf

@@ -209,3 +209,50 @@ def test_upsample_grid_and_boxes(pkg):
     assert np.array_equal(S.boxes(), t.get_boxes())
     t.close()
     S.close()
+
+
+def test_packed_rays_backward_with_axis_aligned_and_tie_rays(pkg):
+    """ray batch mixing ordinary rays with axis-aligned ones (fallback queue -> generic march) and lattice-diagonal
+    ones (exact edge / corner ties inside the warp-per-ray kernel); dense and sparse box sets"""
+    gs = 16
+    g = 1.0 / gs
+    rng = np.random.default_rng(21)
+    o, d = [], []
+    for oo, dd in [((-0.5, 0.5 * g * 5, 0.5 * g * 7), (1, 0, 0)), ((-0.5, 4 * g, 6 * g), (1, 0, 0)), ((-0.25, -0.25, 0.5 * g), (1, 1, 0)),
+                   ((-0.25, -0.25, -0.25), (1, 1, 1)), ((1.25, 1.25, 1.25), (-1, -1, -1)), ((0.5, 0.5, 0.5), (0.3, 0.5, 0.81)),
+                   ((4 * g, 4 * g, 4 * g), (1, 0.5, 0.25)), ((0.5, 0.5, 2.0), (0, 0, -1)), ((0.5, 0.5, 2.0), (0, 0, 1))]:
+        dd = np.array(dd, np.float64)
+        o.append(oo)
+        d.append(dd / np.linalg.norm(dd))
+    for _ in range(150):
+        o.append(rng.integers(-8, 24, 3) * g * 0.5)
+        dd = rng.integers(-3, 4, 3).astype(np.float64)
+        if not dd.any():
+            dd[0] = 1
+        d.append(dd / 4.0)
+    for _ in range(100):
+        p0 = rng.random(3) * 3 - 1
+        p1 = rng.random(3) * 0.8 + 0.1
+        o.append(p0)
+        d.append((p1 - p0) / np.linalg.norm(p1 - p0))
+    o, d = np.array(o, np.float32), np.array(d, np.float32)
+    # a zero direction component with the origin exactly on a lattice plane makes the reference compute 0 * inf = NaN
+    # (RayBoxIntersection, example_tracer.cpp:20-27); such rays poison its gradient too — keep the finite ones
+    probe = OracleScene(gs, libs.lcg_grid(gs, 6.0))
+    _, _, rg, _ = probe.trace_rays(o, d)
+    probe.close()
+    keep = np.isfinite(rg).all(axis=1)
+    assert keep.sum() > 200 and ((d[keep] == 0).any(axis=1)).sum() > 20
+    o, d = o[keep], d[keep]
+    ref = rng.random((o.shape[0], 4)).astype(np.float32)
+    for boxes in (None, sphere_boxes(gs, 0.4)):
+        for grey in (False, True):
+            S, t = make_pair(pkg, gs, 6.0, boxes)
+            S.O.orc_zero_grad(S.h)
+            S.O.orc_rays_grad(S.h, o.shape[0], fp(o), fp(d), fp(ref), int(grey))
+            t.zeroGrad()
+            t.rays_grad(o, d, ref, grey)
+            assert np.abs(S.grad).max() > 0
+            assert_grad_close(S.grad.copy(), t.get_grad(), "mixed ray batch")
+            t.close()
+            S.close()
