@@ -107,9 +107,18 @@ def ncu_traffic():
     return None
 
 
+def sharding():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lrf_sharding", os.path.join(ROOT, "literf-radiancefields_b200", "sharding.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def cameras(pkg, rank, world):
+    """weak scaling: a VIEWS*world-view orbit dealt round-robin, VIEWS views per rank"""
     proj_inv = pkg.inverse4x4(pkg.perspective(45.0, 1.0, 0.1, 100.0))
-    views = [pkg.inverse4x4(pkg.orbit_view(k * world + rank, VIEWS * world)) for k in range(VIEWS)]
+    views = [pkg.inverse4x4(pkg.orbit_view(k, VIEWS * world)) for k in sharding().shard_views(VIEWS * world, rank, world)]
     return proj_inv, views
 
 
@@ -207,6 +216,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    # the contract is ONE JSON line on stdout: NCCL prints its version banner there, so everything but the final line
+    # is sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch
@@ -317,9 +330,12 @@ def main():
             line["cpu_baseline"] = dict(info, value=float(np.mean(rates)) / 1e6, unit="Mrays/s")
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
+        os.dup2(2, 1)
         dist.destroy_process_group()
     return 0
 
@@ -351,14 +367,16 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
         grad_tensor = torch.as_tensor(_Arr(), device="cuda")
         ext = torch.cuda.ExternalStream(t.lib.lrf_stream(t.h))
 
-    def one(it):
+    shard = sharding()
+
+    def one(it, exchange=True):
         off = it * batch
         t._ck(t.lib.lrf_gen_rays_dev_async(t.h, batch, vi_dev.ptr, picks_dev.ptr + off * 8, W, H, o_dev.ptr, d_dev.ptr))
         t._ck(t.lib.lrf_rays_grad_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
-        if grad_tensor is not None:
+        if grad_tensor is not None and exchange:
             import torch
             with torch.cuda.stream(ext):
-                dist.all_reduce(grad_tensor)
+                shard.allreduce_gradient(grad_tensor, dist)
         t._ck(t.lib.lrf_train_percell_async(t.h, it))
 
     for it in range(3):
@@ -369,6 +387,13 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
         one(it)
     ms = max_over_ranks(t.timer_stop_ms())
     barrier()
+    ms_noex = None
+    if grad_tensor is not None:   # same iterations without the exchange step: the all-reduce share of an iteration
+        t.timer_start()
+        for it in range(3, 3 + iters):
+            one(it, exchange=False)
+        ms_noex = max_over_ranks(t.timer_stop_ms())
+        barrier()
     # break-down: backward alone / per-cell alone
     t.timer_start()
     for it in range(5):
@@ -380,10 +405,18 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     ms_cell = t.timer_stop_ms() / 5
     N = GS ** 3
     peak, _ = measured_peak()
+    # algorithmic bytes of one iteration: per-cell pass 428 B/node (dense, parity semantics) + the backward's
+    # node traffic (52 B read + 2 x 52 B gradient read-modify-write per touched node; counted as touched-node upper bound
+    # rays x samples x 8 is NOT used — only the dense per-cell term, which dominates, enters the roofline figure)
+    iter_bytes = 428.0 * N
     out = {"metric": "train_iters_per_s", "value": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "rays_per_iter": batch * world, "n_gpus": world,
+           "scaling": "weak (4096 rays per GPU per iteration)",
            "ms_backward_4096_rays": ms_bwd, "ms_percell_tv_adam_zero": ms_cell,
-           "percell_algorithmic_bytes": 416.0 * N + 12.0 * N, "percell_frac_of_hbm_peak": (428.0 * N / (ms_cell * 1e-3) / 1e9) / peak,
-           "allreduce": "NCCL all_reduce of 13*N fp32 gradient (%d MB) per iteration" % (52 * N // 2 ** 20) if world > 1 else "none (1 GPU)"}
+           "percell_algorithmic_bytes": 428.0 * N, "percell_frac_of_hbm_peak": (428.0 * N / (ms_cell * 1e-3) / 1e9) / peak,
+           "iter_frac_of_hbm_peak_incl_allreduce": (iter_bytes / (ms / iters * 1e-3) / 1e9) / peak,
+           "ms_per_iter_without_allreduce": (ms_noex / iters) if ms_noex else ms / iters,
+           "allreduce_ms_per_iter": ((ms - ms_noex) / iters) if ms_noex else 0.0,
+           "allreduce": "NCCL all_reduce (sum) of the 13*N fp32 gradient planes (%d MB) per iteration, on the context stream" % (52 * N // 2 ** 20) if world > 1 else "none (1 GPU)"}
     for b in (vi_dev, picks_dev, ref_dev, o_dev, d_dev):
         b.free()
     return out

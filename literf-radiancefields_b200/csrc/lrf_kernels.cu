@@ -756,77 +756,78 @@ __global__ void tv_scatter_kernel(int gs, const float *__restrict__ gv, float *_
 }
 
 // Fused TV gradient: the three stages above in ONE kernel over 8^3 output tiles staged through shared memory
-// (12^3 densities -> 11^3 V -> 9^3 G -> 8^3 node gradients).  The stage-by-stage version moves the V and G
-// planes through L2 twice and evaluates every tv cell four times from global memory; here the only global
-// traffic is the density halo in and the density-gradient tile in/out.
+// (12^3 densities -> 11^3 V -> 10^3 tv cells -> 9^3 G -> 8^3 node gradients).  The stage-by-stage version moves the
+// V and G planes through L2 twice and evaluates every tv cell four times from global memory; here the only global
+// traffic is the density halo in and the density-gradient tile in/out, and every tv cell (the sqrt) is evaluated once
+// per tile.  Values agree with the staged kernels to rounding (lam * d / r is formed as d * (lam * rsqrt)); the TV
+// gradient is compared with the oracle to 1e-5 relative, not bit-for-bit (the reference's own sum order is a race).
 constexpr int kTvT = 8;
 __global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens)
 {
   __shared__ float sD[12 * 12 * 12], sV[11 * 11 * 11], sG[9 * 9 * 9];
+  __shared__ float sEx[10 * 10 * 10], sEy[10 * 10 * 10], sEz[10 * 10 * 10];
   const int tiles = gs / kTvT;
   const int bx = blockIdx.x % tiles, by = (blockIdx.x / tiles) % tiles, bz = blockIdx.x / (tiles * tiles);
-  const int q0[3] = {bx * kTvT, by * kTvT, bz * kTvT};
+  const int q0x = bx * kTvT, q0y = by * kTvT, q0z = bz * kTvT;
   const int m = gs - 1;
-  for (int i = threadIdx.x; i < 12 * 12 * 12; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 12 * 12 * 12; i += 256) {
     const int lx = i % 12, ly = (i / 12) % 12, lz = i / 144;
-    const int x = min(max(q0[0] - 2 + lx, 0), m), y = min(max(q0[1] - 2 + ly, 0), m), z = min(max(q0[2] - 2 + lz, 0), m);
+    const int x = min(max(q0x - 2 + lx, 0), m), y = min(max(q0y - 2 + ly, 0), m), z = min(max(q0z - 2 + lz, 0), m);
     sD[i] = __ldg(dens + (size_t)x + (size_t)y * gs + (size_t)z * gs * gs);
   }
   __syncthreads();
-  // V_raw at local (lx,ly,lz) <-> coordinate q0 - 2 + l: trilinear(0.5) over {a, min(a+1, gs-1)}^3 (getVoxel :203-230)
-  for (int i = threadIdx.x; i < 11 * 11 * 11; i += blockDim.x) {
+  // V_raw at local l <-> coordinate q0 - 2 + l: trilinear(0.5) over {a, min(a+1, gs-1)}^3 (getVoxel :203-230)
+  for (int i = threadIdx.x; i < 11 * 11 * 11; i += 256) {
     const int lx = i % 11, ly = (i / 11) % 11, lz = i / 121;
-    auto at = [&](int dx, int dy, int dz) { return sD[(lx + dx) + (ly + dy) * 12 + (lz + dz) * 144]; };
-    const float xy00 = lm_lerp(at(0, 0, 0), at(1, 0, 0), 0.5f), xy10 = lm_lerp(at(0, 1, 0), at(1, 1, 0), 0.5f);
-    const float xy01 = lm_lerp(at(0, 0, 1), at(1, 0, 1), 0.5f), xy11 = lm_lerp(at(0, 1, 1), at(1, 1, 1), 0.5f);
+    const float *p = sD + lx + ly * 12 + lz * 144;
+    const float xy00 = lm_lerp(p[0], p[1], 0.5f), xy10 = lm_lerp(p[12], p[13], 0.5f);
+    const float xy01 = lm_lerp(p[144], p[145], 0.5f), xy11 = lm_lerp(p[156], p[157], 0.5f);
     sV[i] = lm_lerp(lm_lerp(xy00, xy10, 0.5f), lm_lerp(xy01, xy11, 0.5f), 0.5f);
   }
   __syncthreads();
-  // G at local (lx,ly,lz) <-> coordinate p = q0 - 1 + l  (V index of p is l + 1)
-  for (int i = threadIdx.x; i < 9 * 9 * 9; i += blockDim.x) {
-    const int lx = i % 9, ly = (i / 9) % 9, lz = i / 81;
-    const int a = q0[0] - 1 + lx, b = q0[1] - 1 + ly, c = q0[2] - 1 + lz;
-    float g = 0.0f;
-    if (a >= 0 && b >= 0 && c >= 0) {   // a, b, c <= gs - 1 always
-      auto V = [&](int x, int y, int z) { const float v = sV[(x - q0[0] + 2) + (y - q0[1] + 2) * 11 + (z - q0[2] + 2) * 121]; return v < 0.0f ? 0.0f : v; };
-      const float lam = 0.01f;
-      auto cell = [&](int x, int y, int z, int which) -> float {
-        const float v = V(x, y, z);
-        const float dx = v - V(x + 1, y, z), dy = v - V(x, y + 1, z), dz = v - V(x, y, z + 1);
-        const float sum = dx * dx + dy * dy + dz * dz;
-        if (!(sum > 0.0f)) return 0.0f;  // sqrt'(0) := 0
-        const float r = sqrtf(sum);
-        const float num = which == 0 ? (dx + dy + dz) : which == 1 ? -dx : which == 2 ? -dy : -dz;
-        return lam * num / r;
-      };
-      if (a < m && b < m && c < m) g += cell(a, b, c, 0);
-      if (a >= 1 && b < m && c < m) g += cell(a - 1, b, c, 1);
-      if (b >= 1 && a < m && c < m) g += cell(a, b - 1, c, 2);
-      if (c >= 1 && a < m && b < m) g += cell(a, b, c - 1, 3);
-      if (sV[(lx + 1) + (ly + 1) * 11 + (lz + 1) * 121] < 0.0f) g = 0.0f;  // relu gate of getVoxel (:226-227)
+  // tv cell at local l <-> coordinate q0 - 2 + l (needs V at l and l + 1): E = lam * (dx, dy, dz) / sqrt(dx^2 + dy^2 + dz^2),
+  // zero where the cell does not exist (a coordinate outside [0, gs-2]) or the root's argument is 0 (sqrt'(0) := 0)
+  for (int i = threadIdx.x; i < 10 * 10 * 10; i += 256) {
+    const int lx = i % 10, ly = (i / 10) % 10, lz = i / 100;
+    const int a = q0x - 2 + lx, b = q0y - 2 + ly, c = q0z - 2 + lz;
+    float ex = 0.0f, ey = 0.0f, ez = 0.0f;
+    if (a >= 0 && b >= 0 && c >= 0 && a < m && b < m && c < m) {
+      const float *p = sV + lx + ly * 11 + lz * 121;
+      const float v = fmaxf(p[0], 0.0f);
+      const float dx = v - fmaxf(p[1], 0.0f), dy = v - fmaxf(p[11], 0.0f), dz = v - fmaxf(p[121], 0.0f);
+      const float sum = dx * dx + dy * dy + dz * dz;
+      if (sum > 0.0f) {
+        const float k = 0.01f * rsqrtf(sum);
+        ex = dx * k; ey = dy * k; ez = dz * k;
+      }
     }
+    sEx[i] = ex; sEy[i] = ey; sEz[i] = ez;
+  }
+  __syncthreads();
+  // G(p) = d(sum tv)/dV(p), p = q0 - 1 + l: + (Ex+Ey+Ez)(p) - Ex(p - ex) - Ey(p - ey) - Ez(p - ez), relu-gated (:226-227)
+  for (int i = threadIdx.x; i < 9 * 9 * 9; i += 256) {
+    const int lx = i % 9, ly = (i / 9) % 9, lz = i / 81;
+    const int e = (lx + 1) + (ly + 1) * 10 + (lz + 1) * 100;   // tv-cell index of p
+    float g = sEx[e] + sEy[e] + sEz[e] - sEx[e - 1] - sEy[e - 10] - sEz[e - 100];
+    if (sV[(lx + 1) + (ly + 1) * 11 + (lz + 1) * 121] < 0.0f) g = 0.0f;
+    if (q0x - 1 + lx < 0 || q0y - 1 + ly < 0 || q0z - 1 + lz < 0) g = 0.0f;
     sG[i] = g;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kTvT * kTvT * kTvT; i += blockDim.x) {
+  // node gradient: each node is a corner of up to 8 V cells, weight 0.5 per axis, doubled where far == near (last node row)
+  for (int i = threadIdx.x; i < kTvT * kTvT * kTvT; i += 256) {
     const int lx = i % kTvT, ly = (i / kTvT) % kTvT, lz = i / (kTvT * kTvT);
-    const int q[3] = {q0[0] + lx, q0[1] + ly, q0[2] + lz};
+    const int qx = q0x + lx, qy = q0y + ly, qz = q0z + lz;
+    // along an axis: contribution of V cell q (weight 0.5, or 1.0 at the last node where min(q+1, gs-1) == q) and of
+    // V cell q - 1 (weight 0.5, absent at q == 0)
+    const float wx0 = qx == m ? 1.0f : 0.5f, wx1 = qx > 0 ? 0.5f : 0.0f;
+    const float wy0 = qy == m ? 1.0f : 0.5f, wy1 = qy > 0 ? 0.5f : 0.0f;
+    const float wz0 = qz == m ? 1.0f : 0.5f, wz1 = qz > 0 ? 0.5f : 0.0f;
+    const float *p = sG + (lx + 1) + (ly + 1) * 9 + (lz + 1) * 81;
     float acc = 0.0f;
-    for (int dz = -1; dz <= 0; dz++)
-      for (int dy = -1; dy <= 0; dy++)
-        for (int dx = -1; dx <= 0; dx++) {
-          const int pp[3] = {q[0] + dx, q[1] + dy, q[2] + dz};
-          if (pp[0] < 0 || pp[1] < 0 || pp[2] < 0) continue;
-          float wgt = 1.0f;
-#pragma unroll
-          for (int ax = 0; ax < 3; ax++) {
-            const int mult = (q[ax] == pp[ax] ? 1 : 0) + (q[ax] == min(pp[ax] + 1, m) ? 1 : 0);
-            wgt *= 0.5f * (float)mult;
-          }
-          acc += wgt * sG[(lx + 1 + dx) + (ly + 1 + dy) * 9 + (lz + 1 + dz) * 81];
-        }
-    const size_t o = (size_t)q[0] + (size_t)q[1] * gs + (size_t)q[2] * gs * gs;
-    gdens[o] += acc;
+    acc += wz1 * (wy1 * (wx1 * p[-81 - 9 - 1] + wx0 * p[-81 - 9]) + wy0 * (wx1 * p[-81 - 1] + wx0 * p[-81]));
+    acc += wz0 * (wy1 * (wx1 * p[-9 - 1] + wx0 * p[-9]) + wy0 * (wx1 * p[-1] + wx0 * p[0]));
+    gdens[(size_t)qx + (size_t)qy * gs + (size_t)qz * gs * gs] += acc;
   }
 }
 

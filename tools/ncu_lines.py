@@ -47,7 +47,7 @@ for r in body:
     st[key] += int(r[ist]) if r[ist].isdigit() else 0
     tot += int(r[ie])
 src = {}
-for f in ("lrf_kernels.cu", "lrf_device.cuh", "lrf_fast.cuh"):
+for f in ("lrf_kernels.cu", "lrf_device.cuh", "lrf_fast.cuh", "lrf_wray.cuh"):
     src[f] = open(os.path.join(ROOT, "literf-radiancefields_b200", "csrc", f)).read().splitlines()
 ts = max(1, sum(st.values()))
 print("total dynamic warp-instr", tot)
