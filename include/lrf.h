@@ -130,6 +130,33 @@ int lrf_upsample_boxes(lrf_ctx *h);
 /* ref: RebuildOctree(), example_tracer.cpp:449-489 */
 int lrf_rebuild_boxes(lrf_ctx *h);
 
+/* ---- callers either side of the path ------------------------------------- */
+/* ref: the raw model.dat dump / load kept (commented) in main.cpp:54-56,139-141: gs^3 cells x 13 floats, no header.
+ * lrf_model_load fails unless the file size equals the current grid's gs^3 * 52 bytes. */
+int lrf_model_save(lrf_ctx *h, const char *path);
+int lrf_model_load(lrf_ctx *h, const char *path);
+/* Resident target images.  ref: main.cpp:72,88-97 — stbi_set_flip_vertically_on_load(true) + stbi_loadf(.., 4): every
+ * view's PNG is decoded, flipped, linearised (external/stb_image.h:1856-1876: colour = pow(u8/255.0f, 2.2f), alpha =
+ * u8/255.0f) and passed to L1Loss as float4[w*h], then freed.  Here the caller hands over the DECODED 8-bit RGBA rows
+ * (file order, top row first; PNG decoding stays on the host) and the flip + linearisation run on the device into
+ * slot `view` of a resident array, bit-identical to stbi_loadf's output. */
+int lrf_targets_resize(lrf_ctx *h, uint32_t n_views, uint32_t width, uint32_t height);
+int lrf_target_ingest_rgba8(lrf_ctx *h, uint32_t view, const uint8_t *rgba8_host, int flip_vertical);
+/* already-linear float4 pixels (what stbi_loadf returned), HOST memory */
+int lrf_target_upload_rgbaf(lrf_ctx *h, uint32_t view, const float *rgba_host);
+int lrf_target_download(lrf_ctx *h, uint32_t view, float *rgba_host);
+float *lrf_target_device_ptr(lrf_ctx *h, uint32_t view);
+/* kernel2D_RayMarchGrad (example_tracer.cpp:665-718) against resident target `view`, current camera; asynchronous */
+int lrf_render_grad_target_async(lrf_ctx *h, uint32_t view, int greyscale);
+/* reference pixels for a batch of picks {view, pixel index} (DEVICE, as lrf_gen_rays_dev_async takes them) out of the
+ * resident targets -> ref_rgba_dev[n x 4]; asynchronous */
+int lrf_gather_targets_dev_async(lrf_ctx *h, size_t n, const uint32_t *picks_dev, float *ref_rgba_dev);
+/* ref: LiteImage::SaveBMP(fname, pixels, w, h) as L1Loss calls it (example_tracer.cpp:614; external/LiteMath/
+ * Image2d.cpp:488-533): 24-bit BMP, records {(p>>16)&255, (p>>8)&255, p&255}, no row padding, byte-identical file. */
+int lrf_save_bmp(const char *path, const uint32_t *pixels_host, int width, int height);
+/* kernel2D_RayMarch + the BMP record packing as a device epilogue + file write */
+int lrf_render_bmp(lrf_ctx *h, const char *path, uint32_t width, uint32_t height, int greyscale);
+
 /* ---- plumbing -------------------------------------------------------------------------------- */
 /* ref: GetExecutionTime(const char*, float[4]), example_tracer.cpp:759-763.  name in {"RayMarch",
  * "RayMarchGrad","TVGrad","Adam"}: out[0] = device ms of the last such call (CUDA events). */

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "liblrf_b200.so")
+LIB_PATH = os.environ.get("LRF_B200_LIB") or os.path.join(_HERE, "_build", "liblrf_b200.so")   # the override is for kernel-variant experiments (tools/)
 
 _c_fp = C.POINTER(C.c_float)
 _c_u32p = C.POINTER(C.c_uint32)
@@ -81,6 +81,17 @@ SIGNATURES = {
     "lrf_launch_count": (C.c_uint64, [_vp]),
     "lrf_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lrf_count_touched_nodes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
+    "lrf_model_save": (C.c_int, [_vp, C.c_char_p]),
+    "lrf_model_load": (C.c_int, [_vp, C.c_char_p]),
+    "lrf_targets_resize": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "lrf_target_ingest_rgba8": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int]),
+    "lrf_target_upload_rgbaf": (C.c_int, [_vp, C.c_uint32, _c_fp]),
+    "lrf_target_download": (C.c_int, [_vp, C.c_uint32, _c_fp]),
+    "lrf_target_device_ptr": (_vp, [_vp, C.c_uint32]),
+    "lrf_render_grad_target_async": (C.c_int, [_vp, C.c_uint32, C.c_int]),
+    "lrf_gather_targets_dev_async": (C.c_int, [_vp, C.c_size_t, _vp, _vp]),
+    "lrf_save_bmp": (C.c_int, [C.c_char_p, _c_u32p, C.c_int, C.c_int]),
+    "lrf_render_bmp": (C.c_int, [_vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int]),
 }
 
 _lib = None
@@ -403,6 +414,47 @@ class RayMarcherExample:
 
     def launch_count(self):
         return self.lib.lrf_launch_count(self.h)
+
+    # ---- callers either side of the path ----
+    def save_model(self, path):
+        """ref: main.cpp:139-141 (raw gs^3 x Cell dump)"""
+        self._ck(self.lib.lrf_model_save(self.h, os.fsencode(path)))
+
+    def load_model(self, path):
+        """ref: main.cpp:54-56"""
+        self._ck(self.lib.lrf_model_load(self.h, os.fsencode(path)))
+
+    def targets_resize(self, n_views, width, height):
+        self._ck(self.lib.lrf_targets_resize(self.h, n_views, width, height))
+
+    def target_ingest_rgba8(self, view, rgba8, flip_vertical=True):
+        """decoded 8-bit RGBA rows in file order -> resident float4 target (stbi_loadf semantics, main.cpp:72,96)"""
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        self._ck(self.lib.lrf_target_ingest_rgba8(self.h, view, a.ctypes.data, int(flip_vertical)))
+
+    def target_upload(self, view, rgba):
+        self._ck(self.lib.lrf_target_upload_rgbaf(self.h, view, _fp(_f32(rgba))))
+
+    def target_download(self, view, width, height):
+        out = np.zeros((width * height, 4), np.float32)
+        self._ck(self.lib.lrf_target_download(self.h, view, _fp(out)))
+        return out
+
+    def render_grad_target_async(self, view, greyscale=False):
+        self._ck(self.lib.lrf_render_grad_target_async(self.h, view, int(greyscale)))
+
+    def gather_targets_dev_async(self, n, picks_dev_ptr, ref_dev_ptr):
+        self._ck(self.lib.lrf_gather_targets_dev_async(self.h, n, picks_dev_ptr, ref_dev_ptr))
+
+    def render_bmp(self, path, width, height, greyscale=False):
+        self._ck(self.lib.lrf_render_bmp(self.h, os.fsencode(path), width, height, int(greyscale)))
+
+
+def save_bmp(path, pixels, width, height):
+    """ref: LiteImage::SaveBMP as L1Loss calls it (example_tracer.cpp:614)"""
+    a = np.ascontiguousarray(pixels, dtype=np.uint32)
+    if load_library().lrf_save_bmp(os.fsencode(path), a.ctypes.data_as(_c_u32p), width, height):
+        raise LrfError(load_library().lrf_last_error().decode())
 
 
 def L1Loss(ref, gen, width, height, pImpl, fileName=None, greyscale=False):

@@ -43,6 +43,10 @@ struct lrf_ctx
   uint32_t *fb = nullptr;
   size_t fb_cap = 0;
   int force_generic = 0;   // parity taps: 1 = generic march for every ray (tests compare both paths)
+  // resident target images: n_targets x tw x th float4, stbi_loadf layout
+  float *targets = nullptr;
+  float *gamma_lut = nullptr;         // device copy of the 256-entry ldr->hdr table
+  uint32_t n_targets = 0, tw = 0, th = 0;
 };
 
 static thread_local std::string g_err;
@@ -163,6 +167,8 @@ int lrf_destroy(lrf_ctx *h)
   free_grid(h);
   cudaFree(h->stage);
   cudaFree(h->fb);
+  cudaFree(h->targets);
+  cudaFree(h->gamma_lut);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -438,6 +444,156 @@ int lrf_gen_rays_dev_async(lrf_ctx *h, size_t n, const float *view_inv_dev, cons
   h->launches++;
   CK(cudaGetLastError());
   return 0;
+}
+
+// ---- callers either side of the path ----
+// model.dat: the raw gs^3 x Cell dump the reference keeps commented in main.cpp:54-56 (load) and :139-141 (save)
+int lrf_model_save(lrf_ctx *h, const char *path)
+{
+  NEED_GRID(h);
+  if (!path) return fail("null path");
+  std::vector<float> cells(h->N * kCell);
+  if (lrf_grid_download(h, cells.data())) return 1;
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return fail(std::string("cannot open for writing: ") + path);
+  const size_t wr = std::fwrite(cells.data(), sizeof(float), cells.size(), f);
+  const int rc = std::fclose(f);
+  if (wr != cells.size() || rc != 0) return fail(std::string("short write: ") + path);
+  return 0;
+}
+int lrf_model_load(lrf_ctx *h, const char *path)
+{
+  NEED_GRID(h);
+  if (!path) return fail("null path");
+  FILE *f = std::fopen(path, "rb");
+  if (!f) return fail(std::string("cannot open: ") + path);
+  std::fseek(f, 0, SEEK_END);
+  const long sz = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  const size_t want = h->N * kCell * sizeof(float);
+  if (sz < 0 || (size_t)sz != want) {
+    std::fclose(f);
+    return fail(std::string(path) + ": " + std::to_string(sz) + " bytes, but a " + std::to_string(h->gs) + "^3 grid of 52-byte cells is " +
+                std::to_string(want) + " (the reference reads grid.size()*sizeof(Cell) bytes, main.cpp:55)");
+  }
+  std::vector<float> cells(h->N * kCell);
+  const size_t rd = std::fread(cells.data(), sizeof(float), cells.size(), f);
+  std::fclose(f);
+  if (rd != cells.size()) return fail(std::string("short read: ") + path);
+  return lrf_grid_upload(h, cells.data());
+}
+
+int lrf_targets_resize(lrf_ctx *h, uint32_t n_views, uint32_t w, uint32_t hgt)
+{
+  NEED(h);
+  cudaFree(h->targets);
+  h->targets = nullptr;
+  h->n_targets = h->tw = h->th = 0;
+  const size_t bytes = (size_t)n_views * w * hgt * 16;
+  if (bytes) CK(cudaMalloc(&h->targets, bytes));
+  h->n_targets = n_views; h->tw = w; h->th = hgt;
+  if (!h->gamma_lut) {
+    float lut[256];
+    const float gamma = 2.2f, scale = 1.0f;                       // stb_image.h:1572 defaults; main.cpp never changes them
+    for (int i = 0; i < 256; i++) lut[i] = (float)(powf((float)i / 255.0f, gamma) * scale);   // stb_image.h:1868 as C++ sees it: pow(float,float)
+    CK(cudaMalloc(&h->gamma_lut, sizeof(lut)));
+    CK(cudaMemcpy(h->gamma_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+#define NEED_TARGET(h, view) do { NEED(h); if (!(h)->targets || (view) >= (h)->n_targets) return fail("target slot out of range (call lrf_targets_resize)"); } while (0)
+int lrf_target_ingest_rgba8(lrf_ctx *h, uint32_t view, const uint8_t *rgba8_host, int flip_vertical)
+{
+  NEED_TARGET(h, view);
+  const size_t px = (size_t)h->tw * h->th;
+  if (ensure_stage(h, px * 4)) return 1;
+  CK(cudaMemcpyAsync(h->stage, rgba8_host, px * 4, cudaMemcpyHostToDevice, h->stream));
+  launch_ingest_rgba8((const uint8_t *)h->stage, h->targets + (size_t)view * px * 4, h->tw, h->th, flip_vertical, h->gamma_lut, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));   // the caller's buffer and the staging area are free again
+  return 0;
+}
+int lrf_target_upload_rgbaf(lrf_ctx *h, uint32_t view, const float *rgba_host)
+{
+  NEED_TARGET(h, view);
+  const size_t px = (size_t)h->tw * h->th;
+  CK(cudaMemcpyAsync(h->targets + (size_t)view * px * 4, rgba_host, px * 16, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int lrf_target_download(lrf_ctx *h, uint32_t view, float *rgba_host)
+{
+  NEED_TARGET(h, view);
+  const size_t px = (size_t)h->tw * h->th;
+  CK(cudaMemcpyAsync(rgba_host, h->targets + (size_t)view * px * 4, px * 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+float *lrf_target_device_ptr(lrf_ctx *h, uint32_t view)
+{
+  if (!h || !h->targets || view >= h->n_targets) return nullptr;
+  return h->targets + (size_t)view * h->tw * h->th * 4;
+}
+int lrf_render_grad_target_async(lrf_ctx *h, uint32_t view, int grey)
+{
+  NEED_TARGET(h, view);
+  return lrf_render_grad_dev_async(h, h->tw, h->th, lrf_target_device_ptr(h, view), grey);
+}
+int lrf_gather_targets_dev_async(lrf_ctx *h, size_t n, const uint32_t *picks_dev, float *ref_rgba_dev)
+{
+  NEED(h);
+  if (!h->targets) return fail("no resident targets (call lrf_targets_resize)");
+  launch_gather_targets(n, picks_dev, h->targets, (size_t)h->tw * h->th, ref_rgba_dev, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// BMP: LiteImage::SaveBMP / WriteBMP, ref external/LiteMath/Image2d.cpp:488-533 (header bytes and record order restated)
+static int write_bmp_file(const char *path, const uint8_t *records, int width, int height)
+{
+  const int paddedsize = width * height * 3;
+  unsigned char fh[14] = {'B', 'M', 0, 0, 0, 0, 0, 0, 0, 0, 54, 0, 0, 0};
+  unsigned char ih[40] = {40, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 24, 0};
+  for (int b = 0; b < 4; b++) {
+    fh[2 + b] = (unsigned char)(paddedsize >> (8 * b));    // the reference stores the pixel-array size here, not the file size
+    ih[4 + b] = (unsigned char)(width >> (8 * b));
+    ih[8 + b] = (unsigned char)(height >> (8 * b));
+  }
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return fail(std::string("cannot open for writing: ") + path);
+  size_t wr = std::fwrite(fh, 1, 14, f) + std::fwrite(ih, 1, 40, f) + std::fwrite(records, 1, (size_t)paddedsize, f);
+  const int rc = std::fclose(f);
+  if (wr != (size_t)paddedsize + 54 || rc != 0) return fail(std::string("short write: ") + path);
+  return 0;
+}
+int lrf_save_bmp(const char *path, const uint32_t *pixels_host, int width, int height)
+{
+  if (!path || !pixels_host || width < 0 || height < 0) return fail("bad argument");
+  std::vector<uint8_t> rec((size_t)width * height * 3);
+  for (size_t i = 0; i < (size_t)width * height; i++) {
+    rec[3 * i] = (uint8_t)((pixels_host[i] & 0x00FF0000u) >> 16);
+    rec[3 * i + 1] = (uint8_t)((pixels_host[i] & 0x0000FF00u) >> 8);
+    rec[3 * i + 2] = (uint8_t)(pixels_host[i] & 0x000000FFu);
+  }
+  return write_bmp_file(path, rec.data(), width, height);
+}
+int lrf_render_bmp(lrf_ctx *h, const char *path, uint32_t w, uint32_t hgt, int grey)
+{
+  NEED_GRID(h);
+  if (!path) return fail("null path");
+  const size_t px = (size_t)w * hgt, frame = (px * 4 + 255) & ~(size_t)255;
+  if (ensure_stage(h, frame + px * 3 + 16)) return 1;
+  cudaEventRecord(h->ev0, h->stream);
+  if (px && lrf_render_dev_async(h, (uint32_t *)h->stage, w, hgt, grey)) return 1;
+  cudaEventRecord(h->ev1, h->stream);
+  launch_pack_bmp((const uint32_t *)h->stage, (uint8_t *)h->stage + frame, px, h->stream);
+  h->launches++;
+  std::vector<uint8_t> rec(px * 3);
+  if (px) CK(cudaMemcpyAsync(rec.data(), (uint8_t *)h->stage + frame, px * 3, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->t_march, h->ev0, h->ev1);
+  return write_bmp_file(path, rec.data(), (int)w, (int)hgt);
 }
 
 // ---- TV / Adam ----

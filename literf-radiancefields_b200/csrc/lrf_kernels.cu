@@ -693,6 +693,46 @@ __global__ void gen_rays_kernel(size_t n, const float *__restrict__ view_inv, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Callers either side of the path.
+// Target ingest — what stbi_loadf does to a decoded 8-bit RGBA image (ref main.cpp:72,96; external/stb_image.h:1856-1876
+// stbi__ldr_to_hdr: colour = (float)(pow(u8/255.0f, 2.2f) * 1.0f), alpha = u8/255.0f; :1241-1258 vertical flip).  The 256
+// possible colour values are tabulated on the HOST with the same libm call, so the device result is that value by
+// construction; the alpha division is a correctly rounded fp32 divide on both sides.
+__global__ void ingest_rgba8_kernel(const uchar4 *__restrict__ src, float4 *__restrict__ dst, uint32_t w, uint32_t h, int flip,
+                                    const float *__restrict__ lut)
+{
+  __shared__ float slut[256];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) slut[i] = lut[i];
+  __syncthreads();
+  const size_t n = (size_t)w * h;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i % w);
+    const uchar4 p = src[(size_t)(flip ? h - 1 - y : y) * w + x];
+    dst[i] = make_float4(slut[p.x], slut[p.y], slut[p.z], (float)p.w / 255.0f);
+  }
+}
+// reference pixels of a batch of (view, pixel) picks out of the resident targets (config 3's random-ray batches)
+__global__ void gather_targets_kernel(size_t n, const uint32_t *__restrict__ picks, const float4 *__restrict__ targets, size_t view_stride,
+                                      float4 *__restrict__ out)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = __ldg(targets + (size_t)picks[2 * i] * view_stride + picks[2 * i + 1]);
+}
+// BMP epilogue — LiteImage::SaveBMP's pixel conversion (ref external/LiteMath/Image2d.cpp:519-533): the 24-bit record is
+// {(p >> 16) & 255, (p >> 8) & 255, p & 255} in file order (a BMP record is blue, green, red: the packed frame's B byte
+// goes first).  No row padding: the reference writes width*height*3 bytes whatever the width.
+__global__ void pack_bmp_kernel(const uint32_t *__restrict__ pix, uint8_t *__restrict__ out, size_t n)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t p = pix[i];
+    out[3 * i] = (uint8_t)((p & 0x00FF0000u) >> 16);
+    out[3 * i + 1] = (uint8_t)((p & 0x0000FF00u) >> 8);
+    out[3 * i + 2] = (uint8_t)(p & 0x000000FFu);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // TV (density only; ref TVRegularisation :196-239, the SH loop :241-245 is dead — SURVEY §2 defects)
 // stage 1: V_raw(a,b,c) = trilinear(0.5) of density over {a,min(a+1,gs-1)} x ... (getVoxel :203-230), pre-relu
 __global__ void tv_voxel_kernel(int gs, const float *__restrict__ dens, float *__restrict__ vraw)
@@ -1214,6 +1254,24 @@ void launch_build_box_maps(int nv, const int32_t *xyz, size_t n, uint32_t *occ, 
 void launch_count_nonzero(const uint8_t *marks, size_t n, unsigned long long *out, cudaStream_t st)
 {
   count_nonzero_kernel<<<148 * 8, 256, 0, st>>>(marks, n, out);
+}
+void launch_ingest_rgba8(const uint8_t *src_rgba8, float *dst_rgba, uint32_t w, uint32_t h, int flip, const float *lut_dev, cudaStream_t st)
+{
+  const size_t n = (size_t)w * h;
+  if (n == 0) return;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  ingest_rgba8_kernel<<<blocks, 256, 0, st>>>((const uchar4 *)src_rgba8, (float4 *)dst_rgba, w, h, flip, lut_dev);
+}
+void launch_gather_targets(size_t n, const uint32_t *picks, const float *targets, size_t view_stride_px, float *out_rgba, cudaStream_t st)
+{
+  if (n == 0) return;
+  gather_targets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, picks, (const float4 *)targets, view_stride_px, (float4 *)out_rgba);
+}
+void launch_pack_bmp(const uint32_t *pix, uint8_t *out, size_t n, cudaStream_t st)
+{
+  if (n == 0) return;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  pack_bmp_kernel<<<blocks, 256, 0, st>>>(pix, out, n);
 }
 size_t scan_tmp_elems(size_t n) { return (n + kScanBlock - 1) / kScanBlock + 1; }
 void launch_exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *block_tmp, cudaStream_t st)

@@ -39,6 +39,10 @@ void launch_fill(float *p, size_t count, float v, cudaStream_t st);
 // layout conversion: host AoS [N][13]  <->  device planes dens[N] + col[N][12]
 void launch_aos_to_planes(const float *aos, float *planes, size_t N, cudaStream_t st);
 void launch_planes_to_aos(const float *planes, float *aos, size_t N, cudaStream_t st);
+// callers either side of the path: target ingest (stbi_loadf semantics), batch gather of target pixels, BMP record packing
+void launch_ingest_rgba8(const uint8_t *src_rgba8, float *dst_rgba, uint32_t w, uint32_t h, int flip, const float *lut_dev, cudaStream_t st);
+void launch_gather_targets(size_t n, const uint32_t *picks, const float *targets, size_t view_stride_px, float *out_rgba, cudaStream_t st);
+void launch_pack_bmp(const uint32_t *pix, uint8_t *out, size_t n, cudaStream_t st);
 // level transition
 void launch_upsample_grid(int old_gs, const float *old_planes, float *new_planes, cudaStream_t st);
 void launch_box_child_flags(const SceneDev &S_new, const int32_t *old_xyz, size_t n_old, uint32_t *flags, cudaStream_t st);   // 8 per box

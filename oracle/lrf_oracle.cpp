@@ -1037,4 +1037,38 @@ void orc_lcg_fill_grid(void *h, float D, int blob)
 }
 int orc_omp_threads(void) { return omp_get_max_threads(); }
 
+// ---- callers either side of the path ----
+// stbi_loadf's post-decode steps on 8-bit RGBA rows given in file order (ref external/stb_image.h:1241-1258 vertical
+// flip, :1856-1876 stbi__ldr_to_hdr with the default gamma 2.2f / scale 1.0f, compiled as C++: powf)
+void orc_ldr_to_hdr_rgba8(const uint8_t *rgba8, uint32_t w, uint32_t hgt, int flip, float *out)
+{
+  const float gamma = 2.2f, scale = 1.0f;
+  for (uint32_t y = 0; y < hgt; y++)
+    for (uint32_t x = 0; x < w; x++) {
+      const uint8_t *p = rgba8 + ((size_t)(flip ? hgt - 1 - y : y) * w + x) * 4;
+      float *q = out + ((size_t)y * w + x) * 4;
+      for (int k = 0; k < 3; k++) q[k] = (float)(std::pow((float)p[k] / 255.0f, gamma) * scale);
+      q[3] = (float)p[3] / 255.0f;
+    }
+}
+// LiteImage::SaveBMP + WriteBMP (ref external/LiteMath/Image2d.cpp:488-533): the bytes of the file, into out (54 + 3*w*h)
+size_t orc_bmp_bytes(const uint32_t *pixels, int w, int hgt, uint8_t *out)
+{
+  const int padded = w * hgt * 3;
+  uint8_t *f = out;
+  std::memset(f, 0, 54);
+  f[0] = 'B'; f[1] = 'M'; f[10] = 54; f[14] = 40; f[26] = 1; f[28] = 24;
+  for (int b = 0; b < 4; b++) {
+    f[2 + b] = (uint8_t)(padded >> (8 * b));
+    f[18 + b] = (uint8_t)(w >> (8 * b));
+    f[22 + b] = (uint8_t)(hgt >> (8 * b));
+  }
+  for (size_t i = 0; i < (size_t)w * hgt; i++) {
+    f[54 + 3 * i] = (uint8_t)((pixels[i] & 0x00FF0000u) >> 16);
+    f[54 + 3 * i + 1] = (uint8_t)((pixels[i] & 0x0000FF00u) >> 8);
+    f[54 + 3 * i + 2] = (uint8_t)(pixels[i] & 0x000000FFu);
+  }
+  return 54 + (size_t)padded;
+}
+
 }  // extern "C"

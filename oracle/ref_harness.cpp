@@ -21,6 +21,10 @@
 #include <iostream>
 
 #include "example_tracer/example_tracer.cpp"  // the reference, where it lies
+// stb_image exactly as main.cpp instantiates it (main.cpp:12-13: a C++ TU, so stb's `pow(float, float)` is the float overload)
+#define STB_IMAGE_IMPLEMENTATION
+#include <stb_image.h>
+#include "Image2d.h"
 
 float __enzyme_autodiff(...)
 {
@@ -254,5 +258,19 @@ uint32_t ref_pack_color(const float *rgba) { return RealColorToUint32(float4(rgb
 float ref_expf(float x) { return exp(x); }   // whatever `exp(float)` resolves to inside the reference TU (:175)
 float ref_logf(float x) { return log(x); }   // idem for `log(float)` (:173)
 int ref_omp_threads() { return omp_get_max_threads(); }
+// main.cpp:72,96: stbi_set_flip_vertically_on_load(true); stbi_loadf(path, &w, &h, &c, 4).  out (may be NULL) receives w*h*4 floats.
+int ref_stbi_loadf(const char *path, int flip, float *out, size_t cap_floats, int *w, int *hgt)
+{
+  stbi_set_flip_vertically_on_load(flip);
+  int c = 4;
+  float *p = stbi_loadf(path, w, hgt, &c, 4);
+  if (!p) return 1;
+  const size_t n = (size_t)(*w) * (*hgt) * 4;
+  if (out && n <= cap_floats) std::memcpy(out, p, n * sizeof(float));
+  free(p);
+  return 0;
+}
+// example_tracer.cpp:614
+int ref_save_bmp(const char *path, const uint32_t *pixels, int w, int hgt) { return LiteImage::SaveBMP(path, pixels, w, hgt) ? 0 : 1; }
 
 }  // extern "C"

@@ -96,6 +96,34 @@ def percell_case():
     return out
 
 
+def io_case():
+    """a seeded 37x23 RGBA8 image through the reference's own stbi_loadf (flip on, as main.cpp:72 sets it) and a packed
+    frame through its LiteImage::SaveBMP (example_tracer.cpp:614)"""
+    import ctypes as C
+    import tempfile
+    R = libs.ref("O3")
+    rng = np.random.default_rng(7)
+    w, h = 37, 23
+    rgba8 = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    rgba8[0, :8] = np.arange(8, dtype=np.uint8)[:, None] * 36      # make sure 0, 255 and small values occur
+    rgba8[1, :4] = 255
+    out = {"rgba8": rgba8}
+    with tempfile.TemporaryDirectory() as td:
+        png = os.path.join(td, "t.png")
+        libs.write_png_rgba8(png, rgba8)
+        for flip in (0, 1):
+            f = np.zeros(w * h * 4, np.float32)
+            ww, hh = C.c_int(0), C.c_int(0)
+            assert R.ref_stbi_loadf(png.encode(), flip, fp(f), f.size, C.byref(ww), C.byref(hh)) == 0 and (ww.value, hh.value) == (w, h)
+            out["loadf_flip%d" % flip] = f.reshape(h * w, 4)
+        pix = rng.integers(0, 2 ** 32, 29 * 17, dtype=np.uint64).astype(np.uint32)
+        bmp = os.path.join(td, "t.bmp")
+        assert R.ref_save_bmp(bmp.encode(), u32p(pix), 29, 17) == 0
+        out["bmp_pixels"] = pix
+        out["bmp_file"] = np.frombuffer(open(bmp, "rb").read(), dtype=np.uint8)
+    return out
+
+
 def main():
     assert libs.have_ref("O3"), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(OUT, exist_ok=True)
@@ -103,6 +131,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **forward_case(*args))
     np.savez_compressed(os.path.join(OUT, "sparse_upsampled.npz"), **sparse_case())
     np.savez_compressed(os.path.join(OUT, "percell.npz"), **percell_case())
+    np.savez_compressed(os.path.join(OUT, "io.npz"), **io_case())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -101,6 +101,8 @@ def oracle():
         "orc_expf_model": (C.c_float, [C.c_float, C.c_int]),
         "orc_lcg_fill_grid": (None, [vp, C.c_float, C.c_int]),
         "orc_omp_threads": (C.c_int, []),
+        "orc_ldr_to_hdr_rgba8": (None, [vp, C.c_uint32, C.c_uint32, C.c_int, c_fp]),
+        "orc_bmp_bytes": (C.c_size_t, [c_u32p, C.c_int, C.c_int, vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)
@@ -159,6 +161,8 @@ def ref(kind="O3"):
         "ref_expf": (C.c_float, [C.c_float]),
         "ref_logf": (C.c_float, [C.c_float]),
         "ref_omp_threads": (C.c_int, []),
+        "ref_stbi_loadf": (C.c_int, [C.c_char_p, C.c_int, c_fp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "ref_save_bmp": (C.c_int, [C.c_char_p, c_u32p, C.c_int, C.c_int]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)
@@ -211,3 +215,17 @@ def lcg_grid(gs, D=20.0, blob=False, seed=0x9E3779B97F4A7C15):
         r2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2]
         g[:, 0] *= np.exp(-(r2) / np.float32(2.0 * 0.2 * 0.2)).astype(np.float32)
     return g
+
+
+def write_png_rgba8(path, rgba8):
+    """minimal PNG writer (8-bit RGBA, filter 0, zlib) so that the reference's own stbi_loadf can be fed seeded images"""
+    import struct
+    import zlib
+    h, w, _ = rgba8.shape
+    raw = b"".join(b"\x00" + rgba8[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
