@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "liblrf_b200.so")
 SOURCES = ["lrf_kernels.cu", "lrf_capi.cu"]
-HEADERS = ["lrf_device.cuh", "lrf_kernels.cuh", os.path.join("..", "..", "include", "lrf.h")]
+HEADERS = ["lrf_device.cuh", "lrf_kernels.cuh", "lrf_fast.cuh", "lrf_wray.cuh", os.path.join("..", "..", "include", "lrf.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -24,6 +24,20 @@ def stale():
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(name, defines):
+    """kernel-variant experiments (tools/variants.py): same sources with -D knobs -> _build/variants/liblrf_b200_<name>.so"""
+    vdir = os.path.join(OUT_DIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    lib = os.path.join(vdir, "liblrf_b200_%s.so" % name)
+    cmd = [NVCC] + FLAGS + ["-D%s" % d for d in defines] + ["-o", lib] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(lib + ".log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed for variant %s (see %s.log)" % (name, lib))
+    return lib
 
 
 def build(force=False, verbose=False):

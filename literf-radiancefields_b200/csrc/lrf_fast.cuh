@@ -55,6 +55,23 @@ __device__ __forceinline__ bool fast_path_ok(const float *d)
 // MODE 0: render (stops at the reference's throughput break, ref example_tracer.cpp:131)
 // MODE 1: parity taps (keeps traversing after the break to count every hit; records voxels, cauchy, touched nodes)
 constexpr int kFastBlock = 128;   // threads per block of the kernels that use FastMarch (shared-memory stride)
+// Build-time knobs of the colour path (tools/variants.py measures the combinations; the defaults are the fastest):
+//   LRF_NEW_FROM_REGS  1: shade() takes the 4 nodes that were just gathered from registers and reads only the 4 clean
+//                         slots of the window from shared memory (4 LDS.128 instead of 8 per sample)
+//   LRF_BASIS_IN_REGS  1: the ray's 9 SH basis values stay in registers instead of shared memory (9 LDS.32 fewer per sample)
+//   LRF_TWO_PHASE      1: the colour of pairs 2,3 is gathered AFTER the traversal step and overlapped with the density
+//                         lerps + expf chain instead of being in flight across the step (26 fewer live registers:
+//                         60 -> 16 bytes of spills at 128 registers, 2.70 -> 2.26 ms per view, profiles/r1f_variants.txt)
+//                      2: rolling — one node's colour in flight at a time (slower: too little cover per gather)
+#ifndef LRF_NEW_FROM_REGS
+#define LRF_NEW_FROM_REGS 0
+#endif
+#ifndef LRF_TWO_PHASE
+#define LRF_TWO_PHASE 1
+#endif
+#ifndef LRF_BASIS_IN_REGS
+#define LRF_BASIS_IN_REGS 0
+#endif
 
 template <int MODE, bool SPARSE, bool GREY> struct FastMarch
 {
@@ -64,6 +81,9 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   float o_[3], d_[3], idir_[3];
   float4 *csm;       // this thread's colour window in shared memory: csm[slot * kFastBlock] = {R, G, B, q = sum_j sh_j Y_j(d)}
   float *ysm;        // this thread's SH basis in shared memory: ysm[j * kFastBlock], j = 0..8 (frees 9 registers)
+#if LRF_BASIS_IN_REGS
+  float yreg[9];
+#endif
   // traversal state of the CURRENT cell
   int cell[3];
   int sgn[3];
@@ -102,7 +122,13 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       float Y[9];
       sh_eval_2(df, Y);
 #pragma unroll
-      for (int j = 0; j < 9; j++) ysm[j * kFastBlock] = Y[j];
+      for (int j = 0; j < 9; j++) {
+#if LRF_BASIS_IN_REGS
+        yreg[j] = Y[j];
+#else
+        ysm[j * kFastBlock] = Y[j];
+#endif
+      }
     }
   }
 
@@ -179,15 +205,23 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   // bit J of the result: member 7-J of pair J is stale
   static __device__ __forceinline__ uint32_t high_members(uint32_t stale) { return __brev(stale) >> 24; }
 
-  template <int J> __device__ __forceinline__ void issue_pair(uint32_t stale, NodeLoad &L) const
+  template <int J> __device__ __forceinline__ uint32_t pair_node(uint32_t stale) const
   {
     const bool wA = (stale >> J) & 1u;
-    const uint32_t node = wA ? slot_node(J) : slot_node(7 - J);
-    L.td = __ldg(S.dens + node);
+    return wA ? slot_node(J) : slot_node(7 - J);
+  }
+  __device__ __forceinline__ void issue_colour(uint32_t node, NodeLoad &L) const
+  {
     if (!GREY) {
       const float4 *pc = S.col + (size_t)node * kColF4;
       L.a = __ldg(pc); L.b = __ldg(pc + 1); L.e = __ldg(pc + 2);
     }
+  }
+  template <int J> __device__ __forceinline__ void issue_pair(uint32_t stale, NodeLoad &L) const
+  {
+    const uint32_t node = pair_node<J>(stale);
+    L.td = __ldg(S.dens + node);
+    issue_colour(node, L);
   }
   struct Basis
   {
@@ -196,6 +230,11 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   };
   __device__ __forceinline__ void load_basis(Basis &Y) const
   {
+#if LRF_BASIS_IN_REGS
+    Y.Y0 = yreg[0];
+    Y.Y12 = pk2(yreg[1], yreg[2]); Y.Y34 = pk2(yreg[3], yreg[4]); Y.Y56 = pk2(yreg[5], yreg[6]); Y.Y78 = pk2(yreg[7], yreg[8]);
+    return;
+#endif
     Y.Y0 = ysm[0];
     Y.Y12 = pk2(ysm[1 * kFastBlock], ysm[2 * kFastBlock]); Y.Y34 = pk2(ysm[3 * kFastBlock], ysm[4 * kFastBlock]);
     Y.Y56 = pk2(ysm[5 * kFastBlock], ysm[6 * kFastBlock]); Y.Y78 = pk2(ysm[7 * kFastBlock], ysm[8 * kFastBlock]);
@@ -203,11 +242,20 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   // density goes to its register slot; the colour, contracted with this ray's SH basis, to the slot's shared-memory
   // cell — the slot index is an address there, so no selects and no predicates are needed (a clean pair just rewrites
   // member 7-J with its own data)
-  template <int J> __device__ __forceinline__ void commit_pair(uint32_t stale, uint32_t hi, const NodeLoad &L, const Basis &Y)
+  template <int J> __device__ __forceinline__ void commit_density(uint32_t stale, uint32_t hi, float td)
   {
     const bool wA = (stale >> J) & 1u, wB = ((hi & ~stale) >> J) & 1u;
-    dn[J] = wA ? L.td : dn[J];
-    dn[7 - J] = wB ? L.td : dn[7 - J];
+    dn[J] = wA ? td : dn[J];
+    dn[7 - J] = wB ? td : dn[7 - J];
+  }
+  template <int J> __device__ __forceinline__ void commit_pair(uint32_t stale, uint32_t hi, const NodeLoad &L, const Basis &Y, float4 &fresh)
+  {
+    commit_density<J>(stale, hi, L.td);
+    commit_colour<J>(stale, L, Y, fresh);
+  }
+  template <int J> __device__ __forceinline__ void commit_colour(uint32_t stale, const NodeLoad &L, const Basis &Y, float4 &fresh)
+  {
+    const bool wA = (stale >> J) & 1u;
     if (GREY) return;
     u64 q2 = mul2(pk2(L.b.x, L.b.y), Y.Y12);
     q2 = fma2(pk2(L.b.z, L.b.w), Y.Y34, q2);
@@ -216,7 +264,8 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     float ql, qh;
     upk2(q2, ql, qh);
     const float q = fmaf(L.a.w, Y.Y0, ql + qh);
-    csm[(wA ? J : 7 - J) * kFastBlock] = make_float4(L.a.x, L.a.y, L.a.z, q);
+    fresh = make_float4(L.a.x, L.a.y, L.a.z, q);
+    csm[(wA ? J : 7 - J) * kFastBlock] = fresh;
   }
   __device__ __forceinline__ void refill_blocking(uint32_t stale)
   {
@@ -226,7 +275,8 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       issue_pair<0>(stale, L0); issue_pair<1>(stale, L1); issue_pair<2>(stale, L2); issue_pair<3>(stale, L3);
       Basis Y;
       if (!GREY) load_basis(Y);
-      commit_pair<0>(stale, hi, L0, Y); commit_pair<1>(stale, hi, L1, Y); commit_pair<2>(stale, hi, L2, Y); commit_pair<3>(stale, hi, L3, Y);
+      float4 f0, f1, f2, f3;
+      commit_pair<0>(stale, hi, L0, Y, f0); commit_pair<1>(stale, hi, L1, Y, f1); commit_pair<2>(stale, hi, L2, Y, f2); commit_pair<3>(stale, hi, L3, Y, f3);
       // served this round: the low member of each pair if stale, else the high member
       const uint32_t lowm = stale & 0x0fu;
       stale &= ~(lowm | (__brev((hi & ~lowm & 0x0fu)) >> 24));
@@ -260,7 +310,14 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   }
 
   // shade one sample from the window; false = the reference's throughput break fired
-  __device__ __forceinline__ bool shade(const Geom &g)
+  // fresh[J] = the node gathered for pair (J, 7-J) this step, already contracted; fresh_low bit J set = it sits in slot J
+  // (else in slot 7-J).  Only used when LRF_NEW_FROM_REGS.
+  struct Sig
+  {
+    float tr, wgt;
+  };
+  // density part of a sample (decision path, bit-exact): transmittance of the step and the compositing weight
+  __device__ __forceinline__ Sig shade_sigma(const Geom &g)
   {
     const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
     const float *lf = g.lf;
@@ -279,8 +336,21 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     float sigma = lm_lerp(od[2] ? B[1] : B[0], od[2] ? B[0] : B[1], lf[2]);
     if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
     if (MODE == 1) cauchy += logf(1.0f + 2.0f * sigma * sigma);  // :173
-    const float tr = expf_libm(-sigma * g.delta, etab);        // :175
-    const float wgt = thr * (1.0f - tr);                       // :187
+    Sig r;
+    r.tr = expf_libm(-sigma * g.delta, etab);                  // :175
+    r.wgt = thr * (1.0f - r.tr);                               // :187
+    return r;
+  }
+  __device__ __forceinline__ bool shade(const Geom &g, const float4 *fresh, uint32_t fresh_low)
+  {
+    return shade_colour(g, shade_sigma(g), fresh, fresh_low);
+  }
+  // colour part (1e-4-tolerance path) + the throughput update; false = the reference's throughput break fired
+  __device__ __forceinline__ bool shade_colour(const Geom &g, const Sig sg, const float4 *fresh, uint32_t fresh_low)
+  {
+    const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
+    const float *lf = g.lf;
+    const float tr = sg.tr, wgt = sg.wgt;
     if (wgt != 0.0f) {
       if (GREY) { col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt; }
       else {
@@ -292,6 +362,23 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
         const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
         const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
         // two independent accumulation chains per pair of channels (latency), merged at the end
+#if LRF_NEW_FROM_REGS
+        u64 RG0, BQ0, RG1, BQ1;
+#pragma unroll
+        for (int J = 0; J < 4; J++) {
+          const bool lowNew = (fresh_low >> J) & 1u;
+          const float wN = lowNew ? w[J] : w[7 - J], wO = lowNew ? w[7 - J] : w[J];
+          const float4 co = csm[(lowNew ? 7 - J : J) * kFastBlock], cn = fresh[J];
+          const u64 wn2 = pk2(wN, wN), wo2 = pk2(wO, wO);
+          if (J == 0) {
+            RG0 = mul2(wn2, pk2(cn.x, cn.y)); BQ0 = mul2(wn2, pk2(cn.z, cn.w));
+            RG1 = mul2(wo2, pk2(co.x, co.y)); BQ1 = mul2(wo2, pk2(co.z, co.w));
+          } else {
+            RG0 = fma2(wn2, pk2(cn.x, cn.y), RG0); BQ0 = fma2(wn2, pk2(cn.z, cn.w), BQ0);
+            RG1 = fma2(wo2, pk2(co.x, co.y), RG1); BQ1 = fma2(wo2, pk2(co.z, co.w), BQ1);
+          }
+        }
+#else
         const float4 c0 = csm[0], c1 = csm[kFastBlock];
         u64 RG0 = mul2(pk2(w[0], w[0]), pk2(c0.x, c0.y)), BQ0 = mul2(pk2(w[0], w[0]), pk2(c0.z, c0.w));
         u64 RG1 = mul2(pk2(w[1], w[1]), pk2(c1.x, c1.y)), BQ1 = mul2(pk2(w[1], w[1]), pk2(c1.z, c1.w));
@@ -304,6 +391,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
           RG1 = fma2(wk1, pk2(cb.x, cb.y), RG1);
           BQ1 = fma2(wk1, pk2(cb.z, cb.w), BQ1);
         }
+#endif
         float R, G, Bc, Q, R1, G1, B1, Q1;
         upk2(RG0, R, G); upk2(BQ0, Bc, Q); upk2(RG1, R1, G1); upk2(BQ1, B1, Q1);
         R += R1; G += G1; Bc += B1; Q += Q1;
@@ -471,6 +559,47 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
         hi = 0;
       }
       NodeLoad L0, L1, L2, L3;
+#if LRF_TWO_PHASE == 2
+      // rolling gather: the four densities and ONE node's colour cross the traversal step; the other three colours are
+      // gathered one after the other, each behind a slice of the density / expf arithmetic (12 registers in flight)
+      const uint32_t node1 = pair_node<1>(stale), node2 = pair_node<2>(stale), node3 = pair_node<3>(stale);
+      issue_pair<0>(stale, L0);
+      L1.td = __ldg(S.dens + node1); L2.td = __ldg(S.dens + node2); L3.td = __ldg(S.dens + node3);
+      dirty = 0;
+      Geom g;
+      geometry(g);
+      const bool more = next_cell();
+      Basis Y;
+      if (!GREY) load_basis(Y);
+      float4 fresh[4];
+      issue_colour(node1, L1);
+      commit_pair<0>(stale, hi, L0, Y, fresh[0]);
+      commit_density<1>(stale, hi, L1.td); commit_density<2>(stale, hi, L2.td); commit_density<3>(stale, hi, L3.td);
+      issue_colour(node2, L2);
+      const Sig sg = shade_sigma(g);
+      commit_colour<1>(stale, L1, Y, fresh[1]);
+      issue_colour(node3, L3);
+      commit_colour<2>(stale, L2, Y, fresh[2]);
+      commit_colour<3>(stale, L3, Y, fresh[3]);
+      if (!shade_colour(g, sg, fresh, stale & 0x0fu)) {
+#elif LRF_TWO_PHASE
+      const uint32_t node2 = pair_node<2>(stale), node3 = pair_node<3>(stale);
+      issue_pair<0>(stale, L0); issue_pair<1>(stale, L1);
+      L2.td = __ldg(S.dens + node2); L3.td = __ldg(S.dens + node3);
+      dirty = 0;
+      Geom g;
+      geometry(g);
+      const bool more = next_cell();
+      Basis Y;
+      if (!GREY) load_basis(Y);
+      float4 fresh[4];
+      commit_pair<0>(stale, hi, L0, Y, fresh[0]); commit_pair<1>(stale, hi, L1, Y, fresh[1]);
+      commit_density<2>(stale, hi, L2.td); commit_density<3>(stale, hi, L3.td);
+      issue_colour(node2, L2); issue_colour(node3, L3);       // in flight across the density lerps + expf chain
+      const Sig sg = shade_sigma(g);
+      commit_colour<2>(stale, L2, Y, fresh[2]); commit_colour<3>(stale, L3, Y, fresh[3]);
+      if (!shade_colour(g, sg, fresh, stale & 0x0fu)) {
+#else
       issue_pair<0>(stale, L0); issue_pair<1>(stale, L1); issue_pair<2>(stale, L2); issue_pair<3>(stale, L3);
       dirty = 0;
       // 2. this cell's geometry, then the whole traversal step to the next cell — no memory needed
@@ -480,8 +609,11 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       // 3. consume the gathers (second round only after a full reset), shade
       Basis Y;
       if (!GREY) load_basis(Y);
-      commit_pair<0>(stale, hi, L0, Y); commit_pair<1>(stale, hi, L1, Y); commit_pair<2>(stale, hi, L2, Y); commit_pair<3>(stale, hi, L3, Y);
-      if (!shade(g)) {
+      float4 fresh[4];
+      commit_pair<0>(stale, hi, L0, Y, fresh[0]); commit_pair<1>(stale, hi, L1, Y, fresh[1]); commit_pair<2>(stale, hi, L2, Y, fresh[2]);
+      commit_pair<3>(stale, hi, L3, Y, fresh[3]);
+      if (!shade(g, fresh, stale & 0x0fu)) {
+#endif
         alive = false;
         if (MODE == 0) return;
       }

@@ -355,8 +355,11 @@ inline uint32_t tile_grid(uint32_t w, uint32_t h)
 
 // Forward render, one thread per pixel.  Rays that cannot take the fast path (a zero / non-finite reciprocal direction
 // component) are appended to a fallback list and rendered by render_fallback_kernel with the generic march.
+#ifndef LRF_RENDER_MINB
+#define LRF_RENDER_MINB 4   // resident blocks per SM the register allocation is sized for (tools/variants.py)
+#endif
 template <bool SPARSE, bool GREY>
-__global__ void __launch_bounds__(kBlock, 4) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
+__global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
                                                                  uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list)
 {
   __shared__ uint64_t etab[32];
@@ -1138,6 +1141,16 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
 {
   cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
   const dim3 g(tile_grid(w, h));
+#ifdef LRF_CARVEOUT
+  {  // shared-memory carve-out of the unified L1 (percent): the window needs 21 KB per block, the rest is better spent as L1
+    static bool once = false;
+    if (!once) {
+      once = true;
+      cudaFuncSetAttribute(render_image_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, LRF_CARVEOUT);
+      cudaFuncSetAttribute(render_image_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, LRF_CARVEOUT);
+    }
+  }
+#endif
   if (S.occ) {
     if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
     else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);

@@ -1,0 +1,86 @@
+"""Kernel-variant experiments for the forward march.
+    python tools/variants.py build  name=DEF1,DEF2 ...     (here; parallel nvcc, output under _build/variants/)
+    python tools/variants.py run [n_views]                 (on the GPU box; times every built variant + the default library)
+Each run renders the bench workload's views (256^3 D=20, 800x800), prints ms/view (CUDA events on the context stream) and a
+checksum of the frames so that variants can be checked for identical output."""
+import concurrent.futures as cf
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VDIR = os.path.join(ROOT, "literf-radiancefields_b200", "_build", "variants")
+
+
+def build(specs):
+    sys.path.insert(0, os.path.join(ROOT, "literf-radiancefields_b200"))
+    import build as b
+    with cf.ThreadPoolExecutor(max_workers=6) as ex:
+        futs = {}
+        for spec in specs:
+            name, _, defs = spec.partition("=")
+            futs[ex.submit(b.build_variant, name, [d for d in defs.split(",") if d])] = name
+        for f in cf.as_completed(futs):
+            lib = f.result()
+            log = open(lib + ".log").read()
+            info = [l for l in log.splitlines() if "render_image_kernelILb0ELb0" in l]
+            # the ptxas line after "Compiling entry function ... render_image_kernel<0,0>" holds registers / spills
+            lines = log.splitlines()
+            used = ""
+            for i, l in enumerate(lines):
+                if "Compiling entry function" in l and "render_image_kernelILb0ELb0" in l:
+                    used = " | ".join(x.strip() for x in lines[i + 1:i + 4])
+                    break
+            print(futs[f], "->", used)
+
+
+def time_one(n_views):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import __graft_entry__ as ge
+    import bench
+    pkg = ge.package()
+    t = pkg.RayMarcherExample(0)
+    t.InitGrid(bench.GS)
+    t.set_grid(bench.lcg_grid(bench.GS, bench.DENSITY_SCALE))
+    proj_inv, views = bench.cameras(pkg, 0, 1)
+    t.set_proj_inv(proj_inv)
+    frame = pkg.DeviceBuffer(t, bench.W * bench.H * 4)
+    host = np.zeros(bench.W * bench.H, np.uint32)
+    pick = [(k * 13) % len(views) for k in range(n_views)]
+    for k in pick[:3]:
+        t.set_view_inv(views[k])
+        t.render_dev_async(frame.ptr, bench.W, bench.H)
+    t.sync()
+    ck = 0
+    t.timer_start()
+    for k in pick:
+        t.set_view_inv(views[k])
+        t.render_dev_async(frame.ptr, bench.W, bench.H)
+    ms = t.timer_stop_ms()
+    for k in pick[:4]:
+        t.set_view_inv(views[k])
+        t.render_dev_async(frame.ptr, bench.W, bench.H)
+        frame.download(host)
+        ck = (ck * 1000003 + int(host.astype(np.uint64).sum())) % (1 << 61)
+    print(json.dumps({"lib": os.path.basename(os.environ.get("LRF_B200_LIB", "default")), "ms_per_view": ms / len(pick), "Mrays_s": bench.W * bench.H * len(pick) / ms / 1e3,
+                      "checksum": ck}))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build":
+        build(sys.argv[2:])
+    elif sys.argv[1] == "one":
+        time_one(int(sys.argv[2]))
+    else:
+        n = sys.argv[2] if len(sys.argv) > 2 else "30"
+        libs = [None] + sorted(glob.glob(os.path.join(VDIR, "*.so")))
+        for lib in libs:
+            env = dict(os.environ)
+            if lib:
+                env["LRF_B200_LIB"] = lib
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "one", n], env=env, capture_output=True, text=True)
+            print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + str(lib) + r.stderr[-400:])
