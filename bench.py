@@ -38,6 +38,28 @@ GS = 256
 W = H = 800
 VIEWS = 100
 DENSITY_SCALE = 20.0
+ASPECT = 1.0
+FILL_MODE = None         # None: host LCG grid uploaded (default workload); 0/1/2: generated on the device (lrf_fill_synthetic)
+SPARSE = False
+WORKLOAD = "render256"
+# --workload: the default is the configuration the metric is quoted on (BASELINE.json configs[1]); the others are the larger
+# configurations, measured the same way (their lines are kept under profiles/, the driver only runs the default)
+WORKLOADS = {
+    "render256": dict(gs=256, w=800, h=800, views=100, D=20.0, aspect=1.0, fill=None, sparse=False,
+                      text="forward render, dense 256^3 SH-degree-2 grid (13 fp32/node, synthetic LCG, density scale 20), 800x800, 100 orbit views per GPU (BASELINE.json configs[1])"),
+    "sparse512": dict(gs=512, w=800, h=800, views=20, D=20.0, aspect=1.0, fill=2, sparse=True,
+                      text="forward render, sparse box set at 512^3 (density > 0 inside a sphere of radius 0.288, boxes kept by the RebuildOctree criterion: ~10 % of 511^3), 800x800, 20 orbit views per GPU (BASELINE.json configs[3])"),
+    "hires512_1080p": dict(gs=512, w=1920, h=1080, views=8, D=20.0, aspect=16.0 / 9.0, fill=0, sparse=False,
+                           text="forward render, dense 512^3 grid (synthetic LCG, density scale 20), 1920x1080 frames, 8 orbit views per GPU (BASELINE.json configs[4])"),
+    "hires512_4k": dict(gs=512, w=3840, h=2160, views=8, D=20.0, aspect=16.0 / 9.0, fill=0, sparse=False,
+                        text="forward render, dense 512^3 grid (synthetic LCG, density scale 20), 3840x2160 frames, 8 orbit views per GPU (BASELINE.json configs[4])"),
+}
+
+
+def select_workload(name):
+    global GS, W, H, VIEWS, DENSITY_SCALE, ASPECT, FILL_MODE, SPARSE, WORKLOAD
+    wl = WORKLOADS[name]
+    GS, W, H, VIEWS, DENSITY_SCALE, ASPECT, FILL_MODE, SPARSE, WORKLOAD = wl["gs"], wl["w"], wl["h"], wl["views"], wl["D"], wl["aspect"], wl["fill"], wl["sparse"], name
 CPU_SAMPLE = 96          # cpu_baseline / reference arm: one CPU_SAMPLE x CPU_SAMPLE frame per step
 METRIC = "forward_render_Mrays_per_s"
 
@@ -117,7 +139,7 @@ def sharding():
 
 def cameras(pkg, rank, world):
     """weak scaling: a VIEWS*world-view orbit dealt round-robin, VIEWS views per rank"""
-    proj_inv = pkg.inverse4x4(pkg.perspective(45.0, 1.0, 0.1, 100.0))
+    proj_inv = pkg.inverse4x4(pkg.perspective(45.0, ASPECT, 0.1, 100.0))
     views = [pkg.inverse4x4(pkg.orbit_view(k, VIEWS * world)) for k in sharding().shard_views(VIEWS * world, rank, world)]
     return proj_inv, views
 
@@ -173,6 +195,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    select_workload("render256")       # the CPU arm is timed on the configuration the metric is quoted on
     grid = lcg_grid(GS, DENSITY_SCALE)
     steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
     rates, info = cpu_reference_rate(grid, steps, warmup)
@@ -192,11 +215,10 @@ def run_reference(args):
 
 
 def workload_config(world):
-    return {"workload": "forward render, dense %d^3 SH-degree-2 grid (13 fp32/node, synthetic LCG, density scale %g), %dx%d, %d orbit views per GPU (BASELINE.json configs[1])"
-            % (GS, DENSITY_SCALE, W, H, VIEWS),
+    return {"workload": WORKLOADS[WORKLOAD]["text"], "name": WORKLOAD,
             "grid": GS, "width": W, "height": H, "views_per_gpu": VIEWS, "rays_per_step_per_gpu": W * H * VIEWS,
             "density_scale": DENSITY_SCALE, "parallelism": "views sharded over %d GPU(s), grid replica per GPU, no collective" % world,
-            "l2": "inputs exceed L2: the 872 MB grid is re-read by every view (L2 = 126 MB); no explicit flush needed"}
+            "l2": "inputs exceed L2: the %d MB grid is re-read by every view (L2 = 126 MB); no explicit flush needed" % (52 * GS ** 3 // 10 ** 6)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -208,7 +230,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the (extra) training-iteration measurement")
+    ap.add_argument("--workload", default="render256", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.workload != "render256":
+        args.no_train = True          # the training extra and the CPU arm belong to the default workload
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         return run_reference(args)
 
@@ -232,8 +259,14 @@ def main():
     t = pkg.RayMarcherExample(local)          # raises if the CUDA library / a B200 is missing: no fallback
     t.InitGrid(GS)
     t.SetBoundingBox([0, 0, 0], [1, 1, 1])
-    grid = lcg_grid(GS, DENSITY_SCALE)
-    t.set_grid(grid)
+    grid = None
+    if FILL_MODE is None:
+        grid = lcg_grid(GS, DENSITY_SCALE)
+        t.set_grid(grid)
+    else:
+        t.fill_synthetic(DENSITY_SCALE, FILL_MODE)
+    if SPARSE:
+        t.RebuildOctree()              # keeps the boxes whose centre density is > 0 (ref example_tracer.cpp:449-489)
     proj_inv, views = cameras(pkg, rank, world)
     t.set_proj_inv(proj_inv)
     frame = pkg.DeviceBuffer(t, W * H * 4)
@@ -296,7 +329,7 @@ def main():
     e2e_value = rays_per_step * e2e_steps / e2e_s / 1e6
 
     # ---- roofline of the dominant kernel ----
-    sel = list(range(0, VIEWS, 10))
+    sel = list(range(0, VIEWS, 10 if VIEWS >= 20 else 2))
     touched = []
     for k in sel:
         t.set_view_inv(views[k])
@@ -309,8 +342,13 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                 "kernel": "render_image_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "n_touched_nodes_mean": n_touched, "n_touched_sampled_views": len(sel), "peak_source": peak_src}
+    if WORKLOAD != "render256":
+        roofline["traffic"] = None     # the committed ncu capture is of the default workload
 
     extra = {"e2e_checksum": checksum}
+    if SPARSE:
+        extra["boxes"] = int(t.box_count())
+        extra["occupancy"] = t.box_count() / float((GS - 1) ** 3)
     if not args.no_train:
         try:
             extra["train"] = train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier)

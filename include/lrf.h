@@ -42,6 +42,10 @@ int lrf_sync(lrf_ctx *h);
 /* ---- grid / boxes ---------------------------------------------------------------------------- */
 /* ref: InitGrid(float), example_tracer.h:51-91 — density 0.01, other 12 floats 0.1, dense (gs-1)^3 boxes */
 int lrf_init_grid(lrf_ctx *h, int gs);
+/* no reference counterpart: the seeded synthetic grids of the benchmark/test workloads, generated in place on
+ * the device.  mode 0 = LCG grid (density_scale D: 20 "opaque", 2 "thin"), 1 = LCG x Gaussian blob, 2 = sphere-signed
+ * density (positive inside r = 0.288, negative outside: the ~10 % occupancy scene of BASELINE config 4). */
+int lrf_fill_synthetic(lrf_ctx *h, float density_scale, int mode);
 /* ref: InitGrad(), example_tracer.h:93-96 (allocates; contents zero) */
 int lrf_init_grad(lrf_ctx *h);
 /* ref: zeroGrad(), example_tracer.h:104-109 */

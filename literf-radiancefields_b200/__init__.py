@@ -81,6 +81,7 @@ SIGNATURES = {
     "lrf_launch_count": (C.c_uint64, [_vp]),
     "lrf_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lrf_count_touched_nodes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
+    "lrf_fill_synthetic": (C.c_int, [_vp, C.c_float, C.c_int]),
     "lrf_model_save": (C.c_int, [_vp, C.c_char_p]),
     "lrf_model_load": (C.c_int, [_vp, C.c_char_p]),
     "lrf_targets_resize": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32]),
@@ -414,6 +415,10 @@ class RayMarcherExample:
 
     def launch_count(self):
         return self.lib.lrf_launch_count(self.h)
+
+    def fill_synthetic(self, density_scale=20.0, mode=0):
+        """seeded synthetic grid of SURVEY 8(d) generated on the device (== tests/libs.py::lcg_grid bit for bit)"""
+        self._ck(self.lib.lrf_fill_synthetic(self.h, float(density_scale), int(mode)))
 
     # ---- callers either side of the path (SURVEY 8f rows 2-4) ----
     def save_model(self, path):

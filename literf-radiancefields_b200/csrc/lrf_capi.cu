@@ -189,6 +189,17 @@ int lrf_init_grid(lrf_ctx *h, int gs)
   return 0;
 }
 
+// SURVEY 8(d) synthetic grid, generated on the device (bit-identical to the host generator the tests use)
+int lrf_fill_synthetic(lrf_ctx *h, float density_scale, int mode)
+{
+  NEED_GRID(h);
+  if (mode < 0 || mode > 2) return fail("mode must be 0 (LCG), 1 (LCG x Gaussian blob) or 2 (sphere: positive inside r = 0.288, negative outside)");
+  launch_fill_synthetic(h->gs, density_scale, mode, h->params, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int lrf_init_grad(lrf_ctx *h) { return lrf_zero_grad(h); }   // resize() value-initialises in the reference
 
 int lrf_zero_grad(lrf_ctx *h)
@@ -684,14 +695,12 @@ int lrf_upsample_grid(lrf_ctx *h)
   if (was_dense) {
     // materialise the dense old-level list so that lrf_upsample_boxes can subdivide it
     const int n = old_gs - 1;
-    std::vector<int32_t> xyz((size_t)n * n * n * 3);
-    size_t i = 0;
-    for (int z = 0; z < n; z++)
-      for (int y = 0; y < n; y++)
-        for (int x = 0; x < n; x++, i++) { xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z; }
-    CK(cudaMalloc(&h->boxes, (xyz.size() ? xyz.size() : 3) * sizeof(int32_t)));
-    CK(cudaMemcpy(h->boxes, xyz.data(), xyz.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    h->n_boxes = (size_t)n * n * n;
+    const size_t nb = (size_t)n * n * n;
+    CK(cudaMalloc(&h->boxes, (nb ? nb : 1) * 3 * sizeof(int32_t)));
+    launch_dense_boxes(n, h->boxes, h->stream);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_boxes = nb;
   } else { h->boxes = old_boxes; h->n_boxes = old_nb; }
   h->dense = false;  // old-level boxes: maps are rebuilt by lrf_upsample_boxes
   return 0;
@@ -733,10 +742,12 @@ int lrf_upsample_boxes(lrf_ctx *h)
 int lrf_rebuild_boxes(lrf_ctx *h)
 {
   NEED_GRID(h);
-  if (h->dense) {
-    std::vector<int32_t> xyz(h->n_boxes * 3);
-    if (lrf_get_boxes(h, xyz.data())) return 1;
-    if (lrf_set_boxes(h, xyz.data(), h->n_boxes)) return 1;
+  if (h->dense) {   // materialise the InitGrid list on the device (133 M boxes at 512^3: no host round trip)
+    const size_t n = h->n_boxes;
+    CK(cudaMalloc(&h->boxes, (n ? n : 1) * 3 * sizeof(int32_t)));
+    launch_dense_boxes(h->gs - 1, h->boxes, h->stream);
+    h->launches++;
+    h->dense = false;   // compact_boxes reads h->boxes and installs the filtered list (+ occupancy maps)
   }
   return compact_boxes(h, false);
 }

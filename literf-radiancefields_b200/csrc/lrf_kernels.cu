@@ -696,6 +696,56 @@ __global__ void gen_rays_kernel(size_t n, const float *__restrict__ view_inv, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Synthetic grids of SURVEY 8(d), generated in place (a 512^3 grid is 7 GB: it never exists on the host).  Same values,
+// bit for bit, as the host generator tests/libs.py::lcg_grid: 64-bit LCG s <- s*A + C from the fixed seed, 13 draws per node
+// in node order, u = (s >> 40) / 2^24.  Thread i jumps the LCG ahead by 13*i steps (square-and-multiply on the affine map).
+//   mode 0: density = D*(u - 0.25), RGB = u, sh0 = 1 + 2u, sh1..8 = u - 0.5          ("opaque" D = 20 / "thin" D = 2)
+//   mode 1: mode 0 with the density multiplied by the Gaussian blob exp(-|p - .5|^2 / (2 * 0.2^2))
+//   mode 2: |mode-0 density| + 0.5 inside the sphere of radius 0.288 about the centre (volume fraction 0.100), minus that
+//           outside — BASELINE config 4's sparse scene: the box criterion (centre density > 0) keeps ~10 % of the voxels
+__global__ void fill_synthetic_kernel(int gs, float D, int mode, float *__restrict__ dens, float4 *__restrict__ col)
+{
+  const size_t N = (size_t)gs * gs * gs, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint64_t A = 6364136223846793005ULL, Cc = 1442695040888963407ULL;
+  // affine map after k steps: s -> a*s + c, built by doubling
+  uint64_t a = 1, c = 0, pa = A, pc = Cc;
+  for (uint64_t k = 13ULL * i; k; k >>= 1) {
+    if (k & 1) { a = pa * a; c = pa * c + pc; }
+    pc = pa * pc + pc;
+    pa = pa * pa;
+  }
+  uint64_t st = a * 0x9E3779B97F4A7C15ULL + c;
+  float u[13];
+#pragma unroll
+  for (int j = 0; j < 13; j++) {
+    st = st * A + Cc;
+    u[j] = (float)(st >> 40) / 16777216.0f;
+  }
+  float d0 = D * (u[0] - 0.25f);
+  if (mode != 0) {
+    const int x = (int)(i % gs), y = (int)((i / gs) % gs), z = (int)(i / ((size_t)gs * gs));
+    const float px = ((float)x + 0.5f) / (float)gs - 0.5f, py = ((float)y + 0.5f) / (float)gs - 0.5f, pz = ((float)z + 0.5f) / (float)gs - 0.5f;
+    const float r2 = px * px + py * py + pz * pz;
+    if (mode == 1) d0 *= (float)exp((double)(-(r2) / (float)(2.0 * 0.2 * 0.2)));   // numpy float32 exp == correctly rounded here: tests pin it
+    else d0 = (r2 < 0.288f * 0.288f) ? (fabsf(d0) + 0.5f) : -(fabsf(d0) + 0.5f);
+  }
+  dens[i] = d0;
+  col[i * 3] = make_float4(u[1], u[2], u[3], 1.0f + 2.0f * u[4]);
+  col[i * 3 + 1] = make_float4(u[5] - 0.5f, u[6] - 0.5f, u[7] - 0.5f, u[8] - 0.5f);
+  col[i * 3 + 2] = make_float4(u[9] - 0.5f, u[10] - 0.5f, u[11] - 0.5f, u[12] - 0.5f);
+}
+// the InitGrid box list (gs-1)^3 in id order (ref example_tracer.h:69-85), materialised on the device
+__global__ void dense_boxes_kernel(int n, int32_t *__restrict__ xyz)
+{
+  const size_t total = (size_t)n * n * n, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  xyz[3 * i] = (int32_t)(i % n);
+  xyz[3 * i + 1] = (int32_t)((i / n) % n);
+  xyz[3 * i + 2] = (int32_t)(i / ((size_t)n * n));
+}
+
+// ------------------------------------------------------------------------------------------------
 // Callers either side of the path.
 // Target ingest — what stbi_loadf does to a decoded 8-bit RGBA image (ref main.cpp:72,96; external/stb_image.h:1856-1876
 // stbi__ldr_to_hdr: colour = (float)(pow(u8/255.0f, 2.2f) * 1.0f), alpha = u8/255.0f; :1241-1258 vertical flip).  The 256
@@ -1285,6 +1335,16 @@ void launch_pack_bmp(const uint32_t *pix, uint8_t *out, size_t n, cudaStream_t s
   if (n == 0) return;
   const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   pack_bmp_kernel<<<blocks, 256, 0, st>>>(pix, out, n);
+}
+void launch_fill_synthetic(int gs, float D, int mode, float *planes, cudaStream_t st)
+{
+  const size_t N = (size_t)gs * gs * gs;
+  fill_synthetic_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, D, mode, planes, (float4 *)(planes + N));
+}
+void launch_dense_boxes(int n_vox_axis, int32_t *xyz, cudaStream_t st)
+{
+  const size_t total = (size_t)n_vox_axis * n_vox_axis * n_vox_axis;
+  if (total) dense_boxes_kernel<<<blocks_for(total, 256), 256, 0, st>>>(n_vox_axis, xyz);
 }
 size_t scan_tmp_elems(size_t n) { return (n + kScanBlock - 1) / kScanBlock + 1; }
 void launch_exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *block_tmp, cudaStream_t st)

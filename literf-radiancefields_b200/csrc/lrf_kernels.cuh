@@ -43,6 +43,9 @@ void launch_planes_to_aos(const float *planes, float *aos, size_t N, cudaStream_
 void launch_ingest_rgba8(const uint8_t *src_rgba8, float *dst_rgba, uint32_t w, uint32_t h, int flip, const float *lut_dev, cudaStream_t st);
 void launch_gather_targets(size_t n, const uint32_t *picks, const float *targets, size_t view_stride_px, float *out_rgba, cudaStream_t st);
 void launch_pack_bmp(const uint32_t *pix, uint8_t *out, size_t n, cudaStream_t st);
+// SURVEY 8(d) synthetic grids generated in place; dense (gs-1)^3 box list in id order
+void launch_fill_synthetic(int gs, float D, int mode, float *planes, cudaStream_t st);
+void launch_dense_boxes(int n_vox_axis, int32_t *xyz, cudaStream_t st);
 // level transition
 void launch_upsample_grid(int old_gs, const float *old_planes, float *new_planes, cudaStream_t st);
 void launch_box_child_flags(const SceneDev &S_new, const int32_t *old_xyz, size_t n_old, uint32_t *flags, cudaStream_t st);   // 8 per box

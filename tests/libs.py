@@ -178,7 +178,7 @@ def np_view(ptr, n, dtype=np.float32):
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
 
 
-def lcg_grid(gs, D=20.0, blob=False, seed=0x9E3779B97F4A7C15):
+def lcg_grid(gs, D=20.0, blob=False, seed=0x9E3779B97F4A7C15, sphere=False):
     """SURVEY 8(d) synthetic grid (numpy restatement, vectorised): [gs^3, 13] float32."""
     n = gs ** 3 * 13
     # LCG is sequential; use the closed-form jump via modular arithmetic on python ints in blocks
@@ -214,6 +214,13 @@ def lcg_grid(gs, D=20.0, blob=False, seed=0x9E3779B97F4A7C15):
         p = [((v.astype(np.float32) + np.float32(0.5)) / np.float32(gs) - np.float32(0.5)) for v in (x, y, z)]
         r2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2]
         g[:, 0] *= np.exp(-(r2) / np.float32(2.0 * 0.2 * 0.2)).astype(np.float32)
+    if sphere:   # BASELINE config 4: positive density inside r = 0.288 (volume fraction 0.100), negative outside
+        idx = np.arange(gs ** 3)
+        x, y, z = idx % gs, (idx // gs) % gs, idx // (gs * gs)
+        p = [((v.astype(np.float32) + np.float32(0.5)) / np.float32(gs) - np.float32(0.5)) for v in (x, y, z)]
+        r2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2]
+        mag = np.abs(g[:, 0]) + np.float32(0.5)
+        g[:, 0] = np.where(r2 < np.float32(0.288) * np.float32(0.288), mag, -mag)
     return g
 
 
