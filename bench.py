@@ -426,12 +426,35 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     ms = max_over_ranks(t.timer_stop_ms())
     barrier()
     ms_noex = None
+    ms_peer = None
     if grad_tensor is not None:   # same iterations without the exchange step: the all-reduce share of an iteration
         t.timer_start()
         for it in range(3, 3 + iters):
             one(it, exchange=False)
         ms_noex = max_over_ranks(t.timer_stop_ms())
         barrier()
+        # the fused exchange over NVLink peer memory: barrier, own slab {TV + sum of all ranks' gradients + Adam, parameters
+        # stored into every replica}, barrier, gradient zeroing (sharding.PeerExchange / lrf_train_percell_peer_async)
+        import torch
+        t.optimizerInit()
+        t.zeroGrad()
+        ex = shard.PeerExchange(t, dist, torch)
+
+        def one_peer(it):
+            off = it * batch
+            t._ck(t.lib.lrf_gen_rays_dev_async(t.h, batch, vi_dev.ptr, picks_dev.ptr + off * 8, W, H, o_dev.ptr, d_dev.ptr))
+            t._ck(t.lib.lrf_rays_grad_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
+            ex.percell(it)
+
+        for it in range(3):
+            one_peer(it)
+        barrier()
+        t.timer_start()
+        for it in range(3, 3 + iters):
+            one_peer(it)
+        ms_peer = max_over_ranks(t.timer_stop_ms())
+        barrier()
+        ex.close()
     # break-down: backward alone / per-cell alone
     t.timer_start()
     for it in range(5):
@@ -447,11 +470,15 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     # node traffic (52 B read + 2 x 52 B gradient read-modify-write per touched node; counted as touched-node upper bound
     # rays x samples x 8 is NOT used — only the dense per-cell term, which dominates, enters the roofline figure)
     iter_bytes = 428.0 * N
-    out = {"metric": "train_iters_per_s", "value": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "rays_per_iter": batch * world, "n_gpus": world,
+    best = min(ms, ms_peer) if ms_peer else ms
+    out = {"metric": "train_iters_per_s", "value": iters / (best * 1e-3), "ms_per_iter": best / iters, "rays_per_iter": batch * world, "n_gpus": world,
+           "exchange": ("peer-memory fused (lrf_train_percell_peer_async)" if ms_peer and ms_peer <= ms else "NCCL all-reduce + replicated per-cell pass") if world > 1 else "none (1 GPU)",
+           "ms_per_iter_nccl_allreduce": ms / iters, "ms_per_iter_peer_fused": (ms_peer / iters) if ms_peer else None,
            "scaling": "weak (4096 rays per GPU per iteration)",
            "ms_backward_4096_rays": ms_bwd, "ms_percell_tv_adam_zero": ms_cell,
            "percell_algorithmic_bytes": 428.0 * N, "percell_frac_of_hbm_peak": (428.0 * N / (ms_cell * 1e-3) / 1e9) / peak,
            "iter_frac_of_hbm_peak_incl_allreduce": (iter_bytes / (ms / iters * 1e-3) / 1e9) / peak,
+           "iter_frac_of_hbm_peak_peer_fused": ((iter_bytes / (ms_peer / iters * 1e-3) / 1e9) / peak) if ms_peer else None,
            "ms_per_iter_without_allreduce": (ms_noex / iters) if ms_noex else ms / iters,
            "allreduce_ms_per_iter": ((ms - ms_noex) / iters) if ms_noex else 0.0,
            "allreduce": "NCCL all_reduce (sum) of the 13*N fp32 gradient planes (%d MB) per iteration, on the context stream" % (52 * N // 2 ** 20) if world > 1 else "none (1 GPU)"}

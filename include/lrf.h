@@ -126,6 +126,25 @@ int lrf_adam_step(lrf_ctx *h, int iter, int which);
 int lrf_train_percell_async(lrf_ctx *h, int iter);
 int lrf_set_adam_hparams(lrf_ctx *h, float lr, float beta1, float beta2, float eps);
 
+/* ---- multi-GPU exchange over NVLink peer memory (no reference counterpart: the reference is one process) ----
+ * One process per GPU, a grid replica each.  After the backward, rank r owns z-slab r of the planes: it adds the TV
+ * gradient of its slab, reads the gradient of EVERY rank for that slab (peer loads), applies Adam with its local moments
+ * and stores the new parameters into EVERY replica (peer stores) — reduce-scatter + TV + Adam + all-gather in one pass.
+ * The caller orders the GPUs: a barrier between the backward and lrf_train_percell_peer_async, another one after it, then
+ * lrf_zero_grad_async.  In this mode the Adam moments of rank r are current for slab r only.
+ * gridSize must be a multiple of 8 * world; world <= 8. */
+/* 64-byte CUDA IPC handle of the parameter (which = 0) or gradient (1) planes, to be sent to the other ranks */
+int lrf_ipc_export(lrf_ctx *h, int which, void *handle64);
+/* param_handles / grad_handles: world x 64 bytes, rank-ordered (the own rank's entry is ignored) */
+int lrf_peer_attach_ipc(lrf_ctx *h, int world, int rank, const void *param_handles, const void *grad_handles);
+/* the same for contexts living in THIS process (one per device, or several on one device in tests) */
+int lrf_peer_attach_local(lrf_ctx *h, int world, int rank, lrf_ctx *const *ctxs);
+int lrf_peer_detach(lrf_ctx *h);
+int lrf_tv_grad_slab_async(lrf_ctx *h);              /* kernel2D_TVGrad restricted to the own slab */
+int lrf_adam_peer_async(lrf_ctx *h, int iter);       /* optimizerStep(iter) on the own slab, gradient summed over the ranks */
+int lrf_train_percell_peer_async(lrf_ctx *h, int iter);   /* the two above */
+int lrf_zero_grad_async(lrf_ctx *h);                 /* zeroGrad without the stream sync */
+
 /* ---- level transition ------------------------------------------------------------------------ */
 /* ref: UpsampleGrid(), example_tracer.cpp:281-323 */
 int lrf_upsample_grid(lrf_ctx *h);

@@ -82,6 +82,14 @@ SIGNATURES = {
     "lrf_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lrf_count_touched_nodes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
     "lrf_fill_synthetic": (C.c_int, [_vp, C.c_float, C.c_int]),
+    "lrf_ipc_export": (C.c_int, [_vp, C.c_int, _vp]),
+    "lrf_peer_attach_ipc": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "lrf_peer_attach_local": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lrf_peer_detach": (C.c_int, [_vp]),
+    "lrf_tv_grad_slab_async": (C.c_int, [_vp]),
+    "lrf_adam_peer_async": (C.c_int, [_vp, C.c_int]),
+    "lrf_train_percell_peer_async": (C.c_int, [_vp, C.c_int]),
+    "lrf_zero_grad_async": (C.c_int, [_vp]),
     "lrf_model_save": (C.c_int, [_vp, C.c_char_p]),
     "lrf_model_load": (C.c_int, [_vp, C.c_char_p]),
     "lrf_targets_resize": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32]),
@@ -415,6 +423,37 @@ class RayMarcherExample:
 
     def launch_count(self):
         return self.lib.lrf_launch_count(self.h)
+
+    # ---- multi-GPU exchange over peer memory ----
+    def ipc_export(self, which):
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.lrf_ipc_export(self.h, which, buf))
+        return buf.raw
+
+    def peer_attach_ipc(self, world, rank, param_handles, grad_handles):
+        """handles: lists of `world` 64-byte strings in rank order"""
+        pb, gb = b"".join(param_handles), b"".join(grad_handles)
+        assert len(pb) == 64 * world and len(gb) == 64 * world
+        self._ck(self.lib.lrf_peer_attach_ipc(self.h, world, rank, pb, gb))
+
+    def peer_attach_local(self, rank, tracers):
+        arr = (_vp * len(tracers))(*[t.h for t in tracers])
+        self._ck(self.lib.lrf_peer_attach_local(self.h, len(tracers), rank, arr))
+
+    def peer_detach(self):
+        self._ck(self.lib.lrf_peer_detach(self.h))
+
+    def tv_grad_slab_async(self):
+        self._ck(self.lib.lrf_tv_grad_slab_async(self.h))
+
+    def adam_peer_async(self, it):
+        self._ck(self.lib.lrf_adam_peer_async(self.h, it))
+
+    def train_percell_peer_async(self, it):
+        self._ck(self.lib.lrf_train_percell_peer_async(self.h, it))
+
+    def zero_grad_async(self):
+        self._ck(self.lib.lrf_zero_grad_async(self.h))
 
     def fill_synthetic(self, density_scale=20.0, mode=0):
         """seeded synthetic grid of SURVEY 8(d) generated on the device (== tests/libs.py::lcg_grid bit for bit)"""

@@ -47,6 +47,10 @@ struct lrf_ctx
   float *targets = nullptr;
   float *gamma_lut = nullptr;         // device copy of the 256-entry ldr->hdr table
   uint32_t n_targets = 0, tw = 0, th = 0;
+  // multi-GPU exchange over peer memory: parameter / gradient planes of every rank (own rank: the local arrays)
+  int peer_world = 0, peer_rank = 0;
+  float *peer_param[8] = {nullptr}, *peer_grad[8] = {nullptr};
+  bool peer_ipc = false;              // pointers of the other ranks came from cudaIpcOpenMemHandle (must be closed)
 };
 
 static thread_local std::string g_err;
@@ -104,8 +108,18 @@ static SceneDev scene_of(const lrf_ctx *h)
   return S;
 }
 
+static void peer_detach(lrf_ctx *h)
+{
+  if (h->peer_ipc)
+    for (int r = 0; r < h->peer_world; r++)
+      if (r != h->peer_rank) { cudaIpcCloseMemHandle(h->peer_param[r]); cudaIpcCloseMemHandle(h->peer_grad[r]); }
+  h->peer_world = 0;
+  h->peer_ipc = false;
+}
+
 static void free_grid(lrf_ctx *h)
 {
+  peer_detach(h);   // the attached pointers describe replicas of the grid that is going away
   cudaFree(h->params); cudaFree(h->grad); cudaFree(h->V); cudaFree(h->S); cudaFree(h->tv_tmp);
   cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id);
   h->params = h->grad = h->V = h->S = h->tv_tmp = nullptr;
@@ -668,6 +682,99 @@ int lrf_train_percell_async(lrf_ctx *h, int iter)
   launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
   h->launches += (h->gs >= 8) ? 1 : 3;   // fused TV kernel (8^3 tiles), stage-by-stage below that
   adam_launch(h, iter, 0, 1);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- multi-GPU exchange over peer memory ----
+static int peer_check(lrf_ctx *h, int world, int rank)
+{
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail("peer group: world must be 1..8 and 0 <= rank < world");
+  if (h->gs % (8 * world)) return fail("peer group: gridSize must be a multiple of 8 * world (z-slabs of whole 8^3 TV tiles)");
+  return 0;
+}
+int lrf_ipc_export(lrf_ctx *h, int which, void *handle64)
+{
+  NEED_GRID(h);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, which ? (void *)h->grad : (void *)h->params));
+  std::memcpy(handle64, &hd, 64);
+  return 0;
+}
+int lrf_peer_attach_ipc(lrf_ctx *h, int world, int rank, const void *param_handles, const void *grad_handles)
+{
+  NEED_GRID(h);
+  if (peer_check(h, world, rank)) return 1;
+  peer_detach(h);
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { h->peer_param[r] = h->params; h->peer_grad[r] = h->grad; continue; }
+    cudaIpcMemHandle_t hp, hg;
+    std::memcpy(&hp, (const char *)param_handles + 64 * r, 64);
+    std::memcpy(&hg, (const char *)grad_handles + 64 * r, 64);
+    CK(cudaIpcOpenMemHandle((void **)&h->peer_param[r], hp, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle((void **)&h->peer_grad[r], hg, cudaIpcMemLazyEnablePeerAccess));
+  }
+  h->peer_world = world; h->peer_rank = rank; h->peer_ipc = true;
+  return 0;
+}
+int lrf_peer_attach_local(lrf_ctx *h, int world, int rank, lrf_ctx *const *ctxs)
+{
+  NEED_GRID(h);
+  if (peer_check(h, world, rank)) return 1;
+  peer_detach(h);
+  for (int r = 0; r < world; r++) {
+    lrf_ctx *o = ctxs[r];
+    if (!o || !o->params || o->gs != h->gs) return fail("peer group: every context needs a grid of the same size");
+    if (o->device != h->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, h->device, o->device));
+      if (!can) return fail("peer group: device cannot access its peer");
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    h->peer_param[r] = o->params; h->peer_grad[r] = o->grad;
+  }
+  if (ctxs[rank] != h) return fail("peer group: ctxs[rank] must be this context");
+  h->peer_world = world; h->peer_rank = rank; h->peer_ipc = false;
+  return 0;
+}
+int lrf_peer_detach(lrf_ctx *h) { NEED(h); peer_detach(h); return 0; }
+#define NEED_PEERS(h) do { NEED_GRID(h); if ((h)->peer_world < 1) return fail("no peer group attached (lrf_peer_attach_ipc / _local)"); } while (0)
+int lrf_tv_grad_slab_async(lrf_ctx *h)
+{
+  NEED_PEERS(h);
+  const int zs = h->gs / h->peer_world;
+  launch_tv_grad_slab(h->gs, h->params, h->grad, zs * h->peer_rank, zs * (h->peer_rank + 1), h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int lrf_adam_peer_async(lrf_ctx *h, int iter)
+{
+  NEED_PEERS(h);
+  const double b1 = std::pow(h->beta1, iter + 1), b2 = std::pow(h->beta2, iter + 1);   // example_tracer.h:152-153 (double)
+  const size_t n = (size_t)h->peer_world, r = (size_t)h->peer_rank;
+  // own slab of the density plane and of the colour plane (contiguous z-slabs of both)
+  launch_adam_peer(h->peer_world, h->peer_rank, h->peer_grad, h->peer_param, h->V, h->S, h->N / n * r, h->N / n, h->lr, h->beta1, h->beta2, h->eps,
+                   1 - b1, 1 - b2, h->stream);
+  launch_adam_peer(h->peer_world, h->peer_rank, h->peer_grad, h->peer_param, h->V, h->S, h->N + h->N * 12 / n * r, h->N * 12 / n, h->lr, h->beta1,
+                   h->beta2, h->eps, 1 - b1, 1 - b2, h->stream);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+int lrf_train_percell_peer_async(lrf_ctx *h, int iter)
+{
+  if (lrf_tv_grad_slab_async(h)) return 1;
+  return lrf_adam_peer_async(h, iter);
+}
+int lrf_zero_grad_async(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  launch_fill(h->grad, h->N * kCell, 0.0f, h->stream);
+  h->launches++;
   CK(cudaGetLastError());
   return 0;
 }

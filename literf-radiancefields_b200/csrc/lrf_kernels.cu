@@ -855,12 +855,12 @@ __global__ void tv_scatter_kernel(int gs, const float *__restrict__ gv, float *_
 // per tile.  Values agree with the staged kernels to rounding (lam * d / r is formed as d * (lam * rsqrt)); the TV
 // gradient is compared with the oracle to 1e-5 relative, not bit-for-bit (the reference's own sum order is a race).
 constexpr int kTvT = 8;
-__global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens)
+__global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens, int bz0)
 {
   __shared__ float sD[12 * 12 * 12], sV[11 * 11 * 11], sG[9 * 9 * 9];
   __shared__ float sEx[10 * 10 * 10], sEy[10 * 10 * 10], sEz[10 * 10 * 10];
   const int tiles = gs / kTvT;
-  const int bx = blockIdx.x % tiles, by = (blockIdx.x / tiles) % tiles, bz = blockIdx.x / (tiles * tiles);
+  const int bx = blockIdx.x % tiles, by = (blockIdx.x / tiles) % tiles, bz = bz0 + blockIdx.x / (tiles * tiles);   // bz0: first tile layer of a z-slab
   const int q0x = bx * kTvT, q0y = by * kTvT, q0z = bz * kTvT;
   const int m = gs - 1;
   for (int i = threadIdx.x; i < 12 * 12 * 12; i += 256) {
@@ -988,6 +988,56 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, float 
       adam_update(pp, g[i], vv, ss, C);
       p[i] = pp; V[i] = vv; Sq[i] = ss;
       if (zero_grad) g[i] = 0.0f;
+    }
+  }
+}
+
+// Multi-GPU exchange step fused with the per-cell pass, over NVLink peer memory: every rank owns a slab of
+// the element range.  For its slab it reads the gradient of ALL ranks (its own from HBM, the others' through peer
+// loads), sums them in rank order — the full-batch gradient, exactly what a sum all-reduce would leave there —, applies
+// Adam with its local moments, and stores the new parameters into EVERY replica (peer stores).  One pass replaces
+// reduce-scatter + Adam + all-gather: per rank (n-1)/n of the gradient comes in and (n-1)/n of the parameters go out over
+// NVLink, the same volume as the collectives, but nothing is staged and the Adam arithmetic is divided by n.
+// Ordering across GPUs is the caller's: a barrier before (all gradients complete) and after (all replicas written).
+struct PeerSet
+{
+  int world, rank;
+  float *grad[8];
+  float *param[8];
+};
+__device__ __forceinline__ float4 ld_peer(const float *p)
+{
+  float4 v;   // peer memory is another GPU's HBM: bypass L1, never reuse a line from the previous iteration
+  asm volatile("ld.global.cv.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__global__ void __launch_bounds__(256) adam_peer_kernel(const PeerSet P, float *__restrict__ V, float *__restrict__ Sq, size_t off, size_t count,
+                                                        const AdamConst C)
+{
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= count) return;
+  const size_t at = off + i4;
+  if (i4 + 4 <= count) {
+    float4 gv = ld_peer(P.grad[0] + at);
+    for (int r = 1; r < P.world; r++) {
+      const float4 o = ld_peer(P.grad[r] + at);
+      gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+    }
+    float4 pv = *reinterpret_cast<const float4 *>(P.param[P.rank] + at);
+    float4 vv = *reinterpret_cast<float4 *>(V + at), sv = *reinterpret_cast<float4 *>(Sq + at);
+    adam_update(pv.x, gv.x, vv.x, sv.x, C); adam_update(pv.y, gv.y, vv.y, sv.y, C);
+    adam_update(pv.z, gv.z, vv.z, sv.z, C); adam_update(pv.w, gv.w, vv.w, sv.w, C);
+    *reinterpret_cast<float4 *>(V + at) = vv;
+    *reinterpret_cast<float4 *>(Sq + at) = sv;
+    for (int r = 0; r < P.world; r++) *reinterpret_cast<float4 *>(P.param[r] + at) = pv;
+  } else {
+    for (size_t i = at; i < off + count; i++) {
+      float g = P.grad[0][i];
+      for (int r = 1; r < P.world; r++) g += P.grad[r][i];
+      float pp = P.param[P.rank][i], vv = V[i], ss = Sq[i];
+      adam_update(pp, g, vv, ss, C);
+      V[i] = vv; Sq[i] = ss;
+      for (int r = 0; r < P.world; r++) P.param[r][i] = pp;
     }
   }
 }
@@ -1253,7 +1303,7 @@ void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float
   const size_t N = (size_t)gs * gs * gs;
   if (gs >= kTvT) {
     const int tiles = gs / kTvT;
-    tv_fused_kernel<<<tiles * tiles * tiles, 256, 0, st>>>(gs, dens, gdens);
+    tv_fused_kernel<<<tiles * tiles * tiles, 256, 0, st>>>(gs, dens, gdens, 0);
     return;
   }
   tv_voxel_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, dens, tmp_v);
@@ -1269,6 +1319,24 @@ void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t coun
   C.omb1f = 1 - beta1; C.omb2f = 1 - beta2;   // (1 - beta) evaluated in float, as the reference's int - float
   C.om_b1 = om_b1; C.om_b2 = om_b2; C.inv_om_b1 = 1.0 / om_b1; C.inv_om_b2 = 1.0 / om_b2;
   adam_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(p + off, g + off, V + off, S + off, count, C, zero_grad);
+}
+void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, cudaStream_t st)
+{
+  const int tiles = gs / kTvT, l0 = z_begin / kTvT, l1 = z_end / kTvT;
+  if (l1 > l0) tv_fused_kernel<<<tiles * tiles * (l1 - l0), 256, 0, st>>>(gs, dens, gdens, l0);
+}
+void launch_adam_peer(int world, int rank, float *const *grads, float *const *params, float *V, float *S, size_t off, size_t count, float lr,
+                      float beta1, float beta2, float eps, double om_b1, double om_b2, cudaStream_t st)
+{
+  if (count == 0) return;
+  AdamConst C;
+  C.lr = lr; C.beta1 = beta1; C.beta2 = beta2; C.eps = eps;
+  C.omb1f = 1 - beta1; C.omb2f = 1 - beta2;
+  C.om_b1 = om_b1; C.om_b2 = om_b2; C.inv_om_b1 = 1.0 / om_b1; C.inv_om_b2 = 1.0 / om_b2;
+  PeerSet P{};
+  P.world = world; P.rank = rank;
+  for (int r = 0; r < world; r++) { P.grad[r] = grads[r]; P.param[r] = params[r]; }
+  adam_peer_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(P, V, S, off, count, C);
 }
 void launch_fill(float *p, size_t count, float v, cudaStream_t st)
 {

@@ -36,6 +36,11 @@ void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float
 void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t count, float lr, float beta1, float beta2, float eps,
                  double om_b1, double om_b2, int zero_grad, cudaStream_t st);
 void launch_fill(float *p, size_t count, float v, cudaStream_t st);
+// multi-GPU: TV gradient of the nodes in z-planes [z_begin, z_end) (multiples of 8), and the Adam pass over the element range
+// [off, off+count) that sums the gradient of all ranks through peer memory and writes the parameters to every replica
+void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, cudaStream_t st);
+void launch_adam_peer(int world, int rank, float *const *grads, float *const *params, float *V, float *S, size_t off, size_t count, float lr,
+                      float beta1, float beta2, float eps, double om_b1, double om_b2, cudaStream_t st);
 // layout conversion: host AoS [N][13]  <->  device planes dens[N] + col[N][12]
 void launch_aos_to_planes(const float *aos, float *planes, size_t N, cudaStream_t st);
 void launch_planes_to_aos(const float *planes, float *aos, size_t N, cudaStream_t st);

@@ -7,6 +7,12 @@ gradient planes and ONE exchange step — a sum all-reduce (NCCL over NVLink on 
 makes every replica's gradient the full-batch gradient.  The reference's loss is an un-normalised sum over rays
 (example_tracer.cpp:258-268), so data parallelism is mathematically a larger single-GPU batch; TV + Adam then run
 replicated and keep the replicas bit-identical.
+
+PeerExchange is the faster exchange on an NVLink box: the planes of every rank are mapped into every process (CUDA IPC),
+and rank r does TV + gradient sum + Adam for z-slab r in one kernel that reads the other ranks' gradients and writes
+every replica's parameters through peer memory (lrf_train_percell_peer_async): reduce-scatter + Adam + all-gather fused,
+with the Adam work divided by the number of GPUs.  The replicas stay bit-identical because each parameter is computed
+once, by its slab's owner.
 """
 
 
@@ -27,3 +33,33 @@ def allreduce_gradient(grad, dist):
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(grad, op=dist.ReduceOp.SUM)
     return grad
+
+
+class PeerExchange:
+    """per-iteration exchange over NVLink peer memory.  `tracer` = this rank's RayMarcherExample, `dist` = an initialised
+    torch.distributed (NCCL) group used for the handle exchange and as the inter-GPU barrier on the tracer's stream."""
+
+    def __init__(self, tracer, dist, torch):
+        self.t, self.dist, self.torch = tracer, dist, torch
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        mine = (tracer.ipc_export(0), tracer.ipc_export(1))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        tracer.peer_attach_ipc(self.world, self.rank, [e[0] for e in everyone], [e[1] for e in everyone])
+        self.stream = torch.cuda.ExternalStream(tracer.lib.lrf_stream(tracer.h))
+        self.flag = torch.zeros(1, device="cuda")
+
+    def barrier(self):
+        """all ranks' work queued so far on their tracer streams is complete before anything queued after it starts"""
+        with self.torch.cuda.stream(self.stream):
+            self.dist.all_reduce(self.flag)
+
+    def percell(self, it):
+        """between the backward of iteration `it` and the next one"""
+        self.barrier()                       # every rank's gradient is complete
+        self.t.train_percell_peer_async(it)  # own slab: TV + sum over ranks + Adam, parameters written to every replica
+        self.barrier()                       # every replica is fully written, every gradient fully read
+        self.t.zero_grad_async()
+
+    def close(self):
+        self.t.peer_detach()

@@ -1,0 +1,85 @@
+"""Multi-GPU exchange over peer memory (lrf_train_percell_peer_async), exercised on ONE device with two contexts standing
+in for two ranks (lrf_peer_attach_local; the IPC variant of the same kernel runs under torchrun, tools/peer_check.py).
+Each "rank" back-propagates its shard of a ray batch; the slab owner sums the two gradients through the peer pointers,
+applies TV + Adam and writes both replicas.  Expected values come from the oracle's Adam fed with the rank-ordered fp32
+sum of the two gradients — bit-exact — and from a single-context full-batch run (same sum in another association)."""
+import numpy as np
+import pytest
+
+import libs
+from scenes import OracleScene, cameras
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(pkg, gs, grid):
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.set_grid(grid)
+    t.optimizerInit()
+    t.zeroGrad()
+    return t
+
+
+@pytest.mark.parametrize("gs", [16, 32])
+def test_peer_fused_percell_two_ranks(pkg, gs):
+    grid = libs.lcg_grid(gs, 20.0)
+    S = OracleScene(gs, grid)
+    vi, pi = cameras(None, 2, 7)
+    S.set_cam(vi, pi)
+    o, d = S.gen_rays(24, 24)
+    n = o.shape[0]
+    ta, tb, full = _mk(pkg, gs, grid), _mk(pkg, gs, grid), _mk(pkg, gs, grid)
+    ta.peer_attach_local(0, [ta, tb])
+    tb.peer_attach_local(1, [ta, tb])
+    S.O.orc_adam_init(S.h)
+    for it in range(3):
+        ref = np.random.default_rng(50 + it).random((n, 4)).astype(np.float32)
+        half = n // 2
+        ta.rays_grad(o[:half], d[:half], ref[:half])
+        tb.rays_grad(o[half:], d[half:], ref[half:])
+        ta.tv_grad_slab_async(); tb.tv_grad_slab_async()
+        ta.sync(); tb.sync()
+        ga, gb = ta.get_grad(), tb.get_grad()
+        # TV went to the slab owner only: rank 0 owns z < gs/2 of the density plane
+        zs = gs ** 3 // 2
+        # full-batch reference run on one context: same rays, replicated TV
+        full.rays_grad(o, d, ref)
+        full.kernel2D_TVGrad()
+        gf = full.get_grad().astype(np.float64)
+        gsum = ga + gb                                            # fp32, rank order: what the kernel forms
+        assert np.linalg.norm(gsum - gf) <= 1e-5 * np.linalg.norm(gf)
+        # the exchange + Adam
+        ta.adam_peer_async(it); tb.adam_peer_async(it)
+        ta.sync(); tb.sync()
+        pa, pb = ta.get_grid(), tb.get_grid()
+        assert np.array_equal(pa.view(np.uint32), pb.view(np.uint32)), "replicas diverged"
+        S.grad[:] = gsum
+        S.O.orc_adam_step(S.h, it, 0)
+        assert np.array_equal(pa.view(np.uint32), S.grid.view(np.uint32)), "peer Adam differs from the oracle's Adam on the summed gradient"
+        # moments: rank r holds slab r
+        Va, Sa = ta.get_adam_state()
+        Vb, Sb = tb.get_adam_state()
+        assert np.array_equal(Va[:zs], S.adam_v[:zs]) and np.array_equal(Vb[zs:], S.adam_v[zs:])
+        assert np.array_equal(Sa[:zs], S.adam_s[:zs]) and np.array_equal(Sb[zs:], S.adam_s[zs:])
+        full.optimizerStep(it)
+        full.zeroGrad()
+        assert np.allclose(full.get_grid(), pa, rtol=0, atol=0.31)   # Adam's first steps are ~ +-lr: same sign pattern up to cancellation noise
+        ta.zero_grad_async(); tb.zero_grad_async()
+        ta.sync(); tb.sync()
+    for t in (ta, tb, full):
+        t.close()
+    S.close()
+
+
+def test_peer_group_argument_checks(pkg):
+    t = pkg.RayMarcherExample()
+    t.InitGrid(16)
+    with pytest.raises(pkg.LrfError):
+        t.train_percell_peer_async(0)                # nothing attached
+    with pytest.raises(pkg.LrfError):
+        t.peer_attach_local(0, [t, t, t])            # 16 is not a multiple of 8 * 3
+    t.peer_attach_local(0, [t])                      # world 1 degenerates to the local pass
+    t.train_percell_peer_async(0)
+    t.sync()
+    t.close()
