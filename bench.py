@@ -380,7 +380,9 @@ def main():
 
 def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier, iters=20, batch=4096):
     """BASELINE.json configs[2]: grid optimisation on the 256^3 grid, 4096-ray batches per GPU against synthetic targets:
-    one iteration = ray generation + backward(4096 rays) [+ NCCL all-reduce of the 13*N-float gradient] + TV + Adam + zero."""
+    one iteration = ray generation + {backward(4096 rays) || TV gradient} + Adam + zero on one GPU; on N GPUs either
+    backward + NCCL all-reduce of the 13*N-float gradient + replicated TV + Adam + zero, or backward || slab TV + the
+    peer-memory fused exchange (barrier, slab {sum over ranks + Adam -> every replica}, barrier, zero)."""
     import ctypes as C
     n_views = len(views)
     rng = np.random.default_rng(1234 + rank)
@@ -410,6 +412,10 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     def one(it, exchange=True):
         off = it * batch
         t._ck(t.lib.lrf_gen_rays_dev_async(t.h, batch, vi_dev.ptr, picks_dev.ptr + off * 8, W, H, o_dev.ptr, d_dev.ptr))
+        if grad_tensor is None:     # one GPU: TV beside the backward (second stream), then Adam + zero
+            t._ck(t.lib.lrf_rays_grad_tv_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
+            t._ck(t.lib.lrf_adam_zero_async(t.h, it))
+            return
         t._ck(t.lib.lrf_rays_grad_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
         if grad_tensor is not None and exchange:
             import torch
@@ -426,7 +432,7 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     ms = max_over_ranks(t.timer_stop_ms())
     barrier()
     ms_noex = None
-    ms_peer = None
+    ms_peer = ms_peer_exchange = ms_barrier = None
     if grad_tensor is not None:   # same iterations without the exchange step: the all-reduce share of an iteration
         t.timer_start()
         for it in range(3, 3 + iters):
@@ -443,8 +449,8 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
         def one_peer(it):
             off = it * batch
             t._ck(t.lib.lrf_gen_rays_dev_async(t.h, batch, vi_dev.ptr, picks_dev.ptr + off * 8, W, H, o_dev.ptr, d_dev.ptr))
-            t._ck(t.lib.lrf_rays_grad_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
-            ex.percell(it)
+            t._ck(t.lib.lrf_rays_grad_tv_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))   # backward || TV of the own slab
+            ex.percell(it, tv_done=True)
 
         for it in range(3):
             one_peer(it)
@@ -453,6 +459,16 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
         for it in range(3, 3 + iters):
             one_peer(it)
         ms_peer = max_over_ranks(t.timer_stop_ms())
+        barrier()
+        # the exchange alone (no backward): barrier + fused pass + barrier + zero
+        t.timer_start()
+        for it in range(5):
+            ex.percell(200 + it, tv_done=True)
+        ms_peer_exchange = max_over_ranks(t.timer_stop_ms()) / 5
+        t.timer_start()
+        for it in range(5):
+            ex.barrier()
+        ms_barrier = max_over_ranks(t.timer_stop_ms()) / 5
         barrier()
         ex.close()
     # break-down: backward alone / per-cell alone
@@ -474,6 +490,7 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     out = {"metric": "train_iters_per_s", "value": iters / (best * 1e-3), "ms_per_iter": best / iters, "rays_per_iter": batch * world, "n_gpus": world,
            "exchange": ("peer-memory fused (lrf_train_percell_peer_async)" if ms_peer and ms_peer <= ms else "NCCL all-reduce + replicated per-cell pass") if world > 1 else "none (1 GPU)",
            "ms_per_iter_nccl_allreduce": ms / iters, "ms_per_iter_peer_fused": (ms_peer / iters) if ms_peer else None,
+           "ms_peer_exchange_alone": ms_peer_exchange, "ms_stream_barrier": ms_barrier,
            "scaling": "weak (4096 rays per GPU per iteration)",
            "ms_backward_4096_rays": ms_bwd, "ms_percell_tv_adam_zero": ms_cell,
            "percell_algorithmic_bytes": 428.0 * N, "percell_frac_of_hbm_peak": (428.0 * N / (ms_cell * 1e-3) / 1e9) / peak,

@@ -125,6 +125,11 @@ int lrf_adam_step(lrf_ctx *h, int iter, int which);
  * next iteration in one call (same results as lrf_tv_grad; lrf_adam_step(iter,0); lrf_zero_grad).  Asynchronous. */
 int lrf_train_percell_async(lrf_ctx *h, int iter);
 int lrf_set_adam_hparams(lrf_ctx *h, float lr, float beta1, float beta2, float eps);
+/* the same iteration with the TV gradient running BESIDE the ray backward (second stream; TV reads parameters only and both
+ * scatter with red.add): lrf_rays_grad_tv_dev_async = lrf_rays_grad_dev_async || kernel2D_TVGrad (own z-slab only when a peer
+ * group is attached), joined on the context stream; lrf_adam_zero_async = optimizerStep(iter) + zeroGrad.  Asynchronous. */
+int lrf_rays_grad_tv_dev_async(lrf_ctx *h, size_t n, const float *o_dev, const float *d_dev, const float *ref_rgba_dev, int greyscale);
+int lrf_adam_zero_async(lrf_ctx *h, int iter);
 
 /* ---- multi-GPU exchange over NVLink peer memory (no reference counterpart: the reference is one process) ----
  * One process per GPU, a grid replica each.  After the backward, rank r owns z-slab r of the planes: it adds the TV

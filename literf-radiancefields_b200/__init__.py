@@ -82,6 +82,8 @@ SIGNATURES = {
     "lrf_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lrf_count_touched_nodes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
     "lrf_fill_synthetic": (C.c_int, [_vp, C.c_float, C.c_int]),
+    "lrf_rays_grad_tv_dev_async": (C.c_int, [_vp, C.c_size_t, _vp, _vp, _vp, C.c_int]),
+    "lrf_adam_zero_async": (C.c_int, [_vp, C.c_int]),
     "lrf_ipc_export": (C.c_int, [_vp, C.c_int, _vp]),
     "lrf_peer_attach_ipc": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "lrf_peer_attach_local": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -454,6 +456,12 @@ class RayMarcherExample:
 
     def zero_grad_async(self):
         self._ck(self.lib.lrf_zero_grad_async(self.h))
+
+    def rays_grad_tv_dev_async(self, n, o_dev, d_dev, ref_dev, greyscale=False):
+        self._ck(self.lib.lrf_rays_grad_tv_dev_async(self.h, n, o_dev, d_dev, ref_dev, int(greyscale)))
+
+    def adam_zero_async(self, it):
+        self._ck(self.lib.lrf_adam_zero_async(self.h, it))
 
     def fill_synthetic(self, density_scale=20.0, mode=0):
         """seeded synthetic grid of SURVEY 8(d) generated on the device (== tests/libs.py::lcg_grid bit for bit)"""

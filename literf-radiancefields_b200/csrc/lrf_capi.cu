@@ -33,6 +33,8 @@ struct lrf_ctx
   float lr = 0.15f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8;   // example_tracer.h:120-123
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t side = nullptr;        // second stream: the TV gradient beside the ray backward
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
   float t_march = 0, t_grad = 0, t_tv = 0, t_adam = 0;
   uint64_t launches = 0;
@@ -42,6 +44,8 @@ struct lrf_ctx
   // fallback queue of the forward render (rays that need the generic march): [0] = count, [1..] = pixel indices
   uint32_t *fb = nullptr;
   size_t fb_cap = 0;
+  void *hit_scratch = nullptr;        // per-ray hit lists of the packed-batch backward
+  size_t hit_bytes = 0;
   int force_generic = 0;   // parity taps: 1 = generic march for every ray (tests compare both paths)
   // resident target images: n_targets x tw x th float4, stbi_loadf layout
   float *targets = nullptr;
@@ -163,6 +167,9 @@ int lrf_create(int device, lrf_ctx **out)
   lrf_ctx *h = new lrf_ctx();
   h->device = device;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   CK(cudaEventCreate(&h->tm0));
@@ -181,9 +188,12 @@ int lrf_destroy(lrf_ctx *h)
   free_grid(h);
   cudaFree(h->stage);
   cudaFree(h->fb);
+  cudaFree(h->hit_scratch);
   cudaFree(h->targets);
   cudaFree(h->gamma_lut);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
+  cudaStreamDestroy(h->side);
+  cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -441,7 +451,19 @@ int lrf_rays_grad_dev_async(lrf_ctx *h, size_t n, const float *o, const float *d
   NEED_GRID(h);
   if (n == 0) return 0;
   if (ensure_fb(h, n)) return 1;
-  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->fb, h->fb + 4, h->stream);
+  // scratch for the per-ray hit lists (pass A -> pass B of the warp kernel); past 512 MB the kernel walks twice instead
+  const size_t hb = grad_rays_hit_bytes(n, h->gs, nullptr);
+  void *hits = nullptr;
+  if (hb <= ((size_t)512 << 20)) {
+    if (h->hit_bytes < hb) {
+      cudaFree(h->hit_scratch);
+      h->hit_scratch = nullptr; h->hit_bytes = 0;
+      CK(cudaMalloc(&h->hit_scratch, hb));
+      h->hit_bytes = hb;
+    }
+    hits = h->hit_scratch;
+  }
+  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->fb, h->fb + 4, hits, h->stream);
   h->launches += 2;   // grad_rays_warp_kernel + the generic fallback over its queue
   CK(cudaGetLastError());
   return 0;
@@ -686,6 +708,40 @@ int lrf_train_percell_async(lrf_ctx *h, int iter)
   return 0;
 }
 
+// training iteration, first half: the ray backward of a packed batch and — concurrently, on a second stream — the TV gradient
+// (it depends on the parameters only; both scatter into the gradient planes with red.add).  With a peer group attached the TV
+// covers the own z-slab only.  Joined on the context stream before returning control to it.
+int lrf_rays_grad_tv_dev_async(lrf_ctx *h, size_t n, const float *o, const float *d, const float *ref, int grey)
+{
+  NEED_GRID(h);
+  if (h->gs < 8) {   // tiny grids use the staged TV kernels (not atomic): run one after the other
+    if (lrf_rays_grad_dev_async(h, n, o, d, ref, grey)) return 1;
+    if (ensure_tv_tmp(h)) return 1;
+    launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
+    h->launches += 3;
+    return 0;
+  }
+  CK(cudaEventRecord(h->ev_fork, h->stream));
+  CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  int z0 = 0, z1 = h->gs;
+  if (h->peer_world > 1) { const int zs = h->gs / h->peer_world; z0 = zs * h->peer_rank; z1 = z0 + zs; }
+  launch_tv_grad_slab(h->gs, h->params, h->grad, z0, z1, 1, h->side);
+  h->launches++;
+  CK(cudaEventRecord(h->ev_join, h->side));
+  if (lrf_rays_grad_dev_async(h, n, o, d, ref, grey)) return 1;
+  CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  CK(cudaGetLastError());
+  return 0;
+}
+// second half on one GPU: optimizerStep(iter) + gradient zeroing for the next iteration
+int lrf_adam_zero_async(lrf_ctx *h, int iter)
+{
+  NEED_GRID(h);
+  adam_launch(h, iter, 0, 1);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ---- multi-GPU exchange over peer memory ----
 static int peer_check(lrf_ctx *h, int world, int rank)
 {
@@ -746,7 +802,7 @@ int lrf_tv_grad_slab_async(lrf_ctx *h)
 {
   NEED_PEERS(h);
   const int zs = h->gs / h->peer_world;
-  launch_tv_grad_slab(h->gs, h->params, h->grad, zs * h->peer_rank, zs * (h->peer_rank + 1), h->stream);
+  launch_tv_grad_slab(h->gs, h->params, h->grad, zs * h->peer_rank, zs * (h->peer_rank + 1), 0, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   return 0;

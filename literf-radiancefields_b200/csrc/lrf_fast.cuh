@@ -69,6 +69,15 @@ constexpr int kFastBlock = 128;   // threads per block of the kernels that use F
 #ifndef LRF_TWO_PHASE
 #define LRF_TWO_PHASE 1
 #endif
+//   LRF_DENSE_FAST     1: dense render (MODE 0, no occupancy test): the common iteration — no tie, no pending queue, the
+//                         step rule of :145 not triggered — runs as ONE basic block (masked traversal step, branch-free
+//                         expf, unconditional colour); every rare event falls through to the general body
+//                         MEASURED SLOWER (2.68 vs 2.26 ms per view, profiles/r1f_variants.txt box 5): in one block ptxas
+//                         moves the gather consumers ahead of the traversal step and the latency cover that the
+//                         branch boundaries enforce is lost (and spills go 16 -> 96 bytes).  Kept as a knob, off.
+#ifndef LRF_DENSE_FAST
+#define LRF_DENSE_FAST 0
+#endif
 #ifndef LRF_BASIS_IN_REGS
 #define LRF_BASIS_IN_REGS 0
 #endif
@@ -172,7 +181,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       pa[a] = mm[a] ? pan : pa[a];
       cell[a] = mm[a] ? cell[a] + sgn[a] : cell[a];
     }
-    odd ^= 1u << ax;
+    odd ^= (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);   // ax < 0 (masked call): nothing moves
     const int csel = m0 ? cell[0] : (m1 ? cell[1] : cell[2]);
     const int ssel = m0 ? sgn[0] : (m1 ? sgn[1] : sgn[2]);
     // the node that enters lies on the new exit plane (coordinate csel + [ssel > 0]); it takes the slot of its parity
@@ -183,7 +192,8 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     ny[0] += (m1 && !p1) ? delta : 0u; ny[1] += (m1 && p1) ? delta : 0u;
     nz[0] += (m2 && !p1) ? delta : 0u; nz[1] += (m2 && p1) ? delta : 0u;
     const uint32_t f0 = m0 ? 0x55u : (m1 ? 0x33u : 0x0fu);
-    dirty |= p1 ? (f0 ^ 0xffu) : f0;
+    const uint32_t fm = p1 ? (f0 ^ 0xffu) : f0;
+    dirty |= (m0 || m1 || m2) ? fm : 0u;
     return csel;
   }
 
@@ -289,6 +299,29 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     float delta, lf[3];
     uint32_t odd;   // parity bits of the cell coordinates
   };
+  // the same without the step rule of :145-146; returns true when the rule applies (the caller then runs apply_step_rule)
+  __device__ __forceinline__ bool geometry_norule(Geom &g)
+  {
+    const float tmin = fmaxf(fmaxf(tn[0], tn[1]), tn[2]);
+    const float tmax = fminf(fminf(tf[0], tf[1]), tf[2]);
+    tPrev = (tPrev < 0.0f) ? tmin : tPrev;                     // :139
+    const float t = (tmin + tmax) * 0.5f;                      // :142
+    g.delta = t - tPrev;                                       // :144
+    tPrev = t;                                                 // :190
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float bmin = sgn[a] > 0 ? pa[a] - S.inv_gs_f : pa[a];
+      const float p = o(a) + t * d(a);                         // :148
+      g.lf[a] = (p - bmin) * S.gs_f;                           // :150
+    }
+    g.odd = odd;
+    return g.delta > S.step_gate_f;
+  }
+  __device__ __forceinline__ void apply_step_rule(Geom &g) const
+  {
+    if (g.delta > S.step_gate_f)                               // :145-146
+      g.delta = (float)((double)g.delta - (double)((int)((double)g.delta / S.step) - 1) * S.step);
+  }
   __device__ __forceinline__ void geometry(Geom &g)
   {
     const float tmin = fmaxf(fmaxf(tn[0], tn[1]), tn[2]);      // all finite: == the std::max / std::min chains of :18-43
@@ -317,7 +350,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     float tr, wgt;
   };
   // density part of a sample (decision path, bit-exact): transmittance of the step and the compositing weight
-  __device__ __forceinline__ Sig shade_sigma(const Geom &g)
+  template <bool NOBRANCH = false> __device__ __forceinline__ Sig shade_sigma(const Geom &g)
   {
     const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
     const float *lf = g.lf;
@@ -337,7 +370,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
     if (MODE == 1) cauchy += logf(1.0f + 2.0f * sigma * sigma);  // :173
     Sig r;
-    r.tr = expf_libm(-sigma * g.delta, etab);                  // :175
+    r.tr = NOBRANCH ? expf_libm_nobranch(-sigma * g.delta, etab) : expf_libm(-sigma * g.delta, etab);   // :175
     r.wgt = thr * (1.0f - r.tr);                               // :187
     return r;
   }
@@ -346,12 +379,12 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     return shade_colour(g, shade_sigma(g), fresh, fresh_low);
   }
   // colour part (1e-4-tolerance path) + the throughput update; false = the reference's throughput break fired
-  __device__ __forceinline__ bool shade_colour(const Geom &g, const Sig sg, const float4 *fresh, uint32_t fresh_low)
+  template <bool ALWAYS = false> __device__ __forceinline__ bool shade_colour(const Geom &g, const Sig sg, const float4 *fresh, uint32_t fresh_low)
   {
     const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
     const float *lf = g.lf;
     const float tr = sg.tr, wgt = sg.wgt;
-    if (wgt != 0.0f) {
+    if (ALWAYS || wgt != 0.0f) {   // ALWAYS: the reference's own unconditional `col += thr * (1 - tr) * c` (:187)
       if (GREY) { col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt; }
       else {
         // ---- colour: 1e-4-tolerance path, packed-pair FMAs ----
@@ -588,7 +621,32 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       L2.td = __ldg(S.dens + node2); L3.td = __ldg(S.dens + node3);
       dirty = 0;
       Geom g;
+#if LRF_DENSE_FAST
+      if (MODE == 0 && !SPARSE) {
+        const bool rule = geometry_norule(g);
+        if (!(rule || nq > 0 || resync)) {
+          // ---- the common iteration: one basic block ----
+          const int ax = decide_fast();                          // < 0: planes too close for fp32 -> exact step after shading
+          const int moved = advance(ax);                         // masked: a no-op for ax < 0
+          Basis Y;
+          if (!GREY) load_basis(Y);
+          float4 fresh[4];
+          commit_pair<0>(stale, hi, L0, Y, fresh[0]); commit_pair<1>(stale, hi, L1, Y, fresh[1]);
+          commit_density<2>(stale, hi, L2.td); commit_density<3>(stale, hi, L3.td);
+          issue_colour(node2, L2); issue_colour(node3, L3);
+          const Sig sg = shade_sigma<true>(g);
+          commit_colour<2>(stale, L2, Y, fresh[2]); commit_colour<3>(stale, L3, Y, fresh[3]);
+          if (!shade_colour<true>(g, sg, fresh, stale & 0x0fu)) return;
+          if (ax < 0) {
+            if (!next_cell()) return;
+          } else if ((unsigned)moved >= (unsigned)n) return;     // left the lattice
+          continue;
+        }
+        apply_step_rule(g);
+      } else geometry(g);
+#else
       geometry(g);
+#endif
       const bool more = next_cell();
       Basis Y;
       if (!GREY) load_basis(Y);

@@ -657,7 +657,8 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
 template <bool SPARSE, bool GREY>
 __global__ void __launch_bounds__(kBlock, 3) grad_rays_warp_kernel(const __grid_constant__ SceneDev S, size_t n_rays, const float *__restrict__ ro,
                                                                 const float *__restrict__ rd, const float *__restrict__ ref_rgba,
-                                                                uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list)
+                                                                uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list,
+                                                                HitRec *__restrict__ hitbuf, uint32_t hitcap)
 {
   __shared__ uint64_t etab[32];
   load_exp_table(etab);
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(kBlock, 3) grad_rays_warp_kernel(const __grid_
     const float gsc = 0.11f * rp.z + 0.59f * rp.y + 0.3f * rp.x;
     ref[0] = ref[1] = ref[2] = gsc;
   }
-  warp_ray_backward<SPARSE, GREY>(S, etab, o, d, ref);
+  warp_ray_backward<SPARSE, GREY>(S, etab, o, d, ref, hitbuf ? hitbuf + ray * hitcap : nullptr, hitcap);
 }
 
 // device-side ray generation for (view, pixel) picks — ref :635-639
@@ -855,7 +856,7 @@ __global__ void tv_scatter_kernel(int gs, const float *__restrict__ gv, float *_
 // per tile.  Values agree with the staged kernels to rounding (lam * d / r is formed as d * (lam * rsqrt)); the TV
 // gradient is compared with the oracle to 1e-5 relative, not bit-for-bit (the reference's own sum order is a race).
 constexpr int kTvT = 8;
-__global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens, int bz0)
+__global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens, int bz0, int atomic)
 {
   __shared__ float sD[12 * 12 * 12], sV[11 * 11 * 11], sG[9 * 9 * 9];
   __shared__ float sEx[10 * 10 * 10], sEy[10 * 10 * 10], sEz[10 * 10 * 10];
@@ -920,7 +921,9 @@ __global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__re
     float acc = 0.0f;
     acc += wz1 * (wy1 * (wx1 * p[-81 - 9 - 1] + wx0 * p[-81 - 9]) + wy0 * (wx1 * p[-81 - 1] + wx0 * p[-81]));
     acc += wz0 * (wy1 * (wx1 * p[-9 - 1] + wx0 * p[-9]) + wy0 * (wx1 * p[-1] + wx0 * p[0]));
-    gdens[(size_t)qx + (size_t)qy * gs + (size_t)qz * gs * gs] += acc;
+    float *dst = gdens + (size_t)qx + (size_t)qy * gs + (size_t)qz * gs * gs;
+    if (atomic) red_add_f32(dst, acc);   // running beside the ray backward (which scatters with red.add into the same plane)
+    else *dst += acc;
   }
 }
 
@@ -1007,9 +1010,9 @@ struct PeerSet
 };
 __device__ __forceinline__ float4 ld_peer(const float *p)
 {
-  float4 v;   // peer memory is another GPU's HBM: bypass L1, never reuse a line from the previous iteration
-  asm volatile("ld.global.cv.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
+  // peer memory is another GPU's HBM.  .cg = no L1 allocation (nothing is re-read), requests still coalesce into full lines
+  // (.cv — "fetch again every time" — splits them and costs NVLink packet efficiency)
+  return __ldcg(reinterpret_cast<const float4 *>(p));
 }
 __global__ void __launch_bounds__(256) adam_peer_kernel(const PeerSet P, float *__restrict__ V, float *__restrict__ Sq, size_t off, size_t count,
                                                         const AdamConst C)
@@ -1018,18 +1021,24 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(const PeerSet P, float *
   if (i4 >= count) return;
   const size_t at = off + i4;
   if (i4 + 4 <= count) {
-    float4 gv = ld_peer(P.grad[0] + at);
-    for (int r = 1; r < P.world; r++) {
-      const float4 o = ld_peer(P.grad[r] + at);
-      gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
-    }
+    // all ranks' loads are issued before the first one is consumed (a peer load is a microsecond away); summed in rank order
+    float4 gr[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < P.world) gr[r] = ld_peer(P.grad[r] + at);
     float4 pv = *reinterpret_cast<const float4 *>(P.param[P.rank] + at);
     float4 vv = *reinterpret_cast<float4 *>(V + at), sv = *reinterpret_cast<float4 *>(Sq + at);
+    float4 gv = gr[0];
+#pragma unroll
+    for (int r = 1; r < 8; r++)
+      if (r < P.world) { gv.x += gr[r].x; gv.y += gr[r].y; gv.z += gr[r].z; gv.w += gr[r].w; }
     adam_update(pv.x, gv.x, vv.x, sv.x, C); adam_update(pv.y, gv.y, vv.y, sv.y, C);
     adam_update(pv.z, gv.z, vv.z, sv.z, C); adam_update(pv.w, gv.w, vv.w, sv.w, C);
     *reinterpret_cast<float4 *>(V + at) = vv;
     *reinterpret_cast<float4 *>(Sq + at) = sv;
-    for (int r = 0; r < P.world; r++) *reinterpret_cast<float4 *>(P.param[r] + at) = pv;
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < P.world) *reinterpret_cast<float4 *>(P.param[r] + at) = pv;
   } else {
     for (size_t i = at; i < off + count; i++) {
       float g = P.grad[0][i];
@@ -1274,18 +1283,27 @@ void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *r
 {
   grad_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, ref_rgba, grey, nullptr, nullptr);
 }
+size_t grad_rays_hit_bytes(size_t n, int gs, uint32_t *cap_out)
+{
+  const uint32_t cap = 3u * (uint32_t)gs + 40u;   // a ray crosses < 3 gs cells; tie events add a few
+  if (cap_out) *cap_out = cap;
+  return n * cap * sizeof(HitRec);
+}
 void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, uint32_t *fb_count,
-                      uint32_t *fb_list, cudaStream_t st)
+                      uint32_t *fb_list, void *hit_scratch, cudaStream_t st)
 {
   if (n == 0) return;
   cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
   const unsigned g = blocks_for(n * 32, kBlock);
+  uint32_t cap = 0;
+  grad_rays_hit_bytes(n, S.gs, &cap);
+  HitRec *hb = (HitRec *)hit_scratch;
   if (S.occ) {
-    if (grey) grad_rays_warp_kernel<true, true><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
-    else grad_rays_warp_kernel<true, false><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
+    if (grey) grad_rays_warp_kernel<true, true><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
+    else grad_rays_warp_kernel<true, false><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
   } else {
-    if (grey) grad_rays_warp_kernel<false, true><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
-    else grad_rays_warp_kernel<false, false><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list);
+    if (grey) grad_rays_warp_kernel<false, true><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
+    else grad_rays_warp_kernel<false, false><<<g, kBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
   }
   // rays the warp kernel cannot take (axis-aligned): the generic thread-per-ray march, usually an empty launch
   grad_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, ref_rgba, grey, fb_list, fb_count);
@@ -1303,7 +1321,7 @@ void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float
   const size_t N = (size_t)gs * gs * gs;
   if (gs >= kTvT) {
     const int tiles = gs / kTvT;
-    tv_fused_kernel<<<tiles * tiles * tiles, 256, 0, st>>>(gs, dens, gdens, 0);
+    tv_fused_kernel<<<tiles * tiles * tiles, 256, 0, st>>>(gs, dens, gdens, 0, 0);
     return;
   }
   tv_voxel_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, dens, tmp_v);
@@ -1320,10 +1338,10 @@ void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t coun
   C.om_b1 = om_b1; C.om_b2 = om_b2; C.inv_om_b1 = 1.0 / om_b1; C.inv_om_b2 = 1.0 / om_b2;
   adam_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(p + off, g + off, V + off, S + off, count, C, zero_grad);
 }
-void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, cudaStream_t st)
+void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, int atomic, cudaStream_t st)
 {
   const int tiles = gs / kTvT, l0 = z_begin / kTvT, l1 = z_end / kTvT;
-  if (l1 > l0) tv_fused_kernel<<<tiles * tiles * (l1 - l0), 256, 0, st>>>(gs, dens, gdens, l0);
+  if (l1 > l0) tv_fused_kernel<<<tiles * tiles * (l1 - l0), 256, 0, st>>>(gs, dens, gdens, l0, atomic);
 }
 void launch_adam_peer(int world, int rank, float *const *grads, float *const *params, float *V, float *S, size_t off, size_t count, float lr,
                       float beta1, float beta2, float eps, double om_b1, double om_b2, cudaStream_t st)

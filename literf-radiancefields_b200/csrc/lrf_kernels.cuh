@@ -27,8 +27,10 @@ void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float 
 // backward
 void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st);
 // packed rays: warp-per-ray kernel + generic fallback over the queue (fb_count: 1 uint32, fb_list: n uint32); 2 launches
+// hit_scratch: grad_rays_hit_bytes(n, gs) bytes where pass A leaves each ray's hit list for pass B, or nullptr (pass B walks again)
+size_t grad_rays_hit_bytes(size_t n, int gs, uint32_t *cap_out);
 void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, uint32_t *fb_count,
-                      uint32_t *fb_list, cudaStream_t st);
+                      uint32_t *fb_list, void *hit_scratch, cudaStream_t st);
 void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_inv_dev, const uint32_t *picks, uint32_t w, uint32_t h,
                      float *o, float *d, cudaStream_t st);
 // per-cell
@@ -38,7 +40,7 @@ void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t coun
 void launch_fill(float *p, size_t count, float v, cudaStream_t st);
 // multi-GPU: TV gradient of the nodes in z-planes [z_begin, z_end) (multiples of 8), and the Adam pass over the element range
 // [off, off+count) that sums the gradient of all ranks through peer memory and writes the parameters to every replica
-void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, cudaStream_t st);
+void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, int atomic, cudaStream_t st);   // gs >= 8 only
 void launch_adam_peer(int world, int rank, float *const *grads, float *const *params, float *V, float *S, size_t off, size_t count, float lr,
                       float beta1, float beta2, float eps, double om_b1, double om_b2, cudaStream_t st);
 // layout conversion: host AoS [N][13]  <->  device planes dens[N] + col[N][12]

@@ -13,7 +13,9 @@
 //   * the adjoint of sample k needs only prefix/suffix sums of the composited colour (closed form of the reverse sweep,
 //     see grad_kernel), so the backward is sample-parallel too: a warp scan, then each lane scatters its 8 x 13 values
 //     with red.global.add.{f32,v4.f32}.
-// Pass A (forward) and pass B (adjoint + scatter) both walk the ray; nothing per-sample is kept in memory.
+// Pass A (forward) walks the ray and leaves its hit list — 12 bytes per hit: packed cell + the two fp32 slab times — in a
+// per-ray scratch slice; pass B (adjoint + scatter) reads the list back instead of walking again (the lock-step traversal is
+// ~3/4 of the kernel's instructions).  A ray whose list outgrows the slice simply walks twice.
 #pragma once
 #include "lrf_fast.cuh"
 
@@ -208,6 +210,13 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane)
   return v;
 }
 
+// hit list entry left by pass A for pass B
+struct HitRec
+{
+  uint32_t cell;      // pack_cell
+  float tmin, tmax;
+};
+
 // one lane's sample of a 32-hit group
 struct LaneSample
 {
@@ -343,7 +352,8 @@ template <bool SPARSE, bool GREY> struct WarpRay
 // sample in forward order:  a_tr_k = -T_k (c_k . aC) + [ (suffix_k . aC) + aT_n T_n ] / tr_k  (last sample: aT_n T_k),
 // the closed form of the reverse sweep  aT <- tr aT + (1 - tr)(c . aC);  suffix_k = total - prefix_k.
 template <bool SPARSE, bool GREY>
-__device__ void warp_ray_backward(const SceneDev &S, const uint64_t *etab, const float *o, const float *d, const float *ref)
+__device__ void warp_ray_backward(const SceneDev &S, const uint64_t *etab, const float *o, const float *d, const float *ref, HitRec *buf,
+                                  uint32_t cap)
 {
   const int lane = threadIdx.x & 31;
   WarpRay<SPARSE, GREY> R(S, etab);
@@ -351,14 +361,36 @@ __device__ void warp_ray_backward(const SceneDev &S, const uint64_t *etab, const
   double ctot[3] = {0.0, 0.0, 0.0};
   float aC[3] = {0.0f, 0.0f, 0.0f}, Tn = 0.0f, aTn = 0.0f;
   uint32_t n_shaded = 0;
+  uint32_t gathered = 0;                                        // hits latched by pass 0 (the recorded part of the list)
   for (int pass = 0; pass < 2; pass++) {
-    if (!R.begin(o, d)) return;                                // ref :688: empty hit list, no loss term
+    const bool replay = pass == 1 && buf != nullptr;            // pass 1 reads the hit list pass 0 recorded
+    if (!replay && !R.begin(o, d)) return;                      // ref :688: empty hit list, no loss term
     float T_run = 1.0f, carry_t = -1.0f;
     double cpre[3] = {0.0, 0.0, 0.0};
-    uint32_t left = pass ? n_shaded : 0xffffffffu, count = 0;
+    uint32_t left = pass ? n_shaded : 0xffffffffu, count = 0, done = 0;
     while (left) {
       LaneSample L;
-      const int m = R.gather(L, (int)min(left, 32u));
+      int m;
+      if (replay) {
+        m = (int)min(left, 32u);
+        if (lane < m) {
+          const HitRec r = buf[done + lane];
+          unpack_cell(r.cell, L.x, L.y, L.z);
+          L.tmin = r.tmin; L.tmax = r.tmax;
+        }
+        done += (uint32_t)m;
+      } else {
+        m = R.gather(L, (int)min(left, 32u));
+        if (pass == 0 && buf != nullptr) {
+          if (gathered + (uint32_t)m > cap) buf = nullptr;      // list outgrew the slice: pass 1 walks again
+          else if (lane < m) {
+            HitRec r;
+            r.cell = pack_cell(L.x, L.y, L.z); r.tmin = L.tmin; r.tmax = L.tmax;
+            buf[gathered + lane] = r;
+          }
+          gathered += (uint32_t)m;
+        }
+      }
       if (m == 0) break;
       R.shade_density(L, m, carry_t);
       bool broke;

@@ -54,10 +54,14 @@ class PeerExchange:
         with self.torch.cuda.stream(self.stream):
             self.dist.all_reduce(self.flag)
 
-    def percell(self, it):
-        """between the backward of iteration `it` and the next one"""
+    def percell(self, it, tv_done=False):
+        """between the backward of iteration `it` and the next one.  tv_done: the TV gradient of the own slab is already in
+        the local gradient (lrf_rays_grad_tv_dev_async ran it beside the backward)"""
         self.barrier()                       # every rank's gradient is complete
-        self.t.train_percell_peer_async(it)  # own slab: TV + sum over ranks + Adam, parameters written to every replica
+        if tv_done:
+            self.t.adam_peer_async(it)       # own slab: sum over ranks + Adam, parameters written to every replica
+        else:
+            self.t.train_percell_peer_async(it)  # the same preceded by the slab's TV gradient
         self.barrier()                       # every replica is fully written, every gradient fully read
         self.t.zero_grad_async()
 

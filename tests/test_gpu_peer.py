@@ -83,3 +83,35 @@ def test_peer_group_argument_checks(pkg):
     t.train_percell_peer_async(0)
     t.sync()
     t.close()
+
+
+def test_tv_beside_backward_equals_sequential(pkg):
+    """lrf_rays_grad_tv_dev_async (TV on a second stream, red.add) + lrf_adam_zero_async == backward; TV; Adam; zero"""
+    gs = 32
+    grid = libs.lcg_grid(gs, 20.0)
+    S = OracleScene(gs, grid)
+    vi, pi = cameras(None, 3, 7)
+    S.set_cam(vi, pi)
+    o, d = S.gen_rays(32, 32)
+    n = o.shape[0]
+    ref = np.random.default_rng(9).random((n, 4)).astype(np.float32)
+    ta, tb = _mk(pkg, gs, grid), _mk(pkg, gs, grid)
+    bufs = [pkg.DeviceBuffer(ta, a.nbytes) for a in (o, d, ref)]
+    for b, a in zip(bufs, (o, d, ref)):
+        b.upload(a)
+    for it in range(2):
+        ta.rays_grad_tv_dev_async(n, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr)
+        ta.sync()
+        ga = ta.get_grad().astype(np.float64)
+        tb.rays_grad(o, d, ref)
+        tb.kernel2D_TVGrad()
+        gb = tb.get_grad().astype(np.float64)
+        assert np.linalg.norm(ga - gb) <= 1e-5 * np.linalg.norm(gb)
+        tb.set_grad(ta.get_grad())            # same gradient bits into both optimisers
+        ta.adam_zero_async(it)
+        ta.sync()
+        tb.optimizerStep(it)
+        tb.zeroGrad()
+        assert np.array_equal(ta.get_grid().view(np.uint32), tb.get_grid().view(np.uint32))
+        assert not ta.get_grad().any()
+    ta.close(); tb.close(); S.close()
