@@ -25,7 +25,7 @@ struct lrf_ctx
   float *params = nullptr, *grad = nullptr, *V = nullptr, *S = nullptr;
   float *tv_tmp = nullptr;            // 2*N floats
   int32_t *boxes = nullptr;           // device, n_boxes*3 (null while dense)
-  uint32_t *occ = nullptr, *vox2id = nullptr;
+  uint32_t *occ = nullptr, *vox2id = nullptr, *occ8 = nullptr;   // occ8: one bit per 8^3-voxel brick
   size_t n_boxes = 0;
   bool dense = true;
   float bb_min[3] = {0, 0, 0}, bb_max[3] = {1, 1, 1};
@@ -98,6 +98,8 @@ static SceneDev scene_of(const lrf_ctx *h)
   S.gcol = h->grad ? reinterpret_cast<float4 *>(h->grad + h->N) : nullptr;
   S.occ = h->dense ? nullptr : h->occ;
   S.vox2id = h->dense ? nullptr : h->vox2id;
+  S.occ8 = h->dense ? nullptr : h->occ8;
+  S.nb8 = (h->gs - 1 + 7) / 8;
   S.gs_f = (float)h->gs;
   S.inv_gs_f = 1.0f / (float)h->gs;
   S.inv_gs = 1.0 / (double)h->gs;
@@ -125,9 +127,9 @@ static void free_grid(lrf_ctx *h)
 {
   peer_detach(h);   // the attached pointers describe replicas of the grid that is going away
   cudaFree(h->params); cudaFree(h->grad); cudaFree(h->V); cudaFree(h->S); cudaFree(h->tv_tmp);
-  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id);
+  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id); cudaFree(h->occ8);
   h->params = h->grad = h->V = h->S = h->tv_tmp = nullptr;
-  h->boxes = nullptr; h->occ = h->vox2id = nullptr;
+  h->boxes = nullptr; h->occ = h->vox2id = h->occ8 = nullptr;
 }
 
 static int alloc_grid(lrf_ctx *h, int gs)
@@ -274,9 +276,9 @@ int lrf_adam_state_download(lrf_ctx *h, int which, float *c) { return h ? downlo
 
 static int install_boxes_dev(lrf_ctx *h, int32_t *xyz_dev, size_t n)  // takes ownership of xyz_dev
 {
-  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id);
+  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id); cudaFree(h->occ8);
   h->boxes = xyz_dev;
-  h->occ = h->vox2id = nullptr;
+  h->occ = h->vox2id = h->occ8 = nullptr;
   h->n_boxes = n;
   h->dense = false;
   const size_t nv = (size_t)(h->gs - 1) * (h->gs - 1) * (h->gs - 1);
@@ -285,7 +287,11 @@ static int install_boxes_dev(lrf_ctx *h, int32_t *xyz_dev, size_t n)  // takes o
   CK(cudaMalloc(&h->vox2id, (nv + 1) * 4));
   CK(cudaMemsetAsync(h->occ, 0, words * 4, h->stream));
   CK(cudaMemsetAsync(h->vox2id, 0, (nv + 1) * 4, h->stream));
-  launch_build_box_maps(h->gs - 1, h->boxes, n, h->occ, h->vox2id, h->stream);
+  const int nb8 = (h->gs - 1 + 7) / 8;
+  const size_t words8 = ((size_t)nb8 * nb8 * nb8 + 31) / 32 + 1;
+  CK(cudaMalloc(&h->occ8, words8 * 4));
+  CK(cudaMemsetAsync(h->occ8, 0, words8 * 4, h->stream));
+  launch_build_box_maps(h->gs - 1, h->boxes, n, h->occ, h->vox2id, h->occ8, nb8, h->stream);
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -305,8 +311,8 @@ int lrf_set_boxes(lrf_ctx *h, const int32_t *xyz, size_t n)
 int lrf_set_boxes_dense(lrf_ctx *h)
 {
   NEED_GRID(h);
-  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id);
-  h->boxes = nullptr; h->occ = h->vox2id = nullptr;
+  cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id); cudaFree(h->occ8);
+  h->boxes = nullptr; h->occ = h->vox2id = h->occ8 = nullptr;
   h->dense = true;
   h->n_boxes = (size_t)(h->gs - 1) * (h->gs - 1) * (h->gs - 1);
   return 0;

@@ -55,31 +55,12 @@ __device__ __forceinline__ bool fast_path_ok(const float *d)
 // MODE 0: render (stops at the reference's throughput break, ref example_tracer.cpp:131)
 // MODE 1: parity taps (keeps traversing after the break to count every hit; records voxels, cauchy, touched nodes)
 constexpr int kFastBlock = 128;   // threads per block of the kernels that use FastMarch (shared-memory stride)
-// Build-time knobs of the colour path (tools/variants.py measures the combinations; the defaults are the fastest):
-//   LRF_NEW_FROM_REGS  1: shade() takes the 4 nodes that were just gathered from registers and reads only the 4 clean
-//                         slots of the window from shared memory (4 LDS.128 instead of 8 per sample)
-//   LRF_BASIS_IN_REGS  1: the ray's 9 SH basis values stay in registers instead of shared memory (9 LDS.32 fewer per sample)
-//   LRF_TWO_PHASE      1: the colour of pairs 2,3 is gathered AFTER the traversal step and overlapped with the density
-//                         lerps + expf chain instead of being in flight across the step (26 fewer live registers:
-//                         60 -> 16 bytes of spills at 128 registers, 2.70 -> 2.26 ms per view, profiles/r1f_variants.txt)
-//                      2: rolling — one node's colour in flight at a time (slower: too little cover per gather)
-#ifndef LRF_NEW_FROM_REGS
-#define LRF_NEW_FROM_REGS 0
-#endif
-#ifndef LRF_TWO_PHASE
-#define LRF_TWO_PHASE 1
-#endif
-//   LRF_DENSE_FAST     1: dense render (MODE 0, no occupancy test): the common iteration — no tie, no pending queue, the
-//                         step rule of :145 not triggered — runs as ONE basic block (masked traversal step, branch-free
-//                         expf, unconditional colour); every rare event falls through to the general body
-//                         MEASURED SLOWER (2.68 vs 2.26 ms per view, profiles/r1f_variants.txt box 5): in one block ptxas
-//                         moves the gather consumers ahead of the traversal step and the latency cover that the
-//                         branch boundaries enforce is lost (and spills go 16 -> 96 bytes).  Kept as a knob, off.
-#ifndef LRF_DENSE_FAST
-#define LRF_DENSE_FAST 0
-#endif
-#ifndef LRF_BASIS_IN_REGS
-#define LRF_BASIS_IN_REGS 0
+// Measured dead ends (profiles/r1f_variants.txt; the code is in the history of this file): taking the just-gathered nodes from
+// registers instead of re-reading the shared window, the SH basis in registers, a rolling one-node-at-a-time gather, 96 or 168
+// registers per thread, and a branch-free single-basic-block iteration for dense grids (ptxas then schedules the gather
+// consumers ahead of the traversal step and the latency cover is lost).  What paid is the two-phase gather below.
+#ifndef LRF_SEARCH_TRIPS
+#define LRF_SEARCH_TRIPS 4   // sparse render: traversal events per lane between two shading slots of the warp (see run())
 #endif
 
 template <int MODE, bool SPARSE, bool GREY> struct FastMarch
@@ -90,9 +71,6 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   float o_[3], d_[3], idir_[3];
   float4 *csm;       // this thread's colour window in shared memory: csm[slot * kFastBlock] = {R, G, B, q = sum_j sh_j Y_j(d)}
   float *ysm;        // this thread's SH basis in shared memory: ysm[j * kFastBlock], j = 0..8 (frees 9 registers)
-#if LRF_BASIS_IN_REGS
-  float yreg[9];
-#endif
   // traversal state of the CURRENT cell
   int cell[3];
   int sgn[3];
@@ -102,6 +80,10 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   uint32_t nx[2], ny[2], nz[2];   // node index contribution held by parity p of each axis: x, y*gs, z*gs^2
   float dn[8];
   uint32_t dirty;    // slots whose registers are stale
+  // sparse sets: the coarse occupancy bit of the 8^3-voxel brick the ray is in, re-read only when the brick changes — in
+  // empty space a traversal step then costs no memory access at all
+  uint32_t brick_id = 0xffffffffu;   // index of the cached coarse word
+  uint32_t brick_word = 0;
   uint32_t odd;      // parity bits of the cell coordinates
   // compositing
   float thr = 1.0f, tPrev = -1.0f, cauchy = 0.0f;
@@ -131,16 +113,27 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       float Y[9];
       sh_eval_2(df, Y);
 #pragma unroll
-      for (int j = 0; j < 9; j++) {
-#if LRF_BASIS_IN_REGS
-        yreg[j] = Y[j];
-#else
-        ysm[j * kFastBlock] = Y[j];
-#endif
-      }
+      for (int j = 0; j < 9; j++) ysm[j * kFastBlock] = Y[j];
     }
   }
 
+  __device__ __forceinline__ bool present_here()
+  {
+    if (S.occ8 == nullptr) return cell_present(S, cell[0], cell[1], cell[2]);   // dense set seen through a SPARSE instantiation (parity taps)
+    // no branches: the coarse word is re-read only when its index changes, the fine word only inside an occupied brick —
+    // both as PREDICATED loads, so that the lanes of a warp stay in lock-step through empty space
+    const uint32_t b = (uint32_t)(cell[0] >> 3) + (uint32_t)(cell[1] >> 3) * S.nb8 + (uint32_t)(cell[2] >> 3) * S.nb8 * S.nb8;
+    const uint32_t wi = b >> 5;
+    uint32_t w = brick_word;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p ld.global.nc.u32 %0, [%3];\n\t}" : "+r"(w) : "r"(wi), "r"(brick_id), "l"(S.occ8 + wi));
+    brick_word = w;
+    brick_id = wi;
+    const uint32_t on = (w >> (b & 31)) & 1u;
+    const uint32_t lin = (uint32_t)cell[0] + (uint32_t)cell[1] * S.n + (uint32_t)cell[2] * S.n * S.n;
+    uint32_t fw = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.u32 %0, [%2];\n\t}" : "+r"(fw) : "r"(on), "l"(S.occ + (lin >> 5)));
+    return (fw >> (lin & 31)) & 1u;
+  }
   __device__ __forceinline__ uint32_t slot_node(int s) const { return nx[s & 1] + ny[(s >> 1) & 1] + nz[s >> 2]; }
 
   // bring every piece of per-cell state to cell (x,y,z) from scratch (first cell, tie events, resync after them)
@@ -181,7 +174,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       pa[a] = mm[a] ? pan : pa[a];
       cell[a] = mm[a] ? cell[a] + sgn[a] : cell[a];
     }
-    odd ^= (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);   // ax < 0 (masked call): nothing moves
+    odd ^= (m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u);
     const int csel = m0 ? cell[0] : (m1 ? cell[1] : cell[2]);
     const int ssel = m0 ? sgn[0] : (m1 ? sgn[1] : sgn[2]);
     // the node that enters lies on the new exit plane (coordinate csel + [ssel > 0]); it takes the slot of its parity
@@ -240,11 +233,6 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   };
   __device__ __forceinline__ void load_basis(Basis &Y) const
   {
-#if LRF_BASIS_IN_REGS
-    Y.Y0 = yreg[0];
-    Y.Y12 = pk2(yreg[1], yreg[2]); Y.Y34 = pk2(yreg[3], yreg[4]); Y.Y56 = pk2(yreg[5], yreg[6]); Y.Y78 = pk2(yreg[7], yreg[8]);
-    return;
-#endif
     Y.Y0 = ysm[0];
     Y.Y12 = pk2(ysm[1 * kFastBlock], ysm[2 * kFastBlock]); Y.Y34 = pk2(ysm[3 * kFastBlock], ysm[4 * kFastBlock]);
     Y.Y56 = pk2(ysm[5 * kFastBlock], ysm[6 * kFastBlock]); Y.Y78 = pk2(ysm[7 * kFastBlock], ysm[8 * kFastBlock]);
@@ -258,12 +246,12 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     dn[J] = wA ? td : dn[J];
     dn[7 - J] = wB ? td : dn[7 - J];
   }
-  template <int J> __device__ __forceinline__ void commit_pair(uint32_t stale, uint32_t hi, const NodeLoad &L, const Basis &Y, float4 &fresh)
+  template <int J> __device__ __forceinline__ void commit_pair(uint32_t stale, uint32_t hi, const NodeLoad &L, const Basis &Y)
   {
     commit_density<J>(stale, hi, L.td);
-    commit_colour<J>(stale, L, Y, fresh);
+    commit_colour<J>(stale, L, Y);
   }
-  template <int J> __device__ __forceinline__ void commit_colour(uint32_t stale, const NodeLoad &L, const Basis &Y, float4 &fresh)
+  template <int J> __device__ __forceinline__ void commit_colour(uint32_t stale, const NodeLoad &L, const Basis &Y)
   {
     const bool wA = (stale >> J) & 1u;
     if (GREY) return;
@@ -274,8 +262,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     float ql, qh;
     upk2(q2, ql, qh);
     const float q = fmaf(L.a.w, Y.Y0, ql + qh);
-    fresh = make_float4(L.a.x, L.a.y, L.a.z, q);
-    csm[(wA ? J : 7 - J) * kFastBlock] = fresh;
+    csm[(wA ? J : 7 - J) * kFastBlock] = make_float4(L.a.x, L.a.y, L.a.z, q);
   }
   __device__ __forceinline__ void refill_blocking(uint32_t stale)
   {
@@ -285,8 +272,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       issue_pair<0>(stale, L0); issue_pair<1>(stale, L1); issue_pair<2>(stale, L2); issue_pair<3>(stale, L3);
       Basis Y;
       if (!GREY) load_basis(Y);
-      float4 f0, f1, f2, f3;
-      commit_pair<0>(stale, hi, L0, Y, f0); commit_pair<1>(stale, hi, L1, Y, f1); commit_pair<2>(stale, hi, L2, Y, f2); commit_pair<3>(stale, hi, L3, Y, f3);
+      commit_pair<0>(stale, hi, L0, Y); commit_pair<1>(stale, hi, L1, Y); commit_pair<2>(stale, hi, L2, Y); commit_pair<3>(stale, hi, L3, Y);
       // served this round: the low member of each pair if stale, else the high member
       const uint32_t lowm = stale & 0x0fu;
       stale &= ~(lowm | (__brev((hi & ~lowm & 0x0fu)) >> 24));
@@ -299,29 +285,6 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     float delta, lf[3];
     uint32_t odd;   // parity bits of the cell coordinates
   };
-  // the same without the step rule of :145-146; returns true when the rule applies (the caller then runs apply_step_rule)
-  __device__ __forceinline__ bool geometry_norule(Geom &g)
-  {
-    const float tmin = fmaxf(fmaxf(tn[0], tn[1]), tn[2]);
-    const float tmax = fminf(fminf(tf[0], tf[1]), tf[2]);
-    tPrev = (tPrev < 0.0f) ? tmin : tPrev;                     // :139
-    const float t = (tmin + tmax) * 0.5f;                      // :142
-    g.delta = t - tPrev;                                       // :144
-    tPrev = t;                                                 // :190
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      const float bmin = sgn[a] > 0 ? pa[a] - S.inv_gs_f : pa[a];
-      const float p = o(a) + t * d(a);                         // :148
-      g.lf[a] = (p - bmin) * S.gs_f;                           // :150
-    }
-    g.odd = odd;
-    return g.delta > S.step_gate_f;
-  }
-  __device__ __forceinline__ void apply_step_rule(Geom &g) const
-  {
-    if (g.delta > S.step_gate_f)                               // :145-146
-      g.delta = (float)((double)g.delta - (double)((int)((double)g.delta / S.step) - 1) * S.step);
-  }
   __device__ __forceinline__ void geometry(Geom &g)
   {
     const float tmin = fmaxf(fmaxf(tn[0], tn[1]), tn[2]);      // all finite: == the std::max / std::min chains of :18-43
@@ -343,14 +306,12 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   }
 
   // shade one sample from the window; false = the reference's throughput break fired
-  // fresh[J] = the node gathered for pair (J, 7-J) this step, already contracted; fresh_low bit J set = it sits in slot J
-  // (else in slot 7-J).  Only used when LRF_NEW_FROM_REGS.
   struct Sig
   {
     float tr, wgt;
   };
   // density part of a sample (decision path, bit-exact): transmittance of the step and the compositing weight
-  template <bool NOBRANCH = false> __device__ __forceinline__ Sig shade_sigma(const Geom &g)
+  __device__ __forceinline__ Sig shade_sigma(const Geom &g)
   {
     const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
     const float *lf = g.lf;
@@ -370,21 +331,17 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
     if (MODE == 1) cauchy += logf(1.0f + 2.0f * sigma * sigma);  // :173
     Sig r;
-    r.tr = NOBRANCH ? expf_libm_nobranch(-sigma * g.delta, etab) : expf_libm(-sigma * g.delta, etab);   // :175
+    r.tr = expf_libm(-sigma * g.delta, etab);                  // :175
     r.wgt = thr * (1.0f - r.tr);                               // :187
     return r;
   }
-  __device__ __forceinline__ bool shade(const Geom &g, const float4 *fresh, uint32_t fresh_low)
-  {
-    return shade_colour(g, shade_sigma(g), fresh, fresh_low);
-  }
   // colour part (1e-4-tolerance path) + the throughput update; false = the reference's throughput break fired
-  template <bool ALWAYS = false> __device__ __forceinline__ bool shade_colour(const Geom &g, const Sig sg, const float4 *fresh, uint32_t fresh_low)
+  __device__ __forceinline__ bool shade_colour(const Geom &g, const Sig sg)
   {
     const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
     const float *lf = g.lf;
     const float tr = sg.tr, wgt = sg.wgt;
-    if (ALWAYS || wgt != 0.0f) {   // ALWAYS: the reference's own unconditional `col += thr * (1 - tr) * c` (:187)
+    if (wgt != 0.0f) {
       if (GREY) { col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt; }
       else {
         // ---- colour: 1e-4-tolerance path, packed-pair FMAs ----
@@ -395,23 +352,6 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
         const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
         const float w[8] = {w00 * wz0, w10 * wz0, w01 * wz0, w11 * wz0, w00 * wz1, w10 * wz1, w01 * wz1, w11 * wz1};
         // two independent accumulation chains per pair of channels (latency), merged at the end
-#if LRF_NEW_FROM_REGS
-        u64 RG0, BQ0, RG1, BQ1;
-#pragma unroll
-        for (int J = 0; J < 4; J++) {
-          const bool lowNew = (fresh_low >> J) & 1u;
-          const float wN = lowNew ? w[J] : w[7 - J], wO = lowNew ? w[7 - J] : w[J];
-          const float4 co = csm[(lowNew ? 7 - J : J) * kFastBlock], cn = fresh[J];
-          const u64 wn2 = pk2(wN, wN), wo2 = pk2(wO, wO);
-          if (J == 0) {
-            RG0 = mul2(wn2, pk2(cn.x, cn.y)); BQ0 = mul2(wn2, pk2(cn.z, cn.w));
-            RG1 = mul2(wo2, pk2(co.x, co.y)); BQ1 = mul2(wo2, pk2(co.z, co.w));
-          } else {
-            RG0 = fma2(wn2, pk2(cn.x, cn.y), RG0); BQ0 = fma2(wn2, pk2(cn.z, cn.w), BQ0);
-            RG1 = fma2(wo2, pk2(co.x, co.y), RG1); BQ1 = fma2(wo2, pk2(co.z, co.w), BQ1);
-          }
-        }
-#else
         const float4 c0 = csm[0], c1 = csm[kFastBlock];
         u64 RG0 = mul2(pk2(w[0], w[0]), pk2(c0.x, c0.y)), BQ0 = mul2(pk2(w[0], w[0]), pk2(c0.z, c0.w));
         u64 RG1 = mul2(pk2(w[1], w[1]), pk2(c1.x, c1.y)), BQ1 = mul2(pk2(w[1], w[1]), pk2(c1.z, c1.w));
@@ -424,7 +364,6 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
           RG1 = fma2(wk1, pk2(cb.x, cb.y), RG1);
           BQ1 = fma2(wk1, pk2(cb.z, cb.w), BQ1);
         }
-#endif
         float R, G, Bc, Q, R1, G1, B1, Q1;
         upk2(RG0, R, G); upk2(BQ0, Bc, Q); upk2(RG1, R1, G1); upk2(BQ1, B1, Q1);
         R += R1; G += G1; Bc += B1; Q += Q1;
@@ -519,54 +458,125 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     cell[0] = cell[1] = cell[2] = -8;
     dirty = 0;
 
+    // ONE traversal event: +1 = standing on a cell to be shaded, 0 = keep going (empty voxel of a sparse set, or a tie event
+    // was queued), -1 = the ray is done
+    auto step_once = [&]() -> int {
+      if (nq > 0) {
+        int x, y, z;
+        unpack_cell(queue[--nq], x, y, z);
+        set_cell(x, y, z);
+        return 1;
+      }
+      if (resync) {
+        if (leaving_after) return -1;
+        if (cell[0] != cur[0] || cell[1] != cur[1] || cell[2] != cur[2]) set_cell(cur[0], cur[1], cur[2]);
+        resync = false;
+      }
+      // ---- which face does the ray leave through?  fp32 filter, exact fp64 when close ----
+      int ax = decide_fast();
+      if (ax < 0) {
+        const int cross = exact_cross();
+        if (cross & (cross - 1)) {
+          // true tie: the ray passes through a lattice edge / corner — 3 or 7 boxes at the same distance
+          int lo[3];
+          leaving_after = false;
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            lo[a] = cell[a];
+            cur[a] = cell[a];
+            if (cross & (1 << a)) {
+              const int nw = cell[a] + sgn[a];
+              lo[a] = min(cell[a], nw);
+              cur[a] = nw;
+              if ((unsigned)nw >= (unsigned)n) leaving_after = true;
+            }
+          }
+          uint32_t cells[8];
+          const int mm = build_event_cells(S, lo[0], lo[1], lo[2], cross, cross, pos_mask, cells);
+          for (int j = 0; j < mm; j++) queue[j] = cells[mm - 1 - j];
+          nq = mm;
+          resync = true;
+          return 0;
+        }
+        ax = (cross & 1) ? 0 : ((cross & 2) ? 1 : 2);
+      }
+      const int moved = advance(ax);
+      if ((unsigned)moved >= (unsigned)n) return -1;           // left the lattice
+      if (SPARSE && !present_here()) return 0;
+      return 1;
+    };
     // moves the traversal to the next cell to be shaded; false = the ray is done
     auto next_cell = [&]() -> bool {
       for (;;) {
-        if (nq > 0) {
-          int x, y, z;
-          unpack_cell(queue[--nq], x, y, z);
-          set_cell(x, y, z);
-          return true;
-        }
-        if (resync) {
-          if (leaving_after) return false;
-          if (cell[0] != cur[0] || cell[1] != cur[1] || cell[2] != cur[2]) set_cell(cur[0], cur[1], cur[2]);
-          resync = false;
-        }
-        // ---- which face does the ray leave through?  fp32 filter, exact fp64 when close ----
-        int ax = decide_fast();
-        if (ax < 0) {
-          const int cross = exact_cross();
-          if (cross & (cross - 1)) {
-            // true tie: the ray passes through a lattice edge / corner — 3 or 7 boxes at the same distance
-            int lo[3];
-            leaving_after = false;
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-              lo[a] = cell[a];
-              cur[a] = cell[a];
-              if (cross & (1 << a)) {
-                const int nw = cell[a] + sgn[a];
-                lo[a] = min(cell[a], nw);
-                cur[a] = nw;
-                if ((unsigned)nw >= (unsigned)n) leaving_after = true;
-              }
-            }
-            uint32_t cells[8];
-            const int mm = build_event_cells(S, lo[0], lo[1], lo[2], cross, cross, pos_mask, cells);
-            for (int j = 0; j < mm; j++) queue[j] = cells[mm - 1 - j];
-            nq = mm;
-            resync = true;
-            continue;
-          }
-          ax = (cross & 1) ? 0 : ((cross & 2) ? 1 : 2);
-        }
-        const int moved = advance(ax);
-        if ((unsigned)moved >= (unsigned)n) return false;      // left the lattice
-        if (SPARSE && !cell_present(S, cell[0], cell[1], cell[2])) continue;
-        return true;
+        const int st = step_once();
+        if (st) return st > 0;
       }
     };
+
+    // One sample: (1) start the gathers of the current cell's stale nodes — pairs 0,1 complete, pairs 2,3 density only —,
+    // (2) the cell's geometry and the whole traversal step to the next cell (no memory needed: this is what covers the
+    // gathers), (3) commit pairs 0,1, start the colour of pairs 2,3 behind the density lerps + the fp64 expf chain, commit
+    // them, colour, composite.  The two-phase gather keeps 26 fewer registers live across the traversal step: 60 -> 16 bytes
+    // of spills at 128 registers, 2.70 -> 2.26 ms per 800x800 view (profiles/r1f_variants.txt).
+    struct Pending
+    {
+      uint32_t stale, hi, node2, node3;
+      NodeLoad L0, L1, L2, L3;
+      Geom g;
+    };
+    auto sample_begin = [&](Pending &P) {
+      P.stale = dirty;
+      P.hi = high_members(P.stale);
+      if (P.stale & P.hi & 0x0fu) {                            // both members of a pair stale (after a full reset): rare
+        refill_blocking(P.stale);
+        P.stale = 0;
+        P.hi = 0;
+      }
+      P.node2 = pair_node<2>(P.stale); P.node3 = pair_node<3>(P.stale);
+      issue_pair<0>(P.stale, P.L0); issue_pair<1>(P.stale, P.L1);
+      P.L2.td = __ldg(S.dens + P.node2); P.L3.td = __ldg(S.dens + P.node3);
+      dirty = 0;
+      geometry(P.g);
+    };
+    auto sample_end = [&](Pending &P) -> bool {               // false = the reference's throughput break fired
+      Basis Y;
+      if (!GREY) load_basis(Y);
+      commit_pair<0>(P.stale, P.hi, P.L0, Y); commit_pair<1>(P.stale, P.hi, P.L1, Y);
+      commit_density<2>(P.stale, P.hi, P.L2.td); commit_density<3>(P.stale, P.hi, P.L3.td);
+      issue_colour(P.node2, P.L2); issue_colour(P.node3, P.L3);   // in flight across the density lerps + expf chain
+      const Sig sg = shade_sigma(P.g);
+      commit_colour<2>(P.stale, P.L2, Y); commit_colour<3>(P.stale, P.L3, Y);
+      return shade_colour(P.g, sg);
+    };
+
+    if (SPARSE && MODE == 0) {
+      // Sparse render.  A lane that is looking for its next occupied voxel must not hold up the lanes that stand on one
+      // (a ray leaving the sphere of config 4 steps through ~200 empty voxels while its neighbours shade), and the search
+      // itself must stay in lock-step.  So every lane gets LRF_SEARCH_TRIPS traversal events per trip of this loop, taken
+      // warp-synchronously (the vote re-converges the warp after every event; without it the lanes that take a rare path —
+      // an exact-compare step, a coarse-word reload — never re-merge before the search ends: ncu showed 7.8 active lanes per
+      // instruction, profiles/r1k_sparse_ncu_summary.txt), and the lanes that stand on a voxel shade it in the same trip.
+      // Lanes that have left run() have exited the kernel and take no part in the votes.
+      auto search = [&]() -> int {
+        int st = 0, trips = LRF_SEARCH_TRIPS;
+        do {
+          if (st == 0) st = step_once();
+        } while (--trips > 0 && __any_sync(0xffffffffu, st == 0));
+        return st;
+      };
+      int st = search();
+      for (;;) {
+        if (st < 0) return;
+        const bool have = st > 0;
+        Pending P;
+        if (have) {
+          n_hit = 1;
+          sample_begin(P);
+        }
+        st = search();                                         // on a voxel: step to the next one; searching: keep searching
+        if (have && !sample_end(P)) return;
+      }
+    }
 
     if (!next_cell()) return;
     for (;;) {
@@ -583,95 +593,10 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
           for (int s = 0; s < 8; s++) touched[slot_node(s)] = 1;
         }
       } else n_hit = 1;
-      // 1. start the gathers of this cell's stale nodes
-      uint32_t stale = dirty;
-      uint32_t hi = high_members(stale);
-      if (stale & hi & 0x0fu) {                                // both members of a pair stale (after a full reset): rare
-        refill_blocking(stale);
-        stale = 0;
-        hi = 0;
-      }
-      NodeLoad L0, L1, L2, L3;
-#if LRF_TWO_PHASE == 2
-      // rolling gather: the four densities and ONE node's colour cross the traversal step; the other three colours are
-      // gathered one after the other, each behind a slice of the density / expf arithmetic (12 registers in flight)
-      const uint32_t node1 = pair_node<1>(stale), node2 = pair_node<2>(stale), node3 = pair_node<3>(stale);
-      issue_pair<0>(stale, L0);
-      L1.td = __ldg(S.dens + node1); L2.td = __ldg(S.dens + node2); L3.td = __ldg(S.dens + node3);
-      dirty = 0;
-      Geom g;
-      geometry(g);
+      Pending P;
+      sample_begin(P);
       const bool more = next_cell();
-      Basis Y;
-      if (!GREY) load_basis(Y);
-      float4 fresh[4];
-      issue_colour(node1, L1);
-      commit_pair<0>(stale, hi, L0, Y, fresh[0]);
-      commit_density<1>(stale, hi, L1.td); commit_density<2>(stale, hi, L2.td); commit_density<3>(stale, hi, L3.td);
-      issue_colour(node2, L2);
-      const Sig sg = shade_sigma(g);
-      commit_colour<1>(stale, L1, Y, fresh[1]);
-      issue_colour(node3, L3);
-      commit_colour<2>(stale, L2, Y, fresh[2]);
-      commit_colour<3>(stale, L3, Y, fresh[3]);
-      if (!shade_colour(g, sg, fresh, stale & 0x0fu)) {
-#elif LRF_TWO_PHASE
-      const uint32_t node2 = pair_node<2>(stale), node3 = pair_node<3>(stale);
-      issue_pair<0>(stale, L0); issue_pair<1>(stale, L1);
-      L2.td = __ldg(S.dens + node2); L3.td = __ldg(S.dens + node3);
-      dirty = 0;
-      Geom g;
-#if LRF_DENSE_FAST
-      if (MODE == 0 && !SPARSE) {
-        const bool rule = geometry_norule(g);
-        if (!(rule || nq > 0 || resync)) {
-          // ---- the common iteration: one basic block ----
-          const int ax = decide_fast();                          // < 0: planes too close for fp32 -> exact step after shading
-          const int moved = advance(ax);                         // masked: a no-op for ax < 0
-          Basis Y;
-          if (!GREY) load_basis(Y);
-          float4 fresh[4];
-          commit_pair<0>(stale, hi, L0, Y, fresh[0]); commit_pair<1>(stale, hi, L1, Y, fresh[1]);
-          commit_density<2>(stale, hi, L2.td); commit_density<3>(stale, hi, L3.td);
-          issue_colour(node2, L2); issue_colour(node3, L3);
-          const Sig sg = shade_sigma<true>(g);
-          commit_colour<2>(stale, L2, Y, fresh[2]); commit_colour<3>(stale, L3, Y, fresh[3]);
-          if (!shade_colour<true>(g, sg, fresh, stale & 0x0fu)) return;
-          if (ax < 0) {
-            if (!next_cell()) return;
-          } else if ((unsigned)moved >= (unsigned)n) return;     // left the lattice
-          continue;
-        }
-        apply_step_rule(g);
-      } else geometry(g);
-#else
-      geometry(g);
-#endif
-      const bool more = next_cell();
-      Basis Y;
-      if (!GREY) load_basis(Y);
-      float4 fresh[4];
-      commit_pair<0>(stale, hi, L0, Y, fresh[0]); commit_pair<1>(stale, hi, L1, Y, fresh[1]);
-      commit_density<2>(stale, hi, L2.td); commit_density<3>(stale, hi, L3.td);
-      issue_colour(node2, L2); issue_colour(node3, L3);       // in flight across the density lerps + expf chain
-      const Sig sg = shade_sigma(g);
-      commit_colour<2>(stale, L2, Y, fresh[2]); commit_colour<3>(stale, L3, Y, fresh[3]);
-      if (!shade_colour(g, sg, fresh, stale & 0x0fu)) {
-#else
-      issue_pair<0>(stale, L0); issue_pair<1>(stale, L1); issue_pair<2>(stale, L2); issue_pair<3>(stale, L3);
-      dirty = 0;
-      // 2. this cell's geometry, then the whole traversal step to the next cell — no memory needed
-      Geom g;
-      geometry(g);
-      const bool more = next_cell();
-      // 3. consume the gathers (second round only after a full reset), shade
-      Basis Y;
-      if (!GREY) load_basis(Y);
-      float4 fresh[4];
-      commit_pair<0>(stale, hi, L0, Y, fresh[0]); commit_pair<1>(stale, hi, L1, Y, fresh[1]); commit_pair<2>(stale, hi, L2, Y, fresh[2]);
-      commit_pair<3>(stale, hi, L3, Y, fresh[3]);
-      if (!shade(g, fresh, stale & 0x0fu)) {
-#endif
+      if (!sample_end(P)) {
         alive = false;
         if (MODE == 0) return;
       }

@@ -1169,12 +1169,16 @@ __global__ void box_compact_kernel(const int32_t *__restrict__ xyz, size_t n, co
   const size_t o = offs[t];
   new_xyz[3 * o] = xyz[3 * t]; new_xyz[3 * o + 1] = xyz[3 * t + 1]; new_xyz[3 * o + 2] = xyz[3 * t + 2];
 }
-__global__ void build_box_maps_kernel(int nv, const int32_t *__restrict__ xyz, size_t n, uint32_t *__restrict__ occ, uint32_t *__restrict__ vox2id)
+__global__ void build_box_maps_kernel(int nv, const int32_t *__restrict__ xyz, size_t n, uint32_t *__restrict__ occ, uint32_t *__restrict__ vox2id,
+                                      uint32_t *__restrict__ occ8, int nb8)
 {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const uint32_t lin = (uint32_t)xyz[3 * t] + (uint32_t)xyz[3 * t + 1] * nv + (uint32_t)xyz[3 * t + 2] * nv * nv;
+  const uint32_t x = (uint32_t)xyz[3 * t], y = (uint32_t)xyz[3 * t + 1], z = (uint32_t)xyz[3 * t + 2];
+  const uint32_t lin = x + y * nv + z * nv * nv;
   atomicOr(occ + (lin >> 5), 1u << (lin & 31));
+  const uint32_t b = (x >> 3) + (y >> 3) * nb8 + (z >> 3) * nb8 * nb8;
+  if (!((occ8[b >> 5] >> (b & 31)) & 1u)) atomicOr(occ8 + (b >> 5), 1u << (b & 31));
   vox2id[lin] = (uint32_t)t;
 }
 __global__ void count_nonzero_kernel(const uint8_t *__restrict__ marks, size_t n, unsigned long long *out)
@@ -1395,10 +1399,10 @@ void launch_box_compact(const int32_t *xyz, size_t n, const uint32_t *flags, con
   if (n == 0) return;
   box_compact_kernel<<<blocks_for(n, 256), 256, 0, st>>>(xyz, n, flags, offsets, new_xyz);
 }
-void launch_build_box_maps(int nv, const int32_t *xyz, size_t n, uint32_t *occ, uint32_t *vox2id, cudaStream_t st)
+void launch_build_box_maps(int nv, const int32_t *xyz, size_t n, uint32_t *occ, uint32_t *vox2id, uint32_t *occ8, int nb8, cudaStream_t st)
 {
   if (n == 0) return;
-  build_box_maps_kernel<<<blocks_for(n, 256), 256, 0, st>>>(nv, xyz, n, occ, vox2id);
+  build_box_maps_kernel<<<blocks_for(n, 256), 256, 0, st>>>(nv, xyz, n, occ, vox2id, occ8, nb8);
 }
 void launch_count_nonzero(const uint8_t *marks, size_t n, unsigned long long *out, cudaStream_t st)
 {

@@ -13,10 +13,19 @@ import bench
 
 pkg = ge.package()
 n_views = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4
+for a in sys.argv[1:]:
+    if a.startswith("--workload="):
+        bench.select_workload(a.split("=", 1)[1])
 t = pkg.RayMarcherExample(0)
 t.InitGrid(bench.GS)
-grid = bench.lcg_grid(bench.GS, bench.DENSITY_SCALE)
-t.set_grid(grid)
+grid = None
+if bench.FILL_MODE is None:
+    grid = bench.lcg_grid(bench.GS, bench.DENSITY_SCALE)
+    t.set_grid(grid)
+else:
+    t.fill_synthetic(bench.DENSITY_SCALE, bench.FILL_MODE)
+if bench.SPARSE:
+    t.RebuildOctree()
 proj_inv, views = bench.cameras(pkg, 0, 1)
 t.set_proj_inv(proj_inv)
 frame = pkg.DeviceBuffer(t, bench.W * bench.H * 4)
