@@ -529,7 +529,65 @@ struct BwdVisitor
   float aC[3], aTn, Tn;
   uint32_t n_total, k = 0;
   Window W;
-  __device__ BwdVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g) { W.reset(); }
+  // Gradient window.  Consecutive samples of a ray share 4 of their 8 nodes, and for one ray the 13 adjoints of a node are
+  // 5 numbers — density, R, G, B and the adjoint of q = sh . Y(d) (the 9 SH adjoints are that one number times the ray's
+  // basis).  They are accumulated per parity slot and leave for HBM only when the slot's node changes (or the ray ends):
+  // 4 nodes x 4 red.global.add per step instead of 8 x 4, and 5 FMAs per corner instead of 13 multiplies.
+  float ad[8], ar[8], ag[8], ab[8], aq[8];
+  int ca[3][2];     // node coordinates the slots currently accumulate for (-4: empty)
+  __device__ BwdVisitor(const SceneDev &s, const uint64_t *t, bool g) : S(s), etab(t), grey(g)
+  {
+    W.reset();
+#pragma unroll
+    for (int a = 0; a < 3; a++) ca[a][0] = ca[a][1] = -4;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ad[i] = ar[i] = ag[i] = ab[i] = aq[i] = 0.0f;
+  }
+  template <int SLOT> __device__ __forceinline__ void flush_slot()
+  {
+    const int sx = SLOT & 1, sy = (SLOT >> 1) & 1, sz = SLOT >> 2;
+    const uint32_t node = (uint32_t)ca[0][sx] + (uint32_t)ca[1][sy] * S.gs + (uint32_t)ca[2][sz] * S.gs * S.gs;
+    if (ad[SLOT] != 0.0f) red_add(S.gdens + node, ad[SLOT]);
+    if (!grey && (aq[SLOT] != 0.0f || ar[SLOT] != 0.0f || ag[SLOT] != 0.0f || ab[SLOT] != 0.0f)) {
+      float4 *q = S.gcol + (size_t)node * kColF4;
+      const float v = aq[SLOT];
+      red_add4(q, ar[SLOT], ag[SLOT], ab[SLOT], R.Y[0] * v);
+      red_add4(q + 1, R.Y[1] * v, R.Y[2] * v, R.Y[3] * v, R.Y[4] * v);
+      red_add4(q + 2, R.Y[5] * v, R.Y[6] * v, R.Y[7] * v, R.Y[8] * v);
+    }
+    ad[SLOT] = ar[SLOT] = ag[SLOT] = ab[SLOT] = aq[SLOT] = 0.0f;
+  }
+  // bring the gradient window to voxel (x,y,z): slots whose node changes are flushed first
+  __device__ __forceinline__ void grad_window_move(int x, int y, int z)
+  {
+    const int v[3] = {x, y, z};
+    int req[3][2];
+    bool chg[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      req[a][0] = v[a] + (v[a] & 1);
+      req[a][1] = v[a] + 1 - (v[a] & 1);
+      chg[a][0] = ca[a][0] != req[a][0];
+      chg[a][1] = ca[a][1] != req[a][1];
+    }
+    if (ca[0][0] >= 0) {   // not the very first sample
+      if (chg[0][0] | chg[1][0] | chg[2][0]) flush_slot<0>();
+      if (chg[0][1] | chg[1][0] | chg[2][0]) flush_slot<1>();
+      if (chg[0][0] | chg[1][1] | chg[2][0]) flush_slot<2>();
+      if (chg[0][1] | chg[1][1] | chg[2][0]) flush_slot<3>();
+      if (chg[0][0] | chg[1][0] | chg[2][1]) flush_slot<4>();
+      if (chg[0][1] | chg[1][0] | chg[2][1]) flush_slot<5>();
+      if (chg[0][0] | chg[1][1] | chg[2][1]) flush_slot<6>();
+      if (chg[0][1] | chg[1][1] | chg[2][1]) flush_slot<7>();
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) { ca[a][0] = req[a][0]; ca[a][1] = req[a][1]; }
+  }
+  __device__ __forceinline__ void flush_all()
+  {
+    if (ca[0][0] < 0) return;
+    flush_slot<0>(); flush_slot<1>(); flush_slot<2>(); flush_slot<3>(); flush_slot<4>(); flush_slot<5>(); flush_slot<6>(); flush_slot<7>();
+  }
   __device__ __forceinline__ bool sample(int x, int y, int z)
   {
     SampleGeom g;
@@ -566,31 +624,25 @@ struct BwdVisitor
     // d tr / d sigma = -delta * tr ;  cauchy: d/dsigma log(1 + 2 sigma^2) = 4 sigma / (1 + 2 sigma^2), weight 0.0005 (:267)
     const float a_sigma = -g.delta * tr * a_tr + 0.0005f * (4.0f * sigma / (1.0f + 2.0f * sigma * sigma));
     const float a_dens = a_sigma;                              // relu passes iff density >= 0 (:170)
-    if (a_dens != 0.0f) {
-#pragma unroll
-      for (int cn = 0; cn < 8; cn++) red_add(S.gdens + window_node(S, cn, x, y, z), w[cn] * a_dens);
-    }
+    float a_rgb[3] = {0.0f, 0.0f, 0.0f}, a_raw = 0.0f;
     if (!grey && wgt != 0.0f) {
-      float a_rgb[3] = {0.0f, 0.0f, 0.0f}, a_s = 0.0f;
+      float a_s = 0.0f;
 #pragma unroll
       for (int ch = 0; ch < 3; ch++) {
         const float a_c = wgt * aC[ch];
         const float u = acc[ch] * s;
         if (0.0f < u && u <= 1.0f) { a_rgb[ch] = s * a_c; a_s = fmaf(acc[ch], a_c, a_s); }   // clamp passes iff 0 < u <= 1
       }
-      const float a_raw = (0.0f < raw && raw <= 1.0f) ? a_s : 0.0f;
-      if (a_raw != 0.0f || a_rgb[0] != 0.0f || a_rgb[1] != 0.0f || a_rgb[2] != 0.0f) {
-        float a_sh[9];
+      a_raw = (0.0f < raw && raw <= 1.0f) ? a_s : 0.0f;
+    }
+    if (a_dens != 0.0f || a_raw != 0.0f || a_rgb[0] != 0.0f || a_rgb[1] != 0.0f || a_rgb[2] != 0.0f) {
+      grad_window_move(x, y, z);
 #pragma unroll
-        for (int j = 0; j < 9; j++) a_sh[j] = R.Y[j] * a_raw;
-#pragma unroll
-        for (int cn = 0; cn < 8; cn++) {
-          float4 *q = S.gcol + (size_t)window_node(S, cn, x, y, z) * kColF4;
-          const float ww = w[cn];
-          red_add4(q, ww * a_rgb[0], ww * a_rgb[1], ww * a_rgb[2], ww * a_sh[0]);
-          red_add4(q + 1, ww * a_sh[1], ww * a_sh[2], ww * a_sh[3], ww * a_sh[4]);
-          red_add4(q + 2, ww * a_sh[5], ww * a_sh[6], ww * a_sh[7], ww * a_sh[8]);
-        }
+      for (int cn = 0; cn < 8; cn++) {
+        const float ww = w[cn];
+        ad[cn] = fmaf(ww, a_dens, ad[cn]);
+        ar[cn] = fmaf(ww, a_rgb[0], ar[cn]); ag[cn] = fmaf(ww, a_rgb[1], ag[cn]); ab[cn] = fmaf(ww, a_rgb[2], ab[cn]);
+        aq[cn] = fmaf(ww, a_raw, aq[cn]);
       }
     }
     thr *= tr;
@@ -598,6 +650,23 @@ struct BwdVisitor
     return !last;
   }
 };
+
+// hit enumeration for the visitors above: the fp32-filtered exact walker of lrf_wray.cuh (same hit list as march(), a fraction of
+// its fp64 work) for every ray it can take, the generic march for the rest (a zero / non-finite reciprocal direction component)
+template <class Visitor> __device__ __forceinline__ void walk(const SceneDev &S, const float *o, const float *d, Visitor &vis)
+{
+  if (!fast_path_ok(d)) {
+    march(S, o, d, vis);
+    return;
+  }
+  RayWalker<true> W(S);
+  if (!W.start(o, d)) return;
+  bool more = W.next();
+  while (more) {
+    if (!vis.sample(W.cell[0], W.cell[1], W.cell[2])) return;
+    more = W.next();
+  }
+}
 
 // idx_list / idx_count (packed-ray form only): when given, thread i handles ray idx_list[i] for i < *idx_count — the
 // fallback queue of the warp-per-ray kernel (rays with a zero / non-finite reciprocal direction component)
@@ -627,7 +696,7 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
   }
   FwdAVisitor fa(S, etab, grey != 0);
   ray_ctx_init(fa.R, o, d, grey != 0);
-  march(S, o, d, fa);
+  walk(S, o, d, fa);
   if (fa.n_shaded == 0) return;  // ref :688  empty hit list: no loss term
   const float4 rp = __ldg(reinterpret_cast<const float4 *>(ref_rgba) + ray);
   float ref[3] = {rp.x, rp.y, rp.z};
@@ -650,7 +719,8 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
   bw.Tn = fa.thr;
   bw.aTn = (float)((double)0.0001f * (1.0 / ((double)fa.thr + 1e-3) - 1.0 / ((double)(1.0f - fa.thr) + 1e-3)));
   bw.n_total = fa.n_shaded;
-  march(S, o, d, bw);
+  walk(S, o, d, bw);
+  bw.flush_all();
 }
 
 // packed ray batch, one WARP per ray (lrf_wray.cuh)
