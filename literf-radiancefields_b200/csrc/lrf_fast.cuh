@@ -57,8 +57,9 @@ __device__ __forceinline__ bool fast_path_ok(const float *d)
 constexpr int kFastBlock = 128;   // threads per block of the kernels that use FastMarch (shared-memory stride)
 // Measured dead ends (profiles/r1f_variants.txt; the code is in the history of this file): taking the just-gathered nodes from
 // registers instead of re-reading the shared window, the SH basis in registers, a rolling one-node-at-a-time gather, 96 or 168
-// registers per thread, and a branch-free single-basic-block iteration for dense grids (ptxas then schedules the gather
-// consumers ahead of the traversal step and the latency cover is lost).  What paid is the two-phase gather below.
+// registers per thread, a branch-free single-basic-block iteration for dense grids (ptxas then schedules the gather
+// consumers ahead of the traversal step and the latency cover is lost), and an L2 prefetch of the ray's coming nodes 2 / 4 / 8
+// cells ahead (-2 %: the first-touch DRAM misses are not what the loop waits for).  What paid is the two-phase gather below.
 #ifndef LRF_SEARCH_TRIPS
 #define LRF_SEARCH_TRIPS 4   // sparse render: traversal events per lane between two shading slots of the warp (see run())
 #endif
