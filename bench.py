@@ -380,7 +380,8 @@ def main():
 
 def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier, iters=20, batch=4096):
     """BASELINE.json configs[2]: grid optimisation on the 256^3 grid, 4096-ray batches per GPU against synthetic targets:
-    one iteration = ray generation + {backward(4096 rays) || TV gradient} + Adam + zero on one GPU; on N GPUs either
+    one iteration = ray generation + backward(4096 rays) + per-cell pass ({TV -> Adam(density)} || Adam(colour), zeroing
+    fused) on one GPU; on N GPUs either
     backward + NCCL all-reduce of the 13*N-float gradient + replicated TV + Adam + zero, or backward || slab TV + the
     peer-memory fused exchange (barrier, slab {sum over ranks + Adam -> every replica}, barrier, zero)."""
     import ctypes as C
@@ -412,10 +413,6 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     def one(it, exchange=True):
         off = it * batch
         t._ck(t.lib.lrf_gen_rays_dev_async(t.h, batch, vi_dev.ptr, picks_dev.ptr + off * 8, W, H, o_dev.ptr, d_dev.ptr))
-        if grad_tensor is None:     # one GPU: TV beside the backward (second stream), then Adam + zero
-            t._ck(t.lib.lrf_rays_grad_tv_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
-            t._ck(t.lib.lrf_adam_zero_async(t.h, it))
-            return
         t._ck(t.lib.lrf_rays_grad_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + off * 16, 0))
         if grad_tensor is not None and exchange:
             import torch

@@ -683,13 +683,13 @@ int lrf_set_adam_hparams(lrf_ctx *h, float lr, float b1, float b2, float eps)
   h->lr = lr; h->beta1 = b1; h->beta2 = b2; h->eps = eps;
   return 0;
 }
-static void adam_launch(lrf_ctx *h, int iter, int which, int zero)
+static void adam_launch(lrf_ctx *h, int iter, int which, int zero, cudaStream_t st = nullptr)
 {
   const double b1 = std::pow(h->beta1, iter + 1), b2 = std::pow(h->beta2, iter + 1);   // example_tracer.h:152-153 (double)
   size_t off = 0, count = h->N * kCell;
   if (which == 1) count = h->N;                            // density plane
   else if (which == 2) { off = h->N; count = h->N * 12; }  // everything but density (i % CellSize != 0)
-  launch_adam(h->params, h->grad, h->V, h->S, off, count, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, zero, h->stream);
+  launch_adam(h->params, h->grad, h->V, h->S, off, count, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, zero, st ? st : h->stream);
   h->launches++;
 }
 int lrf_adam_step(lrf_ctx *h, int iter, int which)
@@ -707,6 +707,9 @@ int lrf_train_percell_async(lrf_ctx *h, int iter)
 {
   NEED_GRID(h);
   if (ensure_tv_tmp(h)) return 1;
+  // (Measured: running {TV -> Adam(density)} on the second stream beside Adam(colour) buys nothing — the TV kernel needs the
+  // whole GPU to be fast (latency-bound shared-memory phases), throttled to a persistent grid it becomes the long pole:
+  // 1.46 ms sequential vs 1.51-2.28 ms overlapped, tools/time_percell.py.)
   launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
   h->launches += (h->gs >= 8) ? 1 : 3;   // fused TV kernel (8^3 tiles), stage-by-stage below that
   adam_launch(h, iter, 0, 1);
@@ -731,7 +734,7 @@ int lrf_rays_grad_tv_dev_async(lrf_ctx *h, size_t n, const float *o, const float
   CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
   int z0 = 0, z1 = h->gs;
   if (h->peer_world > 1) { const int zs = h->gs / h->peer_world; z0 = zs * h->peer_rank; z1 = z0 + zs; }
-  launch_tv_grad_slab(h->gs, h->params, h->grad, z0, z1, 1, h->side);
+  launch_tv_grad_slab(h->gs, h->params, h->grad, z0, z1, 1, 0, h->side);
   h->launches++;
   CK(cudaEventRecord(h->ev_join, h->side));
   if (lrf_rays_grad_dev_async(h, n, o, d, ref, grey)) return 1;
@@ -808,7 +811,7 @@ int lrf_tv_grad_slab_async(lrf_ctx *h)
 {
   NEED_PEERS(h);
   const int zs = h->gs / h->peer_world;
-  launch_tv_grad_slab(h->gs, h->params, h->grad, zs * h->peer_rank, zs * (h->peer_rank + 1), 0, h->stream);
+  launch_tv_grad_slab(h->gs, h->params, h->grad, zs * h->peer_rank, zs * (h->peer_rank + 1), 0, 0, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -926,14 +926,18 @@ __global__ void tv_scatter_kernel(int gs, const float *__restrict__ gv, float *_
 // per tile.  Values agree with the staged kernels to rounding (lam * d / r is formed as d * (lam * rsqrt)); the TV
 // gradient is compared with the oracle to 1e-5 relative, not bit-for-bit (the reference's own sum order is a race).
 constexpr int kTvT = 8;
-__global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens, int bz0, int atomic)
+__global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens, int bz0, int atomic,
+                                                       int n_tiles)
 {
   __shared__ float sD[12 * 12 * 12], sV[11 * 11 * 11], sG[9 * 9 * 9];
   __shared__ float sEx[10 * 10 * 10], sEy[10 * 10 * 10], sEz[10 * 10 * 10];
   const int tiles = gs / kTvT;
-  const int bx = blockIdx.x % tiles, by = (blockIdx.x / tiles) % tiles, bz = bz0 + blockIdx.x / (tiles * tiles);   // bz0: first tile layer of a z-slab
-  const int q0x = bx * kTvT, q0y = by * kTvT, q0z = bz * kTvT;
   const int m = gs - 1;
+  // a block walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...: with gridDim.x == n_tiles one tile per block; a small
+  // grid (2 blocks per SM) is used when the kernel shares the GPU with the HBM-bound Adam pass of the colour planes
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int bx = tile % tiles, by = (tile / tiles) % tiles, bz = bz0 + tile / (tiles * tiles);   // bz0: first tile layer of a z-slab
+  const int q0x = bx * kTvT, q0y = by * kTvT, q0z = bz * kTvT;
   for (int i = threadIdx.x; i < 12 * 12 * 12; i += 256) {
     const int lx = i % 12, ly = (i / 12) % 12, lz = i / 144;
     const int x = min(max(q0x - 2 + lx, 0), m), y = min(max(q0y - 2 + ly, 0), m), z = min(max(q0z - 2 + lz, 0), m);
@@ -994,6 +998,8 @@ __global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__re
     float *dst = gdens + (size_t)qx + (size_t)qy * gs + (size_t)qz * gs * gs;
     if (atomic) red_add_f32(dst, acc);   // running beside the ray backward (which scatters with red.add into the same plane)
     else *dst += acc;
+  }
+  __syncthreads();   // the shared arrays are reused by the next tile
   }
 }
 
@@ -1395,7 +1401,7 @@ void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float
   const size_t N = (size_t)gs * gs * gs;
   if (gs >= kTvT) {
     const int tiles = gs / kTvT;
-    tv_fused_kernel<<<tiles * tiles * tiles, 256, 0, st>>>(gs, dens, gdens, 0, 0);
+    tv_fused_kernel<<<tiles * tiles * tiles, 256, 0, st>>>(gs, dens, gdens, 0, 0, tiles * tiles * tiles);
     return;
   }
   tv_voxel_kernel<<<blocks_for(N, 256), 256, 0, st>>>(gs, dens, tmp_v);
@@ -1412,10 +1418,13 @@ void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t coun
   C.om_b1 = om_b1; C.om_b2 = om_b2; C.inv_om_b1 = 1.0 / om_b1; C.inv_om_b2 = 1.0 / om_b2;
   adam_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(p + off, g + off, V + off, S + off, count, C, zero_grad);
 }
-void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, int atomic, cudaStream_t st)
+void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, int atomic, int max_blocks, cudaStream_t st)
 {
   const int tiles = gs / kTvT, l0 = z_begin / kTvT, l1 = z_end / kTvT;
-  if (l1 > l0) tv_fused_kernel<<<tiles * tiles * (l1 - l0), 256, 0, st>>>(gs, dens, gdens, l0, atomic);
+  const int n_tiles = tiles * tiles * (l1 - l0);
+  if (n_tiles <= 0) return;
+  const int grid = (max_blocks > 0 && max_blocks < n_tiles) ? max_blocks : n_tiles;
+  tv_fused_kernel<<<grid, 256, 0, st>>>(gs, dens, gdens, l0, atomic, n_tiles);
 }
 void launch_adam_peer(int world, int rank, float *const *grads, float *const *params, float *V, float *S, size_t off, size_t count, float lr,
                       float beta1, float beta2, float eps, double om_b1, double om_b2, cudaStream_t st)

@@ -40,7 +40,7 @@ void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t coun
 void launch_fill(float *p, size_t count, float v, cudaStream_t st);
 // multi-GPU: TV gradient of the nodes in z-planes [z_begin, z_end) (multiples of 8), and the Adam pass over the element range
 // [off, off+count) that sums the gradient of all ranks through peer memory and writes the parameters to every replica
-void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, int atomic, cudaStream_t st);   // gs >= 8 only
+void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, int atomic, int max_blocks, cudaStream_t st);   // gs >= 8 only; max_blocks > 0: persistent grid of that many blocks
 void launch_adam_peer(int world, int rank, float *const *grads, float *const *params, float *V, float *S, size_t off, size_t count, float lr,
                       float beta1, float beta2, float eps, double om_b1, double om_b2, cudaStream_t st);
 // layout conversion: host AoS [N][13]  <->  device planes dens[N] + col[N][12]
