@@ -724,8 +724,11 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
 }
 
 // packed ray batch, one WARP per ray (lrf_wray.cuh)
+#ifndef LRF_WRAY_MINB
+#define LRF_WRAY_MINB 3
+#endif
 template <bool SPARSE, bool GREY>
-__global__ void __launch_bounds__(kBlock, 3) grad_rays_warp_kernel(const __grid_constant__ SceneDev S, size_t n_rays, const float *__restrict__ ro,
+__global__ void __launch_bounds__(kBlock, LRF_WRAY_MINB) grad_rays_warp_kernel(const __grid_constant__ SceneDev S, size_t n_rays, const float *__restrict__ ro,
                                                                 const float *__restrict__ rd, const float *__restrict__ ref_rgba,
                                                                 uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list,
                                                                 HitRec *__restrict__ hitbuf, uint32_t hitcap)

@@ -16,6 +16,9 @@
 // Pass A (forward) walks the ray and leaves its hit list — 12 bytes per hit: packed cell + the two fp32 slab times — in a
 // per-ray scratch slice; pass B (adjoint + scatter) reads the list back instead of walking again (the lock-step traversal is
 // ~3/4 of the kernel's instructions).  A ray whose list outgrows the slice simply walks twice.
+// ncu (profiles/r1n_wray_ncu_summary.txt): 27 K warp instructions per ray, issue slots 26 % busy, 51 % of the stall samples on
+// the load scoreboard, 10 warps per SM — the gathers' latency is the bound.  Tried without gain: 128 / 96 registers per thread
+// (16 / 20 warps per SM: -2.5 % / +16 %) and an L2 prefetch of the next group's nodes from the recorded list (+2 %).
 #pragma once
 #include "lrf_fast.cuh"
 

@@ -66,8 +66,29 @@ def time_one(n_views):
         t.render_dev_async(frame.ptr, bench.W, bench.H)
         frame.download(host)
         ck = (ck * 1000003 + int(host.astype(np.uint64).sum())) % (1 << 61)
-    print(json.dumps({"lib": os.path.basename(os.environ.get("LRF_B200_LIB", "default")), "ms_per_view": ms / len(pick), "Mrays_s": bench.W * bench.H * len(pick) / ms / 1e3,
-                      "checksum": ck}))
+    out = {"lib": os.path.basename(os.environ.get("LRF_B200_LIB", "default")), "ms_per_view": ms / len(pick), "Mrays_s": bench.W * bench.H * len(pick) / ms / 1e3,
+           "checksum": ck}
+    if os.environ.get("LRF_VARIANTS_TRAIN"):   # packed-batch backward: 4096 rays, CUDA events
+        rng = np.random.default_rng(1)
+        n = 4096
+        vi_dev = pkg.DeviceBuffer(t, len(views) * 64)
+        vi_dev.upload(np.stack(views).astype(np.float32))
+        picks = np.stack([rng.integers(0, len(views), n), rng.integers(0, bench.W * bench.H, n)], axis=1).astype(np.uint32)
+        pk, rf = pkg.DeviceBuffer(t, picks.nbytes), pkg.DeviceBuffer(t, n * 16)
+        pk.upload(picks)
+        rf.upload(rng.random((n, 4)).astype(np.float32))
+        od, dd = pkg.DeviceBuffer(t, n * 12), pkg.DeviceBuffer(t, n * 12)
+        t.zeroGrad()
+        t._ck(t.lib.lrf_gen_rays_dev_async(t.h, n, vi_dev.ptr, pk.ptr, bench.W, bench.H, od.ptr, dd.ptr))
+        for _ in range(2):
+            t._ck(t.lib.lrf_rays_grad_dev_async(t.h, n, od.ptr, dd.ptr, rf.ptr, 0))
+        t.sync()
+        t.timer_start()
+        for _ in range(10):
+            t._ck(t.lib.lrf_rays_grad_dev_async(t.h, n, od.ptr, dd.ptr, rf.ptr, 0))
+        out["ms_backward_4096"] = t.timer_stop_ms() / 10
+        out["grad_abs_sum"] = float(np.abs(t.get_grad().astype(np.float64)).sum())
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
