@@ -59,7 +59,11 @@ constexpr int kFastBlock = 128;   // threads per block of the kernels that use F
 // registers instead of re-reading the shared window, the SH basis in registers, a rolling one-node-at-a-time gather, 96 or 168
 // registers per thread, a branch-free single-basic-block iteration for dense grids (ptxas then schedules the gather
 // consumers ahead of the traversal step and the latency cover is lost), and an L2 prefetch of the ray's coming nodes 2 / 4 / 8
-// cells ahead (-2 %: the first-touch DRAM misses are not what the loop waits for).  What paid is the two-phase gather below.
+// cells ahead (-2 %: the first-touch DRAM misses are not what the loop waits for).  Two more, both telling: replacing the exact
+// density lerps + fp64 expf by 11 approximate instructions made the loop 7 % SLOWER (that arithmetic is what covers the second
+// gather), and a rotated schedule that issues the next cell's pairs 0,1 before this cell's shading (twice the cover on paper)
+// ran 36 % slower with the load-scoreboard stalls tripled (profiles/r1f_variants.txt boxes 8, 9).  What paid is the two-phase
+// gather below.
 #ifndef LRF_SEARCH_TRIPS
 #define LRF_SEARCH_TRIPS 4   // sparse render: traversal events per lane between two shading slots of the warp (see run())
 #endif
