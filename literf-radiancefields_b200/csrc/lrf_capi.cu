@@ -46,6 +46,7 @@ struct lrf_ctx
   size_t fb_cap = 0;
   void *hit_scratch = nullptr;        // per-ray hit lists of the packed-batch backward
   size_t hit_bytes = 0;
+  int generic_image_grad = 0;   // 1: whole-image backward by the generic thread-per-ray kernel (tests compare the two)
   int force_generic = 0;   // parity taps: 1 = generic march for every ray (tests compare both paths)
   // resident target images: n_targets x tw x th float4, stbi_loadf layout
   float *targets = nullptr;
@@ -433,8 +434,14 @@ int lrf_render_grad_dev_async(lrf_ctx *h, uint32_t w, uint32_t hgt, const float 
 {
   NEED_GRID(h);
   if (w == 0 || hgt == 0) return 0;
-  launch_grad_image(scene_of(h), w, hgt, ref_dev, grey, h->stream);
-  h->launches++;
+  if (h->generic_image_grad) {
+    launch_grad_image(scene_of(h), w, hgt, ref_dev, grey, nullptr, nullptr, h->stream);
+    h->launches++;
+  } else {
+    if (ensure_fb(h, (size_t)w * hgt)) return 1;
+    launch_grad_image(scene_of(h), w, hgt, ref_dev, grey, h->fb, h->fb + 4, h->stream);
+    h->launches += 2;   // grad_image_fast_kernel + the generic kernel over its fallback queue
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -970,6 +977,7 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   NEED(h);
   const std::string s(name ? name : "");
   if (s == "force_generic_march") h->force_generic = value ? 1 : 0;
+  else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
   else return fail("unknown option: " + s);
   return 0;
 }

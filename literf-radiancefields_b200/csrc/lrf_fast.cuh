@@ -54,6 +54,10 @@ __device__ __forceinline__ bool fast_path_ok(const float *d)
 
 // MODE 0: render (stops at the reference's throughput break, ref example_tracer.cpp:131)
 // MODE 1: parity taps (keeps traversing after the break to count every hit; records voxels, cauchy, touched nodes)
+// MODE 2: backward, pass A — the forward again, keeping per-channel colour sums in fp64 and the shaded-sample count
+// MODE 3: backward, pass B — the adjoint of every sample in forward order (closed form of the reverse sweep, see
+//         lrf_kernels.cu), accumulated per window slot in shared memory and flushed with red.global.add when the slot's node
+//         changes (gradient window: half the atomics of a per-sample scatter, 5 accumulators per node instead of 13)
 constexpr int kFastBlock = 128;   // threads per block of the kernels that use FastMarch (shared-memory stride)
 // Measured dead ends (profiles/r1f_variants.txt; the code is in the history of this file): taking the just-gathered nodes from
 // registers instead of re-reading the shared window, the SH basis in registers, a rolling one-node-at-a-time gather, 96 or 168
@@ -99,6 +103,14 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   int32_t *vox = nullptr;
   uint32_t keep = 0;
   uint8_t *touched = nullptr;
+  // backward (MODE 2 out / MODE 3 in)
+  double csum[3] = {0.0, 0.0, 0.0};     // MODE 2: sum_k T_k (1 - tr_k) c_k per channel;  MODE 3: the running prefix of the same
+  double ctot[3];                       // MODE 3: pass A's totals
+  float aC[3], aTn, Tn;                 // MODE 3: adjoint of the clamped colour and of the final transmittance; the final transmittance
+  uint32_t n_total = 0, k_done = 0;     // MODE 3: samples pass A shaded / samples processed so far
+  float4 *gsm = nullptr;                // MODE 3: gradient window in shared memory, per slot {a_R, a_G, a_B, a_q} (stride kFastBlock)
+  float *gdm = nullptr;                 //         ... density adjoint per slot
+  uint32_t *nsm = nullptr;              //         ... node index the slot accumulates for
 
   __device__ FastMarch(const SceneDev &s, const uint64_t *t, float *ysm_, float4 *csm_) : S(s), etab(t), csm(csm_), ysm(ysm_) {}
   __device__ __forceinline__ float o(int a) const { return o_[a]; }
@@ -209,6 +221,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   {
     float td;
     float4 a, b, e;   // {R,G,B,sh0}, {sh1..sh4}, {sh5..sh8}
+    uint32_t node;    // MODE 3: the node these values belong to (the gradient window needs it when the slot is flushed)
   };
   // bit J of the result: member 7-J of pair J is stale
   static __device__ __forceinline__ uint32_t high_members(uint32_t stale) { return __brev(stale) >> 24; }
@@ -229,7 +242,47 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   {
     const uint32_t node = pair_node<J>(stale);
     L.td = __ldg(S.dens + node);
+    if (MODE == 3) L.node = node;
     issue_colour(node, L);
+  }
+  // ---- gradient window (MODE 3) ----
+  // Shared memory or registers, 2 / 3 / 4 blocks per SM: all 13.1-13.4 ms per 800x800 view at 256^3, and 7.0 ms with the red
+  // instructions removed — the L2 atomic throughput is the bound (profiles/r1f_variants.txt boxes 10, 11).
+  __device__ __forceinline__ void grad_window_reset()
+  {
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      gsm[s * kFastBlock] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      gdm[s * kFastBlock] = 0.0f;
+      nsm[s * kFastBlock] = 0u;
+    }
+  }
+  // send slot s's accumulated adjoints to the gradient planes and clear them (what Enzyme's `grid_d +=` does per sample)
+  __device__ __forceinline__ void grad_flush_slot(int s)
+  {
+    const uint32_t node = nsm[s * kFastBlock];
+    const float ad = gdm[s * kFastBlock];
+    if (ad != 0.0f) {
+      asm volatile("red.global.add.f32 [%0], %1;" ::"l"(S.gdens + node), "f"(ad) : "memory");
+      gdm[s * kFastBlock] = 0.0f;
+    }
+    if (GREY) return;
+    const float4 a = gsm[s * kFastBlock];
+    if (a.x != 0.0f || a.y != 0.0f || a.z != 0.0f || a.w != 0.0f) {
+      float4 *q = S.gcol + (size_t)node * kColF4;
+      const float v = a.w;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(a.x), "f"(a.y), "f"(a.z), "f"(ysm[0] * v) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 1), "f"(ysm[1 * kFastBlock] * v), "f"(ysm[2 * kFastBlock] * v),
+                   "f"(ysm[3 * kFastBlock] * v), "f"(ysm[4 * kFastBlock] * v) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 2), "f"(ysm[5 * kFastBlock] * v), "f"(ysm[6 * kFastBlock] * v),
+                   "f"(ysm[7 * kFastBlock] * v), "f"(ysm[8 * kFastBlock] * v) : "memory");
+      gsm[s * kFastBlock] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+  __device__ __forceinline__ void grad_flush_all()
+  {
+#pragma unroll
+    for (int s = 0; s < 8; s++) grad_flush_slot(s);
   }
   struct Basis
   {
@@ -245,6 +298,15 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   // density goes to its register slot; the colour, contracted with this ray's SH basis, to the slot's shared-memory
   // cell — the slot index is an address there, so no selects and no predicates are needed (a clean pair just rewrites
   // member 7-J with its own data)
+  template <int J> __device__ __forceinline__ void grad_window_turn(uint32_t stale, uint32_t hi, uint32_t node)
+  {
+    const bool wA = (stale >> J) & 1u, wB = ((hi & ~stale) >> J) & 1u;
+    if (wA || wB) {                                            // the slot's node really changes (a clean pair rewrites itself)
+      const int slot = wA ? J : 7 - J;
+      grad_flush_slot(slot);
+      nsm[slot * kFastBlock] = node;
+    }
+  }
   template <int J> __device__ __forceinline__ void commit_density(uint32_t stale, uint32_t hi, float td)
   {
     const bool wA = (stale >> J) & 1u, wB = ((hi & ~stale) >> J) & 1u;
@@ -253,6 +315,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   }
   template <int J> __device__ __forceinline__ void commit_pair(uint32_t stale, uint32_t hi, const NodeLoad &L, const Basis &Y)
   {
+    if (MODE == 3) grad_window_turn<J>(stale, hi, L.node);
     commit_density<J>(stale, hi, L.td);
     commit_colour<J>(stale, L, Y);
   }
@@ -314,6 +377,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   struct Sig
   {
     float tr, wgt;
+    float dens;   // interpolated density before the relu (the backward needs its sign and, as sigma, its value)
   };
   // density part of a sample (decision path, bit-exact): transmittance of the step and the compositing weight
   __device__ __forceinline__ Sig shade_sigma(const Geom &g)
@@ -333,22 +397,102 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       B[j] = lm_lerp(od[1] ? p1 : p0, od[1] ? p0 : p1, lf[1]);
     }
     float sigma = lm_lerp(od[2] ? B[1] : B[0], od[2] ? B[0] : B[1], lf[2]);
+    Sig r;
+    r.dens = sigma;
     if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
     if (MODE == 1) cauchy += logf(1.0f + 2.0f * sigma * sigma);  // :173
-    Sig r;
     r.tr = expf_libm(-sigma * g.delta, etab);                  // :175
     r.wgt = thr * (1.0f - r.tr);                               // :187
     return r;
   }
+  // interpolation weight of every window slot (the parity permutation applied to the weights instead of the values)
+  __device__ __forceinline__ void slot_weights(const Geom &g, float *w) const
+  {
+    const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
+    const float *lf = g.lf;
+    const float gx = 1.0f - lf[0], gy = 1.0f - lf[1], gz = 1.0f - lf[2];
+    const float wx0 = od[0] ? lf[0] : gx, wx1 = od[0] ? gx : lf[0];
+    const float wy0 = od[1] ? lf[1] : gy, wy1 = od[1] ? gy : lf[1];
+    const float wz0 = od[2] ? lf[2] : gz, wz1 = od[2] ? gz : lf[2];
+    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+    w[0] = w00 * wz0; w[1] = w10 * wz0; w[2] = w01 * wz0; w[3] = w11 * wz0;
+    w[4] = w00 * wz1; w[5] = w10 * wz1; w[6] = w01 * wz1; w[7] = w11 * wz1;
+  }
+  // MODE 3: the adjoint of one sample, ref RayGridLoss / RayGridIntersection differentiated by hand (the same
+  // formulas as BwdVisitor in lrf_kernels.cu, which the oracle's orc_render_grad restates on the CPU).  false = last sample.
+  __device__ __forceinline__ bool shade_backward(const Geom &g, const Sig sg)
+  {
+    const bool last = (k_done + 1 == n_total);
+    k_done++;
+    if (sg.dens < 0.0f) return !last;                          // relu closed: sigma = 0, tr = 1, weight 0 — no adjoint reaches the grid (:170-171)
+    const float sigma = sg.dens, tr = sg.tr, wgt = sg.wgt;
+    float w[8];
+    slot_weights(g, w);
+    // the colour is needed even when wgt == 0: d colour / d tr = -T_k c_k does not vanish with (1 - tr)
+    float c[3] = {1.0f, 1.0f, 1.0f}, acc[3] = {0.0f, 0.0f, 0.0f}, raw = 0.0f, s = 0.0f;
+    if (!GREY) {
+      float R = 0.0f, G = 0.0f, Bc = 0.0f, Q = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float4 cv = csm[k * kFastBlock];
+        R = fmaf(w[k], cv.x, R); G = fmaf(w[k], cv.y, G); Bc = fmaf(w[k], cv.z, Bc); Q = fmaf(w[k], cv.w, Q);
+      }
+      acc[0] = R; acc[1] = G; acc[2] = Bc;
+      raw = Q;
+      s = lm_clamp(Q, 0.0f, 1.0f);                             // :181
+      c[0] = lm_clamp(R * s, 0.0f, 1.0f); c[1] = lm_clamp(G * s, 0.0f, 1.0f); c[2] = lm_clamp(Bc * s, 0.0f, 1.0f);
+    }
+    if (wgt != 0.0f) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) csum[ch] += (double)(wgt * c[ch]);   // prefix INCLUDING this sample
+    }
+    const float dot = c[0] * aC[0] + c[1] * aC[1] + c[2] * aC[2];
+    float a_tr;
+    if (last) a_tr = -thr * dot + aTn * thr;
+    else {
+      const double suffix = (ctot[0] - csum[0]) * (double)aC[0] + (ctot[1] - csum[1]) * (double)aC[1] + (ctot[2] - csum[2]) * (double)aC[2];
+      a_tr = -thr * dot + (float)((suffix + (double)aTn * (double)Tn) / (double)tr);
+    }
+    // d tr / d sigma = -delta tr;  cauchy: d/dsigma log(1 + 2 sigma^2) = 4 sigma / (1 + 2 sigma^2), weight 0.0005 (:267)
+    const float a_dens = -g.delta * tr * a_tr + 0.0005f * (4.0f * sigma / (1.0f + 2.0f * sigma * sigma));
+    float a_rgb[3] = {0.0f, 0.0f, 0.0f}, a_raw = 0.0f;
+    if (!GREY && wgt != 0.0f) {
+      float a_s = 0.0f;
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const float a_c = wgt * aC[ch];
+        const float u = acc[ch] * s;
+        if (0.0f < u && u <= 1.0f) { a_rgb[ch] = s * a_c; a_s = fmaf(acc[ch], a_c, a_s); }   // clamp passes iff 0 < u <= 1
+      }
+      a_raw = (0.0f < raw && raw <= 1.0f) ? a_s : 0.0f;
+    }
+    if (a_dens != 0.0f) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) gdm[k * kFastBlock] = fmaf(w[k], a_dens, gdm[k * kFastBlock]);
+    }
+    if (a_raw != 0.0f || a_rgb[0] != 0.0f || a_rgb[1] != 0.0f || a_rgb[2] != 0.0f) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        float4 a = gsm[k * kFastBlock];
+        a.x = fmaf(w[k], a_rgb[0], a.x); a.y = fmaf(w[k], a_rgb[1], a.y); a.z = fmaf(w[k], a_rgb[2], a.z); a.w = fmaf(w[k], a_raw, a.w);
+        gsm[k * kFastBlock] = a;
+      }
+    }
+    thr *= tr;                                                 // :189
+    return !last;
+  }
   // colour part (1e-4-tolerance path) + the throughput update; false = the reference's throughput break fired
   __device__ __forceinline__ bool shade_colour(const Geom &g, const Sig sg)
   {
+    if (MODE == 3) return shade_backward(g, sg);
     const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
     const float *lf = g.lf;
     const float tr = sg.tr, wgt = sg.wgt;
     if (wgt != 0.0f) {
-      if (GREY) { col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt; }
-      else {
+      if (GREY) {
+        col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt;
+        if (MODE == 2) { csum[0] += (double)wgt; csum[1] += (double)wgt; csum[2] += (double)wgt; }
+      } else {
         // ---- colour: 1e-4-tolerance path, packed-pair FMAs ----
         const float gx = 1.0f - lf[0], gy = 1.0f - lf[1], gz = 1.0f - lf[2];
         const float wx0 = od[0] ? lf[0] : gx, wx1 = od[0] ? gx : lf[0];
@@ -373,9 +517,15 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
         upk2(RG0, R, G); upk2(BQ0, Bc, Q); upk2(RG1, R1, G1); upk2(BQ1, B1, Q1);
         R += R1; G += G1; Bc += B1; Q += Q1;
         const float s = lm_clamp(Q, 0.0f, 1.0f);               // :181
-        col[0] = fmaf(wgt, lm_clamp(R * s, 0.0f, 1.0f), col[0]);  // :182-187
-        col[1] = fmaf(wgt, lm_clamp(G * s, 0.0f, 1.0f), col[1]);
-        col[2] = fmaf(wgt, lm_clamp(Bc * s, 0.0f, 1.0f), col[2]);
+        if (MODE == 2) {                                       // backward pass A: the terms also go into the fp64 sums
+          const float t0 = wgt * lm_clamp(R * s, 0.0f, 1.0f), t1 = wgt * lm_clamp(G * s, 0.0f, 1.0f), t2 = wgt * lm_clamp(Bc * s, 0.0f, 1.0f);
+          col[0] = col[0] + t0; col[1] = col[1] + t1; col[2] = col[2] + t2;
+          csum[0] += (double)t0; csum[1] += (double)t1; csum[2] += (double)t2;
+        } else {
+          col[0] = fmaf(wgt, lm_clamp(R * s, 0.0f, 1.0f), col[0]);  // :182-187
+          col[1] = fmaf(wgt, lm_clamp(G * s, 0.0f, 1.0f), col[1]);
+          col[2] = fmaf(wgt, lm_clamp(Bc * s, 0.0f, 1.0f), col[2]);
+        }
       }
     }
     thr *= tr;                                                 // :189
@@ -547,6 +697,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       Basis Y;
       if (!GREY) load_basis(Y);
       commit_pair<0>(P.stale, P.hi, P.L0, Y); commit_pair<1>(P.stale, P.hi, P.L1, Y);
+      if (MODE == 3) { grad_window_turn<2>(P.stale, P.hi, P.node2); grad_window_turn<3>(P.stale, P.hi, P.node3); }
       commit_density<2>(P.stale, P.hi, P.L2.td); commit_density<3>(P.stale, P.hi, P.L3.td);
       issue_colour(P.node2, P.L2); issue_colour(P.node3, P.L3);   // in flight across the density lerps + expf chain
       const Sig sg = shade_sigma(P.g);
@@ -603,7 +754,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       const bool more = next_cell();
       if (!sample_end(P)) {
         alive = false;
-        if (MODE == 0) return;
+        if (MODE != 1) return;
       }
       if (!more) return;
     }

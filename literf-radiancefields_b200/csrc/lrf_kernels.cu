@@ -681,7 +681,11 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
   float o[3], d[3];
   if (IMAGE) {
     uint32_t px, py;
-    if (!tile_pixel(w, h, px, py)) return;
+    if (idx_list) {   // the fallback queue of grad_image_fast_kernel: pixel indices
+      const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+      if (i >= *idx_count) return;
+      px = idx_list[i] % w; py = idx_list[i] / w;
+    } else if (!tile_pixel(w, h, px, py)) return;
     ray = (size_t)py * w + px;
     gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
   } else {
@@ -721,6 +725,67 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
   bw.n_total = fa.n_shaded;
   walk(S, o, d, bw);
   bw.flush_all();
+}
+
+// Whole-image backward on the forward's machinery (lrf_fast.cuh MODE 2 / MODE 3): thread per ray, pass A = the forward with fp64
+// colour sums, pass B = the adjoint of every sample through the same incremental window, gradients accumulated per window slot
+// in shared memory and flushed with red.global.add when the slot's node changes.  Rays the streamlined march cannot take go
+// to a queue that grad_kernel<true> (generic march) works off afterwards.
+template <bool SPARSE, bool GREY>
+__global__ void __launch_bounds__(kBlock, 3) grad_image_fast_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h,
+                                                                    const float *__restrict__ ref_rgba, uint32_t *__restrict__ fb_count,
+                                                                    uint32_t *__restrict__ fb_list)
+{
+  __shared__ uint64_t etab[32];
+  __shared__ float ysm[9 * kFastBlock];
+  __shared__ float4 csm[8 * kFastBlock];
+  __shared__ float4 gsm[8 * kFastBlock];
+  __shared__ float gdm[8 * kFastBlock];
+  __shared__ uint32_t nsm[8 * kFastBlock];
+  load_exp_table(etab);
+  uint32_t px, py;
+  if (!tile_pixel(w, h, px, py)) return;
+  float o[3], d[3];
+  gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
+  if (!fast_path_ok(d)) {
+    fb_list[atomicAdd(fb_count, 1u)] = py * w + px;
+    return;
+  }
+  double ctot[3];
+  float craw[3], Tn;
+  uint32_t n_total;
+  {
+    FastMarch<2, SPARSE, GREY> fa(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
+    fa.run(o, d);
+    if (fa.n_shaded == 0) return;                              // ref :688  empty hit list: no loss term
+    n_total = fa.n_shaded;
+    Tn = fa.thr;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) { ctot[ch] = fa.csum[ch]; craw[ch] = fa.col[ch]; }
+  }
+  const float4 rp = __ldg(reinterpret_cast<const float4 *>(ref_rgba) + (size_t)py * w + px);
+  float ref[3] = {rp.x, rp.y, rp.z};
+  if (GREY) {  // ref :696-704
+    const float gsc = 0.11f * rp.z + 0.59f * rp.y + 0.3f * rp.x;
+    ref[0] = ref[1] = ref[2] = gsc;
+  }
+  FastMarch<3, SPARSE, GREY> fb(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
+  fb.gsm = gsm + threadIdx.x; fb.gdm = gdm + threadIdx.x; fb.nsm = nsm + threadIdx.x;
+  fb.grad_window_reset();
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const float cc = lm_clamp(craw[ch], 0.0f, 1.0f);           // :193
+    const float diff = cc - ref[ch];                           // :266
+    const float sg = diff < 0.0f ? -1.0f : 1.0f;
+    fb.aC[ch] = (0.0f < craw[ch] && craw[ch] <= 1.0f) ? sg : 0.0f;
+    fb.ctot[ch] = ctot[ch];
+  }
+  fb.Tn = Tn;
+  // d/dT of 0.0001f * (log(T + 1e-3) + log(1 - T + 1e-3))   (:267, double arithmetic there)
+  fb.aTn = (float)((double)0.0001f * (1.0 / ((double)Tn + 1e-3) - 1.0 / ((double)(1.0f - Tn) + 1e-3)));
+  fb.n_total = n_total;
+  fb.run(o, d);
+  fb.grad_flush_all();
 }
 
 // packed ray batch, one WARP per ray (lrf_wray.cuh)
@@ -1362,9 +1427,24 @@ void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float 
   if (n == 0) return;
   debug_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, grey, taps, force_generic);
 }
-void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st)
+void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, uint32_t *fb_count, uint32_t *fb_list,
+                       cudaStream_t st)
 {
-  grad_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, ref_rgba, grey, nullptr, nullptr);
+  if (fb_count == nullptr) {   // generic thread-per-ray kernel for every pixel (kept for comparison: option "generic_image_grad")
+    grad_kernel<true><<<tile_grid(w, h), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, ref_rgba, grey, nullptr, nullptr);
+    return;
+  }
+  cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
+  const dim3 g(tile_grid(w, h));
+  if (S.occ) {
+    if (grey) grad_image_fast_kernel<true, true><<<g, kBlock, 0, st>>>(S, w, h, ref_rgba, fb_count, fb_list);
+    else grad_image_fast_kernel<true, false><<<g, kBlock, 0, st>>>(S, w, h, ref_rgba, fb_count, fb_list);
+  } else {
+    if (grey) grad_image_fast_kernel<false, true><<<g, kBlock, 0, st>>>(S, w, h, ref_rgba, fb_count, fb_list);
+    else grad_image_fast_kernel<false, false><<<g, kBlock, 0, st>>>(S, w, h, ref_rgba, fb_count, fb_list);
+  }
+  // axis-aligned rays (at most a centre row / column): the generic march over the queue, usually an empty launch
+  grad_kernel<true><<<blocks_for((size_t)w + h + 64, kBlock), kBlock, 0, st>>>(S, w, h, 0, nullptr, nullptr, ref_rgba, grey, fb_list, fb_count);
 }
 size_t grad_rays_hit_bytes(size_t n, int gs, uint32_t *cap_out)
 {

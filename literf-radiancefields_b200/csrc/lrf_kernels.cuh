@@ -25,7 +25,9 @@ void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, con
 void launch_debug_rays(const SceneDev &S, size_t n, const float *o, const float *d, int grey, const DebugTaps &taps, int force_generic,
                        cudaStream_t st);
 // backward
-void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, cudaStream_t st);
+// fb_count / fb_list as for launch_render_image (w*h entries); fb_count == nullptr: the generic kernel for every pixel
+void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *ref_rgba, int grey, uint32_t *fb_count, uint32_t *fb_list,
+                       cudaStream_t st);
 // packed rays: warp-per-ray kernel + generic fallback over the queue (fb_count: 1 uint32, fb_list: n uint32); 2 launches
 // hit_scratch: grad_rays_hit_bytes(n, gs) bytes where pass A leaves each ray's hit list for pass B, or nullptr (pass B walks again)
 size_t grad_rays_hit_bytes(size_t n, int gs, uint32_t *cap_out);

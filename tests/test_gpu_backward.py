@@ -256,3 +256,30 @@ def test_packed_rays_backward_with_axis_aligned_and_tie_rays(pkg):
             assert_grad_close(S.grad.copy(), t.get_grad(), "mixed ray batch")
             t.close()
             S.close()
+
+
+@pytest.mark.parametrize("gs,wh,grey,sparse", [(32, 48, False, False), (32, 40, True, False), (64, 40, False, True)])
+def test_image_backward_fast_equals_generic(pkg, gs, wh, grey, sparse):
+    """the whole-image backward on the forward's incremental window (lrf_fast.cuh MODE 2/3) against the older generic
+    thread-per-ray kernel (option generic_image_grad): two independent implementations of the same adjoint"""
+    from scenes import sphere_boxes
+    grid = libs.lcg_grid(gs, 20.0)
+    ref = np.random.default_rng(gs + wh).random((wh * wh, 4)).astype(np.float32)
+    out = []
+    for generic in (0, 1):
+        t = pkg.RayMarcherExample()
+        t.InitGrid(gs)
+        t.set_grid(grid)
+        if sparse:
+            t.set_boxes(sphere_boxes(gs, 0.35))
+        t.set_option("generic_image_grad", generic)
+        t.zeroGrad()
+        for k in (1, 4, 6):
+            vi, pi = cameras(pkg, k, 7)
+            t.set_view_inv(vi)
+            t.set_proj_inv(pi)
+            t.kernel2D_RayMarchGrad(wh, wh, ref, grey)
+        out.append(t.get_grad())
+        t.close()
+    assert np.abs(out[1]).max() > 0
+    assert_grad_close(out[1], out[0], "fast vs generic image backward")

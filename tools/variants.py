@@ -88,6 +88,17 @@ def time_one(n_views):
             t._ck(t.lib.lrf_rays_grad_dev_async(t.h, n, od.ptr, dd.ptr, rf.ptr, 0))
         out["ms_backward_4096"] = t.timer_stop_ms() / 10
         out["grad_abs_sum"] = float(np.abs(t.get_grad().astype(np.float64)).sum())
+    if os.environ.get("LRF_VARIANTS_IMGGRAD"):   # whole-image backward, 800x800
+        t.zeroGrad()
+        t.targets_resize(1, bench.W, bench.H)
+        t.target_upload(0, np.random.default_rng(0).random((bench.W * bench.H, 4)).astype(np.float32))
+        t.set_view_inv(views[7])
+        t.render_grad_target_async(0); t.sync()
+        t.timer_start()
+        for _ in range(3):
+            t.render_grad_target_async(0)
+        out["ms_image_backward"] = t.timer_stop_ms() / 3
+        out["grad_abs_sum"] = float(np.abs(t.get_grad().astype(np.float64)).sum())
     print(json.dumps(out))
 
 
