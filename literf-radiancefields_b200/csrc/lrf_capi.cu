@@ -78,12 +78,13 @@ static int ensure_stage(lrf_ctx *h, size_t bytes)
   return 0;
 }
 
+constexpr size_t kFbHeader = 4;   // [0] = fallback count
 static int ensure_fb(lrf_ctx *h, size_t rays)
 {
   if (h->fb_cap >= rays) return 0;
   if (h->fb) cudaFree(h->fb);
   h->fb = nullptr; h->fb_cap = 0;
-  CK(cudaMalloc(&h->fb, (rays + 4) * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->fb, (rays + kFbHeader) * sizeof(uint32_t)));
   h->fb_cap = rays;
   return 0;
 }
@@ -344,7 +345,7 @@ int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt
   NEED_GRID(h);
   if (w == 0 || hgt == 0) return 0;
   if (ensure_fb(h, (size_t)w * hgt)) return 1;
-  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + 4, h->stream);
+  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream);
   h->launches += 2;   // render_image_kernel + render_fallback_kernel
   CK(cudaGetLastError());
   return 0;
@@ -439,7 +440,7 @@ int lrf_render_grad_dev_async(lrf_ctx *h, uint32_t w, uint32_t hgt, const float 
     h->launches++;
   } else {
     if (ensure_fb(h, (size_t)w * hgt)) return 1;
-    launch_grad_image(scene_of(h), w, hgt, ref_dev, grey, h->fb, h->fb + 4, h->stream);
+    launch_grad_image(scene_of(h), w, hgt, ref_dev, grey, h->fb, h->fb + kFbHeader, h->stream);
     h->launches += 2;   // grad_image_fast_kernel + the generic kernel over its fallback queue
   }
   CK(cudaGetLastError());
@@ -476,7 +477,7 @@ int lrf_rays_grad_dev_async(lrf_ctx *h, size_t n, const float *o, const float *d
     }
     hits = h->hit_scratch;
   }
-  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->fb, h->fb + 4, hits, h->stream);
+  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->fb, h->fb + kFbHeader, hits, h->stream);
   h->launches += 2;   // grad_rays_warp_kernel + the generic fallback over its queue
   CK(cudaGetLastError());
   return 0;

@@ -353,33 +353,52 @@ inline uint32_t tile_grid(uint32_t w, uint32_t h)
   return (tiles + (kBlock / 32) - 1) / (kBlock / 32);
 }
 
-// Forward render, one thread per pixel.  Rays that cannot take the fast path (a zero / non-finite reciprocal direction
-// component) are appended to a fallback list and rendered by render_fallback_kernel with the generic march.
 #ifndef LRF_RENDER_MINB
 #define LRF_RENDER_MINB 4   // resident blocks per SM the register allocation is sized for (tools/variants.py)
 #endif
+
+// Forward render, one thread per pixel.  Rays that cannot take the fast path (a zero / non-finite reciprocal direction
+// component) are appended to a fallback list and rendered by render_fallback_kernel with the generic march.
+//
+// Tried and dropped (profiles/r1f_variants.txt box 12): a persistent grid of 148 x 4 blocks pulling 8x4-pixel tiles in Morton
+// order from per-SM queues (%smid-affine, so that the warps sharing an L1 work on adjacent pixels; with stealing), from 8
+// queues and from one global queue, per block and per warp: 2.40-2.50 ms per view against 2.30 ms for the plain grid.  The
+// hardware's in-order block dispatch keeps the whole GPU on one compact band of the image, and that L2 locality is worth
+// more than the L1 locality or the finer load balance.
+// executed by all 32 lanes of a warp together (valid = the lane has a pixel): the sparse march votes among the lanes that run it
+template <bool SPARSE, bool GREY>
+__device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *etab, float *ysm, float4 *csm, uint32_t *__restrict__ out, uint32_t w,
+                                             uint32_t h, uint32_t px, uint32_t py, bool valid, uint32_t *__restrict__ fb_count,
+                                             uint32_t *__restrict__ fb_list)
+{
+  float o[3], d[3];
+  gen_ray(S.view_inv, S.proj_inv, valid ? px : 0u, valid ? py : 0u, w, h, o, d);
+  const bool fast = fast_path_ok(d);
+  const uint32_t mask = __ballot_sync(0xffffffffu, valid && fast);
+  if (!valid) return;
+  if (!fast) {
+    fb_list[atomicAdd(fb_count, 1u)] = py * w + px;
+    return;
+  }
+  FastMarch<0, SPARSE, GREY> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
+  fm.run(o, d, mask);
+  uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
+  if (fm.n_hit)
+    pix = pack_color(lm_clamp(fm.col[0], 0.0f, 1.0f), lm_clamp(fm.col[1], 0.0f, 1.0f), lm_clamp(fm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
+  out[(size_t)py * w + px] = pix;
+}
+
 template <bool SPARSE, bool GREY>
 __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
                                                                  uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list)
 {
   __shared__ uint64_t etab[32];
-  load_exp_table(etab);
-  uint32_t px, py;
-  if (!tile_pixel(w, h, px, py)) return;
-  float o[3], d[3];
-  gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
-  if (!fast_path_ok(d)) {
-    fb_list[atomicAdd(fb_count, 1u)] = py * w + px;
-    return;
-  }
   __shared__ float ysm[9 * kFastBlock];
   __shared__ float4 csm[8 * kFastBlock];
-  FastMarch<0, SPARSE, GREY> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
-  fm.run(o, d);
-  uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
-  if (fm.n_hit)
-    pix = pack_color(lm_clamp(fm.col[0], 0.0f, 1.0f), lm_clamp(fm.col[1], 0.0f, 1.0f), lm_clamp(fm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
-  out[(size_t)py * w + px] = pix;
+  load_exp_table(etab);
+  uint32_t px, py;
+  const bool valid = tile_pixel(w, h, px, py);
+  render_pixel<SPARSE, GREY>(S, etab, ysm, csm, out, w, h, px, py, valid, fb_count, fb_list);
 }
 
 __global__ void __launch_bounds__(kBlock) render_fallback_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h, int grey,
@@ -1398,16 +1417,6 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
 {
   cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
   const dim3 g(tile_grid(w, h));
-#ifdef LRF_CARVEOUT
-  {  // shared-memory carve-out of the unified L1 (percent): the window needs 21 KB per block, the rest is better spent as L1
-    static bool once = false;
-    if (!once) {
-      once = true;
-      cudaFuncSetAttribute(render_image_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, LRF_CARVEOUT);
-      cudaFuncSetAttribute(render_image_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, LRF_CARVEOUT);
-    }
-  }
-#endif
   if (S.occ) {
     if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
     else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
