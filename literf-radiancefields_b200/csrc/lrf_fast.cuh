@@ -561,9 +561,8 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     // ---- entry: exact fp64, once per ray (same construction as the generic march) ----
     uint32_t queue[8];
     int nq = 0;
-    int cur[3] = {0, 0, 0};
+    int cur[3];
     bool leaving_after = false;
-    bool missed = false;   // sparse render only: a lane whose ray misses the lattice still has to take part in the warp votes
     {
       const double INF = __longlong_as_double(0x7ff0000000000000LL);
       double t_enter = -INF, t_exit = INF, od[3], hd[3];
@@ -576,14 +575,10 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
         t_exit = fmin(t_exit, sgn[a] > 0 ? Tn : T0);
       }
       const double t_start = fmax(t_enter, 0.0);
-      if (!(t_exit >= t_start)) {                              // ref octree.h:483 for the whole lattice
-        if (SPARSE && MODE == 0) missed = true;
-        else return;
-      }
-      int lo[3] = {0, 0, 0}, two_mask = 0;
+      if (!(t_exit >= t_start)) return;                        // ref octree.h:483 for the whole lattice
+      int lo[3], two_mask = 0;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        if (missed) break;
         const int s = sgn[a];
         auto Tex = [&](int j) { return ((double)j * S.inv_gs - od[a]) / hd[a]; };
         int i = (int)floor((od[a] + t_start * hd[a]) * (double)S.gs);
@@ -604,8 +599,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
           cur[a] = i + s;
         }
       }
-      if (missed) {
-      } else if (two_mask == 0) {
+      if (two_mask == 0) {
         if (cell_present(S, lo[0], lo[1], lo[2])) queue[nq++] = pack_cell(lo[0], lo[1], lo[2]);
       } else {
         uint32_t cells[8];
@@ -718,12 +712,10 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       // warp-synchronously (the vote re-converges the warp after every event; without it the lanes that take a rare path —
       // an exact-compare step, a coarse-word reload — never re-merge before the search ends: ncu showed 7.8 active lanes per
       // instruction, profiles/r1k_sparse_ncu_summary.txt), and the lanes that stand on a voxel shade it in the same trip.
-      // ws_mask = the lanes of this warp that march a ray in this call (a ballot taken by the kernel at a converged point);
-      // a lane whose ray is finished keeps taking part in the votes until the whole warp is done — in the persistent kernel
-      // it is still alive and would otherwise be waited for.
-      bool done = missed;
+      // ws_mask = the lanes of this warp that march a ray in this call (a ballot taken by the kernel at a converged point).
+      // A lane whose ray is finished returns and exits the kernel: exited lanes are not waited for by the votes.
       auto search = [&]() -> int {
-        int st = done ? -1 : 0, trips = LRF_SEARCH_TRIPS;
+        int st = 0, trips = LRF_SEARCH_TRIPS;
         do {
           if (st == 0) st = step_once();
         } while (--trips > 0 && __any_sync(ws_mask, st == 0));
@@ -731,16 +723,15 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       };
       int st = search();
       for (;;) {
-        if (st < 0) done = true;
-        if (!__any_sync(ws_mask, !done)) return;
-        const bool have = !done && st > 0;
+        if (st < 0) return;
+        const bool have = st > 0;
         Pending P;
         if (have) {
           n_hit = 1;
           sample_begin(P);
         }
         st = search();                                         // on a voxel: step to the next one; searching: keep searching
-        if (have && !sample_end(P)) done = true;
+        if (have && !sample_end(P)) return;
       }
     }
 
