@@ -138,13 +138,20 @@ int lrf_adam_zero_async(lrf_ctx *h, int iter);
  * The caller orders the GPUs: a barrier between the backward and lrf_train_percell_peer_async, another one after it, then
  * lrf_zero_grad_async.  In this mode the Adam moments of rank r are current for slab r only.
  * gridSize must be a multiple of 8 * world; world <= 8. */
-/* 64-byte CUDA IPC handle of the parameter (which = 0) or gradient (1) planes, to be sent to the other ranks */
+/* 64-byte CUDA IPC handle of the parameter (which = 0) or gradient (1) planes or the barrier flags (2), to be sent to the other ranks */
 int lrf_ipc_export(lrf_ctx *h, int which, void *handle64);
 /* param_handles / grad_handles: world x 64 bytes, rank-ordered (the own rank's entry is ignored) */
 int lrf_peer_attach_ipc(lrf_ctx *h, int world, int rank, const void *param_handles, const void *grad_handles);
 /* the same for contexts living in THIS process (one per device, or several on one device in tests) */
 int lrf_peer_attach_local(lrf_ctx *h, int world, int rank, lrf_ctx *const *ctxs);
 int lrf_peer_detach(lrf_ctx *h);
+/* the barrier the exchange needs, over peer memory instead of a collective: every rank stores an epoch into every rank's flag
+ * array and waits for all slots of its own (release / acquire at system scope; ~10 us).  lrf_ipc_export(h, 2, ..) exports the
+ * flag array; lrf_peer_attach_flags_ipc maps the group's (world x 64 bytes, after lrf_peer_attach_ipc; a group attached with
+ * lrf_peer_attach_local needs no call).  A peer that never arrives trips a 2 s time-out instead of hanging the GPU. */
+int lrf_peer_attach_flags_ipc(lrf_ctx *h, const void *flag_handles);
+int lrf_peer_barrier_async(lrf_ctx *h);
+int lrf_peer_barrier_timed_out(lrf_ctx *h);
 int lrf_tv_grad_slab_async(lrf_ctx *h);              /* kernel2D_TVGrad restricted to the own slab */
 int lrf_adam_peer_async(lrf_ctx *h, int iter);       /* optimizerStep(iter) on the own slab, gradient summed over the ranks */
 int lrf_train_percell_peer_async(lrf_ctx *h, int iter);   /* the two above */

@@ -88,6 +88,9 @@ SIGNATURES = {
     "lrf_peer_attach_ipc": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "lrf_peer_attach_local": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lrf_peer_detach": (C.c_int, [_vp]),
+    "lrf_peer_attach_flags_ipc": (C.c_int, [_vp, _vp]),
+    "lrf_peer_barrier_async": (C.c_int, [_vp]),
+    "lrf_peer_barrier_timed_out": (C.c_int, [_vp]),
     "lrf_tv_grad_slab_async": (C.c_int, [_vp]),
     "lrf_adam_peer_async": (C.c_int, [_vp, C.c_int]),
     "lrf_train_percell_peer_async": (C.c_int, [_vp, C.c_int]),
@@ -441,6 +444,16 @@ class RayMarcherExample:
     def peer_attach_local(self, rank, tracers):
         arr = (_vp * len(tracers))(*[t.h for t in tracers])
         self._ck(self.lib.lrf_peer_attach_local(self.h, len(tracers), rank, arr))
+
+    def peer_attach_flags_ipc(self, flag_handles):
+        fb = b"".join(flag_handles)
+        self._ck(self.lib.lrf_peer_attach_flags_ipc(self.h, fb))
+
+    def peer_barrier_async(self):
+        self._ck(self.lib.lrf_peer_barrier_async(self.h))
+
+    def peer_barrier_timed_out(self):
+        return bool(self.lib.lrf_peer_barrier_timed_out(self.h))
 
     def peer_detach(self):
         self._ck(self.lib.lrf_peer_detach(self.h))

@@ -56,6 +56,9 @@ struct lrf_ctx
   int peer_world = 0, peer_rank = 0;
   float *peer_param[8] = {nullptr}, *peer_grad[8] = {nullptr};
   bool peer_ipc = false;              // pointers of the other ranks came from cudaIpcOpenMemHandle (must be closed)
+  uint32_t *flags = nullptr;          // own barrier flag array: [0..8) one slot per rank, [16] = time-out marker
+  uint32_t *peer_flags[8] = {nullptr};
+  uint32_t peer_epoch = 0;
 };
 
 static thread_local std::string g_err;
@@ -120,7 +123,11 @@ static void peer_detach(lrf_ctx *h)
 {
   if (h->peer_ipc)
     for (int r = 0; r < h->peer_world; r++)
-      if (r != h->peer_rank) { cudaIpcCloseMemHandle(h->peer_param[r]); cudaIpcCloseMemHandle(h->peer_grad[r]); }
+      if (r != h->peer_rank) {
+        cudaIpcCloseMemHandle(h->peer_param[r]); cudaIpcCloseMemHandle(h->peer_grad[r]);
+        if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+      }
+  for (int r = 0; r < 8; r++) h->peer_flags[r] = nullptr;
   h->peer_world = 0;
   h->peer_ipc = false;
 }
@@ -174,6 +181,8 @@ int lrf_create(int device, lrf_ctx **out)
   CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CK(cudaMalloc(&h->flags, 32 * sizeof(uint32_t)));
+  CK(cudaMemset(h->flags, 0, 32 * sizeof(uint32_t)));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   CK(cudaEventCreate(&h->tm0));
@@ -196,6 +205,7 @@ int lrf_destroy(lrf_ctx *h)
   cudaFree(h->targets);
   cudaFree(h->gamma_lut);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
+  cudaFree(h->flags);
   cudaStreamDestroy(h->side);
   cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -771,7 +781,7 @@ int lrf_ipc_export(lrf_ctx *h, int which, void *handle64)
   NEED_GRID(h);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
   cudaIpcMemHandle_t hd;
-  CK(cudaIpcGetMemHandle(&hd, which ? (void *)h->grad : (void *)h->params));
+  CK(cudaIpcGetMemHandle(&hd, which == 2 ? (void *)h->flags : which ? (void *)h->grad : (void *)h->params));
   std::memcpy(handle64, &hd, 64);
   return 0;
 }
@@ -808,12 +818,48 @@ int lrf_peer_attach_local(lrf_ctx *h, int world, int rank, lrf_ctx *const *ctxs)
       cudaGetLastError();
     }
     h->peer_param[r] = o->params; h->peer_grad[r] = o->grad;
+    h->peer_flags[r] = o->flags;
   }
   if (ctxs[rank] != h) return fail("peer group: ctxs[rank] must be this context");
   h->peer_world = world; h->peer_rank = rank; h->peer_ipc = false;
   return 0;
 }
 int lrf_peer_detach(lrf_ctx *h) { NEED(h); peer_detach(h); return 0; }
+// barrier flags of the group (after lrf_peer_attach_*): flag_handles = world x 64 bytes from lrf_ipc_export(which = 2), or
+// NULL for a group attached with lrf_peer_attach_local (ctxs give the arrays directly)
+int lrf_peer_attach_flags_ipc(lrf_ctx *h, const void *flag_handles)
+{
+  NEED(h);
+  if (h->peer_world < 1 || !h->peer_ipc) return fail("attach the group with lrf_peer_attach_ipc first");
+  for (int r = 0; r < h->peer_world; r++) {
+    if (r == h->peer_rank) { h->peer_flags[r] = h->flags; continue; }
+    cudaIpcMemHandle_t hf;
+    std::memcpy(&hf, (const char *)flag_handles + 64 * r, 64);
+    CK(cudaIpcOpenMemHandle((void **)&h->peer_flags[r], hf, cudaIpcMemLazyEnablePeerAccess));
+  }
+  return 0;
+}
+int lrf_peer_barrier_async(lrf_ctx *h)
+{
+  NEED(h);
+  if (h->peer_world < 1 || !h->peer_flags[h->peer_rank]) return fail("no barrier flags attached (lrf_peer_attach_flags_ipc / lrf_peer_attach_local)");
+  h->peer_epoch++;
+  launch_peer_barrier(h->peer_world, h->peer_rank, h->peer_flags, h->peer_epoch, h->flags + 16, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+// 1 if a barrier of this context gave up waiting for a peer (2 s) since the last call; synchronises the stream
+int lrf_peer_barrier_timed_out(lrf_ctx *h)
+{
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  uint32_t v = 0;
+  cudaMemcpy(&v, h->flags + 16, 4, cudaMemcpyDeviceToHost);
+  if (v) cudaMemset(h->flags + 16, 0, 4);
+  return v ? 1 : 0;
+}
 #define NEED_PEERS(h) do { NEED_GRID(h); if ((h)->peer_world < 1) return fail("no peer group attached (lrf_peer_attach_ipc / _local)"); } while (0)
 int lrf_tv_grad_slab_async(lrf_ctx *h)
 {

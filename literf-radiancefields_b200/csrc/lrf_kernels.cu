@@ -1214,6 +1214,37 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(const PeerSet P, float *
   }
 }
 
+// Inter-GPU barrier over peer memory for the exchange above: rank r stores the epoch into slot r of EVERY rank's flag array
+// (release, system scope) and waits until every slot of its own array has reached the epoch (acquire, system scope).  Stream
+// order makes the kernels queued before it complete first, so "all ranks passed the barrier" implies "all ranks finished what
+// they had queued before it".  ~10 us on an NVSwitch box, against ~170 us for a 1-element NCCL all-reduce at 8 GPUs.
+// A rank that never arrives (a crashed peer) trips the time-out instead of hanging the GPU: *timed_out is set and the wait ends.
+struct PeerFlags
+{
+  int world, rank;
+  uint32_t *flags[8];
+};
+__global__ void peer_barrier_kernel(const PeerFlags F, uint32_t epoch, uint32_t *timed_out)
+{
+  const int t = threadIdx.x;
+  if (t >= F.world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(F.flags[t] + F.rank), "r"(epoch) : "memory");
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(F.flags[F.rank] + t) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ULL) {   // 2 s
+      *timed_out = 1u;
+      break;
+    }
+  }
+}
+
 __global__ void fill_kernel(float *__restrict__ p, size_t count, float v)
 {
   const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -1530,6 +1561,13 @@ void launch_adam_peer(int world, int rank, float *const *grads, float *const *pa
   P.world = world; P.rank = rank;
   for (int r = 0; r < world; r++) { P.grad[r] = grads[r]; P.param[r] = params[r]; }
   adam_peer_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(P, V, S, off, count, C);
+}
+void launch_peer_barrier(int world, int rank, uint32_t *const *flags, uint32_t epoch, uint32_t *timed_out, cudaStream_t st)
+{
+  PeerFlags F{};
+  F.world = world; F.rank = rank;
+  for (int r = 0; r < world; r++) F.flags[r] = flags[r];
+  peer_barrier_kernel<<<1, 32, 0, st>>>(F, epoch, timed_out);
 }
 void launch_fill(float *p, size_t count, float v, cudaStream_t st)
 {

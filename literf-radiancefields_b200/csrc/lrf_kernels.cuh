@@ -40,6 +40,8 @@ void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float
 void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t count, float lr, float beta1, float beta2, float eps,
                  double om_b1, double om_b2, int zero_grad, cudaStream_t st);
 void launch_fill(float *p, size_t count, float v, cudaStream_t st);
+// inter-GPU barrier over peer memory: flags[r] = rank r's flag array (>= world + 1 uint32; slot [world] unused), epoch strictly increasing
+void launch_peer_barrier(int world, int rank, uint32_t *const *flags, uint32_t epoch, uint32_t *timed_out, cudaStream_t st);
 // multi-GPU: TV gradient of the nodes in z-planes [z_begin, z_end) (multiples of 8), and the Adam pass over the element range
 // [off, off+count) that sums the gradient of all ranks through peer memory and writes the parameters to every replica
 void launch_tv_grad_slab(int gs, const float *dens, float *gdens, int z_begin, int z_end, int atomic, int max_blocks, cudaStream_t st);   // gs >= 8 only; max_blocks > 0: persistent grid of that many blocks

@@ -115,3 +115,16 @@ def test_tv_beside_backward_equals_sequential(pkg):
         assert np.array_equal(ta.get_grid().view(np.uint32), tb.get_grid().view(np.uint32))
         assert not ta.get_grad().any()
     ta.close(); tb.close(); S.close()
+
+
+def test_peer_flag_barrier_two_contexts(pkg):
+    """the peer-memory barrier between two contexts on one device: both kernels must be in flight together (own streams)"""
+    ta, tb = pkg.RayMarcherExample(), pkg.RayMarcherExample()
+    ta.InitGrid(16); tb.InitGrid(16)
+    ta.peer_attach_local(0, [ta, tb])
+    tb.peer_attach_local(1, [ta, tb])
+    for _ in range(20):
+        ta.peer_barrier_async()
+        tb.peer_barrier_async()
+    assert not ta.peer_barrier_timed_out() and not tb.peer_barrier_timed_out()
+    ta.close(); tb.close()
