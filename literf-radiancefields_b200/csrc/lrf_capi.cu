@@ -147,10 +147,19 @@ static int alloc_grid(lrf_ctx *h, int gs)
   h->gs = gs;
   h->N = (size_t)gs * gs * gs;
   const size_t bytes = h->N * kCell * sizeof(float);
-  CK(cudaMalloc(&h->params, bytes));
-  CK(cudaMalloc(&h->grad, bytes));
-  CK(cudaMalloc(&h->V, bytes));
-  CK(cudaMalloc(&h->S, bytes));
+  cudaError_t e = cudaMalloc(&h->params, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->grad, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->V, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->S, bytes);
+  if (e != cudaSuccess) {   // e.g. 1024^3: 4 x 56 GB does not fit — leave the context without a grid rather than half-built
+    cudaGetLastError();
+    free_grid(h);
+    h->gs = 0;
+    h->N = 0;
+    h->n_boxes = 0;
+    return fail(std::string("cannot allocate a ") + std::to_string(gs) + "^3 grid (4 arrays of " + std::to_string(bytes >> 20) + " MB): " +
+                cudaGetErrorString(e));
+  }
   CK(cudaMemsetAsync(h->grad, 0, bytes, h->stream));
   CK(cudaMemsetAsync(h->V, 0, bytes, h->stream));
   CK(cudaMemsetAsync(h->S, 0, bytes, h->stream));

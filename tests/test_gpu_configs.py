@@ -102,3 +102,22 @@ def test_sparse512_properties(pkg):
     assert ((img == 0) == (nh_f == 0)).all()             # ref :645,660: rays with an empty hit list give pixel 0
     assert (ns_f[nh_f > 0] >= 1).all() and (ns_f <= nh_f).all()
     t.close()
+
+
+def test_grid_too_large_fails_cleanly(pkg):
+    """the largest size the API accepts (1024^3 = 4 x 56 GB) does not fit in 180 GB: an error, not a half-built context"""
+    t = pkg.RayMarcherExample()
+    with pytest.raises(pkg.LrfError):
+        t.InitGrid(1024)
+    with pytest.raises(pkg.LrfError):
+        t.kernel2D_RayMarch(np.zeros(16, np.uint32), 4, 4)     # no grid
+    with pytest.raises(pkg.LrfError):
+        t.InitGrid(48)                                          # not a power of two
+    t.InitGrid(16)                                              # still usable
+    img = np.zeros(64, np.uint32)
+    vi, pi = cameras(pkg, 0, 7)
+    t.set_view_inv(vi); t.set_proj_inv(pi)
+    t.kernel2D_RayMarch(img, 8, 8)
+    t.kernel2D_RayMarch(img, 0, 0)                              # empty frame: a no-op
+    assert img.any()
+    t.close()
