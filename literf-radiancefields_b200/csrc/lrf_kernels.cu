@@ -1013,6 +1013,25 @@ __global__ void tv_scatter_kernel(int gs, const float *__restrict__ gv, float *_
 // per tile.  Values agree with the staged kernels to rounding (lam * d / r is formed as d * (lam * rsqrt)); the TV
 // gradient is compared with the oracle to 1e-5 relative, not bit-for-bit (the reference's own sum order is a race).
 constexpr int kTvT = 8;
+// (x, y, z) of a linear index into an A^3 cube, advanced by the block's stride of 256 without divisions: ncu showed the first
+// version of tv_fused_kernel issue-bound (87 % issue slots busy) with 55 % of its instructions integer index arithmetic
+// (i % A, i / A % A, i / A^2 per element); the decomposition is now done once per thread and carried incrementally.
+template <int A> struct CubeIdx
+{
+  int x, y, z;
+  __device__ __forceinline__ explicit CubeIdx(int i) : x(i % A), y((i / A) % A), z(i / (A * A)) {}
+  __device__ __forceinline__ void step()
+  {
+    constexpr int sx = 256 % A, sy = (256 / A) % A, sz = 256 / (A * A);
+    x += sx;
+    int carry = 0;
+    if (x >= A) { x -= A; carry = 1; }
+    y += sy + carry;
+    carry = 0;
+    if (y >= A) { y -= A; carry = 1; }
+    z += sz + carry;
+  }
+};
 __global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__restrict__ dens, float *__restrict__ gdens, int bz0, int atomic,
                                                        int n_tiles)
 {
@@ -1025,15 +1044,17 @@ __global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__re
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   const int bx = tile % tiles, by = (tile / tiles) % tiles, bz = bz0 + tile / (tiles * tiles);   // bz0: first tile layer of a z-slab
   const int q0x = bx * kTvT, q0y = by * kTvT, q0z = bz * kTvT;
-  for (int i = threadIdx.x; i < 12 * 12 * 12; i += 256) {
-    const int lx = i % 12, ly = (i / 12) % 12, lz = i / 144;
+  CubeIdx<12> c12(threadIdx.x);
+  for (int i = threadIdx.x; i < 12 * 12 * 12; i += 256, c12.step()) {
+    const int lx = c12.x, ly = c12.y, lz = c12.z;
     const int x = min(max(q0x - 2 + lx, 0), m), y = min(max(q0y - 2 + ly, 0), m), z = min(max(q0z - 2 + lz, 0), m);
     sD[i] = __ldg(dens + (size_t)x + (size_t)y * gs + (size_t)z * gs * gs);
   }
   __syncthreads();
   // V_raw at local l <-> coordinate q0 - 2 + l: trilinear(0.5) over {a, min(a+1, gs-1)}^3 (getVoxel :203-230)
-  for (int i = threadIdx.x; i < 11 * 11 * 11; i += 256) {
-    const int lx = i % 11, ly = (i / 11) % 11, lz = i / 121;
+  CubeIdx<11> c11(threadIdx.x);
+  for (int i = threadIdx.x; i < 11 * 11 * 11; i += 256, c11.step()) {
+    const int lx = c11.x, ly = c11.y, lz = c11.z;
     const float *p = sD + lx + ly * 12 + lz * 144;
     const float xy00 = lm_lerp(p[0], p[1], 0.5f), xy10 = lm_lerp(p[12], p[13], 0.5f);
     const float xy01 = lm_lerp(p[144], p[145], 0.5f), xy11 = lm_lerp(p[156], p[157], 0.5f);
@@ -1042,8 +1063,9 @@ __global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__re
   __syncthreads();
   // tv cell at local l <-> coordinate q0 - 2 + l (needs V at l and l + 1): E = lam * (dx, dy, dz) / sqrt(dx^2 + dy^2 + dz^2),
   // zero where the cell does not exist (a coordinate outside [0, gs-2]) or the root's argument is 0 (sqrt'(0) := 0)
-  for (int i = threadIdx.x; i < 10 * 10 * 10; i += 256) {
-    const int lx = i % 10, ly = (i / 10) % 10, lz = i / 100;
+  CubeIdx<10> c10(threadIdx.x);
+  for (int i = threadIdx.x; i < 10 * 10 * 10; i += 256, c10.step()) {
+    const int lx = c10.x, ly = c10.y, lz = c10.z;
     const int a = q0x - 2 + lx, b = q0y - 2 + ly, c = q0z - 2 + lz;
     float ex = 0.0f, ey = 0.0f, ez = 0.0f;
     if (a >= 0 && b >= 0 && c >= 0 && a < m && b < m && c < m) {
@@ -1060,8 +1082,9 @@ __global__ void __launch_bounds__(256) tv_fused_kernel(int gs, const float *__re
   }
   __syncthreads();
   // G(p) = d(sum tv)/dV(p), p = q0 - 1 + l: + (Ex+Ey+Ez)(p) - Ex(p - ex) - Ey(p - ey) - Ez(p - ez), relu-gated (:226-227)
-  for (int i = threadIdx.x; i < 9 * 9 * 9; i += 256) {
-    const int lx = i % 9, ly = (i / 9) % 9, lz = i / 81;
+  CubeIdx<9> c9(threadIdx.x);
+  for (int i = threadIdx.x; i < 9 * 9 * 9; i += 256, c9.step()) {
+    const int lx = c9.x, ly = c9.y, lz = c9.z;
     const int e = (lx + 1) + (ly + 1) * 10 + (lz + 1) * 100;   // tv-cell index of p
     float g = sEx[e] + sEy[e] + sEz[e] - sEx[e - 1] - sEy[e - 10] - sEz[e - 100];
     if (sV[(lx + 1) + (ly + 1) * 11 + (lz + 1) * 121] < 0.0f) g = 0.0f;
