@@ -128,3 +128,18 @@ def test_peer_flag_barrier_two_contexts(pkg):
         tb.peer_barrier_async()
     assert not ta.peer_barrier_timed_out() and not tb.peer_barrier_timed_out()
     ta.close(); tb.close()
+
+
+def test_peer_exchange_ipc_two_processes():
+    """the CUDA-IPC path of the exchange under torchrun (2 ranks, one GPU each) against the NCCL all-reduce path; needs 2 GPUs"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run by hand with gpurun --gpus 2; output kept in profiles/r1h_peer_check_n2.txt)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "peer_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "peer replicas identical to rank 0: True" in r.stdout
