@@ -88,45 +88,6 @@ __device__ __forceinline__ float density_at(const SceneDev &S, const SampleGeom 
   return lm_lerp(xyz0, xyz1, g.lf[2]);
 }
 
-__device__ __forceinline__ void corner_weights(const SampleGeom &g, float *w)
-{
-  const float fx = g.lf[0], fy = g.lf[1], fz = g.lf[2];
-  const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
-  const float w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
-  w[0] = w00 * gz; w[1] = w10 * gz; w[2] = w01 * gz; w[3] = w11 * gz;
-  w[4] = w00 * fz; w[5] = w10 * fz; w[6] = w01 * fz; w[7] = w11 * fz;
-}
-
-// trilinear colour channels {R,G,B,sh0..sh8} as a weighted sum of the 8 corners (explicit FMA: this path
-// is bounded by the 1e-4 RGB tolerance, not bit-exactness)
-__device__ __forceinline__ void colour_at(const SceneDev &S, const SampleGeom &g, const float *w, float *acc /*12*/)
-{
-  const uint32_t sy = S.gs, sz = (uint32_t)S.gs * S.gs;
-#pragma unroll
-  for (int j = 0; j < 12; j++) acc[j] = 0.0f;
-#pragma unroll
-  for (int c = 0; c < 8; c++) {
-    const uint32_t idx = g.base + (c & 1) + ((c >> 1) & 1) * sy + ((c >> 2) & 1) * sz;
-    const float4 *q = S.col + (size_t)idx * kColF4;
-    const float4 a = __ldg(q), b = __ldg(q + 1), e = __ldg(q + 2);
-    acc[0] = fmaf(w[c], a.x, acc[0]); acc[1] = fmaf(w[c], a.y, acc[1]); acc[2] = fmaf(w[c], a.z, acc[2]); acc[3] = fmaf(w[c], a.w, acc[3]);
-    acc[4] = fmaf(w[c], b.x, acc[4]); acc[5] = fmaf(w[c], b.y, acc[5]); acc[6] = fmaf(w[c], b.z, acc[6]); acc[7] = fmaf(w[c], b.w, acc[7]);
-    acc[8] = fmaf(w[c], e.x, acc[8]); acc[9] = fmaf(w[c], e.y, acc[9]); acc[10] = fmaf(w[c], e.z, acc[10]); acc[11] = fmaf(w[c], e.w, acc[11]);
-  }
-}
-
-// SH dot + clamps, ref: eval_sh :108-118 and :181-184
-__device__ __forceinline__ void colour_from(const float *acc, const float *Y, float &raw, float &s, float *c)
-{
-  float sum = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 9; i++) sum = fmaf(acc[3 + i], Y[i], sum);
-  raw = sum;
-  s = lm_clamp(sum, 0.0f, 1.0f);
-#pragma unroll
-  for (int ch = 0; ch < 3; ch++) c[ch] = lm_clamp(acc[ch] * s, 0.0f, 1.0f);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Register window over the 2x2x2 nodes of the current voxel.
 //
@@ -209,14 +170,6 @@ __device__ __forceinline__ void window_weights(const SampleGeom &g, int x, int y
   const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
   w[0] = w00 * wz0; w[1] = w10 * wz0; w[2] = w01 * wz0; w[3] = w11 * wz0;
   w[4] = w00 * wz1; w[5] = w10 * wz1; w[6] = w01 * wz1; w[7] = w11 * wz1;
-}
-
-// node index held by parity slot s for voxel (x,y,z)
-__device__ __forceinline__ uint32_t window_node(const SceneDev &S, int s, int x, int y, int z)
-{
-  const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
-  const int cx = sx ? x + 1 - (x & 1) : x + (x & 1), cy = sy ? y + 1 - (y & 1) : y + (y & 1), cz = sz ? z + 1 - (z & 1) : z + (z & 1);
-  return (uint32_t)cx + (uint32_t)cy * S.gs + (uint32_t)cz * S.gs * S.gs;
 }
 
 // bring the colour part of the window to voxel (x,y,z): load the nodes whose coordinates changed, contracting the 9 SH
