@@ -66,8 +66,9 @@ constexpr int kFastBlock = 128;   // threads per block of the kernels that use F
 // cells ahead (-2 %: the first-touch DRAM misses are not what the loop waits for).  Two more, both telling: replacing the exact
 // density lerps + fp64 expf by 11 approximate instructions made the loop 7 % SLOWER (that arithmetic is what covers the second
 // gather), and a rotated schedule that issues the next cell's pairs 0,1 before this cell's shading (twice the cover on paper)
-// ran 36 % slower with the load-scoreboard stalls tripled (profiles/r1f_variants.txt boxes 8, 9).  What paid is the two-phase
-// gather below.
+// ran 36 % slower with the load-scoreboard stalls tripled (profiles/r1f_variants.txt boxes 8, 9); landing the next cell's nodes
+// in shared memory through per-thread cp.async one sample ahead (no registers in flight) ran 2.2-2.8x slower (boxes 17, 18).
+// What paid is the two-phase gather below.
 #ifndef LRF_SEARCH_TRIPS
 #define LRF_SEARCH_TRIPS 4   // sparse render: traversal events per lane between two shading slots of the warp (see run())
 #endif
