@@ -186,6 +186,7 @@ def cpu_reference_rate(grid, steps, warmup, quiet=False):
         dt = time.perf_counter() - t0
         if i >= warmup:
             rates.append(n / dt)
+    cpu_reference_rate.last_frame = out.copy()    # the sample frame itself: bench compares the GPU's render of the same frame with it
     info = {"kind": kind, "cores": int(cores),
             "sample": "%dx%d frame of orbit view 0 (%d rays) per step on the %d^3 D=%g grid, %d timed step(s); %s" % (CPU_SAMPLE, CPU_SAMPLE, n, GS, DENSITY_SCALE, steps, what)}
     return rates, info
@@ -366,6 +367,16 @@ def main():
         try:
             rates, info = cpu_reference_rate(grid, 2, 1)
             line["cpu_baseline"] = dict(info, value=float(np.mean(rates)) / 1e6, unit="Mrays/s")
+            # the same CPU_SAMPLE^2 frame through the CUDA path, compared with what the CPU code just produced (full-size grid)
+            mine = np.zeros(CPU_SAMPLE * CPU_SAMPLE, np.uint32)
+            t.set_view_inv(views[0])
+            t.kernel2D_RayMarch(mine, CPU_SAMPLE, CPU_SAMPLE)
+            theirs = cpu_reference_rate.last_frame
+            ch = lambda f: np.stack([(f >> sft) & 255 for sft in (0, 8, 16, 24)]).astype(np.int32)
+            dlt = np.abs(ch(mine) - ch(theirs))
+            line["cpu_baseline"]["frame_check"] = {"pixels": int(mine.size), "max_channel_diff_of_255": int(dlt.max()),
+                                                   "channels_differing": int((dlt != 0).sum()),
+                                                   "note": "GPU render of the sample frame vs the CPU arm's own output; RGB tolerance 1e-4 allows +-1 of 255"}
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
     sys.stdout.flush()
