@@ -163,6 +163,9 @@ void RayMarcherExample::syncToHost(bool with_grad, bool with_adam)
   }
 }
 
+void RayMarcherExample::SaveModelDat(const char *path) { must(lrf_model_save(ctx, path), "SaveModelDat"); }
+void RayMarcherExample::LoadModelDat(const char *path) { must(lrf_model_load(ctx, path), "LoadModelDat"); }
+
 // ref example_tracer.cpp:603-625: backward over the whole image, forward render, BMP of the render.  The reference
 // zeroes *loss and never computes it; so does this.
 void L1Loss(float *loss, float4 *ref, uint *gen, int width, int height, RayMarcherExample *pImpl, const char *fileName, bool greyscale)

@@ -90,6 +90,9 @@ public:
 
   // device -> host mirrors (no reference counterpart)
   void syncToHost(bool with_grad = true, bool with_adam = true);
+  // the raw model.dat dump / load that main.cpp keeps commented out (main.cpp:54-56,139-141): gridSize^3 x Cell, no header
+  void SaveModelDat(const char *path);
+  void LoadModelDat(const char *path);
 
   float4x4 m_worldViewProjInv;
   float4x4 m_worldViewInv;
