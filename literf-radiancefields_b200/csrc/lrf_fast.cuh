@@ -69,6 +69,9 @@ constexpr int kFastBlock = 128;   // threads per block of the kernels that use F
 // ran 36 % slower with the load-scoreboard stalls tripled (profiles/r1f_variants.txt boxes 8, 9); landing the next cell's nodes
 // in shared memory through per-thread cp.async one sample ahead (no registers in flight) ran 2.2-2.8x slower (boxes 17, 18).
 // What paid is the two-phase gather below.
+#ifndef LRF_GRAD_MERGE
+#define LRF_GRAD_MERGE 1     // image backward: lanes flushing the same node merge their adjoints before the reductions (0 = off; 1, 2, 4 = largest butterfly step)
+#endif
 #ifndef LRF_SEARCH_TRIPS
 #define LRF_SEARCH_TRIPS 4   // sparse render: traversal events per lane between two shading slots of the warp (see run())
 #endif
@@ -262,6 +265,53 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   __device__ __forceinline__ void grad_flush_slot(int s)
   {
     const uint32_t node = nsm[s * kFastBlock];
+#if LRF_GRAD_MERGE
+    // Neighbouring rays of a warp (pixels 0.2-0.5 voxel apart) walk the same voxel columns and reach this point with the SAME
+    // node: the lanes that flush the same node here add their 13 adjoints with shuffles and one of them issues the four
+    // reductions (the backward is bound by the L2 atomic throughput: 7.0 of its 12.6 ms remain when the red instructions are
+    // removed).  Measured (profiles/r1f_variants.txt boxes 19, 20): partner lane ^ 1 only 13.1 -> 12.2 ms; adding lane ^ 2 /
+    // lane ^ 4 costs more shuffles than it saves (12.4 / 13.0 ms); a __match_any_sync grouping with a serial shuffle loop over
+    // the peers 22 ms (the groups are large, and merging 13 values per lane is ~150 instructions per node).
+    float v[13];
+    v[0] = gdm[s * kFastBlock];
+    float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (!GREY) a = gsm[s * kFastBlock];
+    v[1] = a.x; v[2] = a.y; v[3] = a.z;
+#pragma unroll
+    for (int j = 0; j < 9; j++) v[4 + j] = GREY ? 0.0f : ysm[j * kFastBlock] * a.w;
+    gdm[s * kFastBlock] = 0.0f;
+    if (!GREY) gsm[s * kFastBlock] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    // butterfly over the x-neighbours of the warp's 8x4 pixel tile (lane ^ 1, lane ^ 2[, lane ^ 4]): when the partner flushes the
+    // same node the lower lane takes the sum and the upper one drops out
+    const uint32_t active = __activemask();
+    const int me = threadIdx.x & 31;
+    uint32_t mynode = node;
+#pragma unroll
+    for (int step = 1; step <= LRF_GRAD_MERGE; step <<= 1) {
+      const uint32_t pn = __shfl_xor_sync(active, mynode, step);
+      const bool partner_on = (active >> (me ^ step)) & 1u;
+      const bool same = partner_on && pn == mynode && mynode != 0xffffffffu;
+      const bool upper = (me & step) != 0;
+#pragma unroll
+      for (int j = 0; j < (GREY ? 1 : 13); j++) {
+        const float t = __shfl_xor_sync(active, v[j], step);
+        if (same && !upper) v[j] += t;
+      }
+      if (same && upper) mynode = 0xffffffffu;                 // handed over
+    }
+    if (mynode == 0xffffffffu) return;
+    if (v[0] != 0.0f) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(S.gdens + node), "f"(v[0]) : "memory");
+    if (GREY) return;
+    bool any = false;
+#pragma unroll
+    for (int j = 1; j < 13; j++) any = any || (v[j] != 0.0f);
+    if (any) {
+      float4 *q = S.gcol + (size_t)node * kColF4;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 1), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 2), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]) : "memory");
+    }
+#else
     const float ad = gdm[s * kFastBlock];
     if (ad != 0.0f) {
       asm volatile("red.global.add.f32 [%0], %1;" ::"l"(S.gdens + node), "f"(ad) : "memory");
@@ -279,6 +329,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
                    "f"(ysm[7 * kFastBlock] * v), "f"(ysm[8 * kFastBlock] * v) : "memory");
       gsm[s * kFastBlock] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+#endif
   }
   __device__ __forceinline__ void grad_flush_all()
   {
