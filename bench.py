@@ -369,6 +369,7 @@ def main():
             line["cpu_baseline"] = dict(info, value=float(np.mean(rates)) / 1e6, unit="Mrays/s")
             # the same CPU_SAMPLE^2 frame through the CUDA path, compared with what the CPU code just produced (full-size grid)
             mine = np.zeros(CPU_SAMPLE * CPU_SAMPLE, np.uint32)
+            t.set_grid(grid)                      # the training extra above has moved the parameters: back to the CPU arm's grid
             t.set_view_inv(views[0])
             t.kernel2D_RayMarch(mine, CPU_SAMPLE, CPU_SAMPLE)
             theirs = cpu_reference_rate.last_frame
