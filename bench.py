@@ -153,8 +153,13 @@ def cpu_reference_rate(grid, steps, warmup, quiet=False):
     n = CPU_SAMPLE * CPU_SAMPLE
     out = np.zeros(n, np.uint32)
     rates = []
+    try:
+        host_cores = len(os.sched_getaffinity(0))
+    except Exception:
+        host_cores = os.cpu_count() or 1
     if libs.have_ref("O3"):
         R = libs.ref("O3")
+        R.ref_set_omp_threads(host_cores)     # torchrun exports OMP_NUM_THREADS=1; the CPU arm runs on all the host cores it can use
         kind, cores = "reference", R.ref_omp_threads()
         h = R.ref_create()
         R.ref_init_grid(h, GS)   # builds the 255^3-box octree (~15 s, not timed: setup, like InitGrid in main.cpp)
@@ -168,6 +173,7 @@ def cpu_reference_rate(grid, steps, warmup, quiet=False):
         what = "oracle/_ref/libref_O3.so: reference example_tracer.cpp compiled -O3 -fopenmp -ffp-contract=off"
     else:
         O = libs.oracle()
+        O.orc_set_omp_threads(host_cores)
         kind, cores = "port", O.orc_omp_threads()
         h = O.orc_create(GS)
         np_view(O.orc_grid_ptr(h), GS ** 3 * 13)[:] = grid.ravel()

@@ -1036,6 +1036,7 @@ void orc_lcg_fill_grid(void *h, float D, int blob)
   }
 }
 int orc_omp_threads(void) { return omp_get_max_threads(); }
+void orc_set_omp_threads(int n) { omp_set_num_threads(n); }
 
 // ---- callers either side of the path ----
 // stbi_loadf's post-decode steps on 8-bit RGBA rows given in file order (ref external/stb_image.h:1241-1258 vertical

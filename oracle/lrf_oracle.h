@@ -90,6 +90,7 @@ uint32_t orc_pack_color(const float *rgba);
 float orc_expf_model(float x, int use_fma);            /* glibc 2.27+ expf algorithm, restated */
 void orc_lcg_fill_grid(void *h, float density_scale, int blob);  /* SURVEY 8(d) synthetic grid */
 int orc_omp_threads(void);
+void orc_set_omp_threads(int n);
 /* stbi_loadf's flip + ldr->hdr on decoded RGBA8 rows (ref external/stb_image.h:1241-1258,1856-1876; main.cpp:72,96) */
 void orc_ldr_to_hdr_rgba8(const uint8_t *rgba8, uint32_t w, uint32_t hgt, int flip, float *out);
 /* LiteImage::SaveBMP file image (ref external/LiteMath/Image2d.cpp:488-533); returns 54 + 3*w*h */

@@ -258,6 +258,7 @@ uint32_t ref_pack_color(const float *rgba) { return RealColorToUint32(float4(rgb
 float ref_expf(float x) { return exp(x); }   // whatever `exp(float)` resolves to inside the reference TU (:175)
 float ref_logf(float x) { return log(x); }   // idem for `log(float)` (:173)
 int ref_omp_threads() { return omp_get_max_threads(); }
+void ref_set_omp_threads(int n) { omp_set_num_threads(n); }   // torchrun exports OMP_NUM_THREADS=1: the CPU arm asks for the cores back
 // main.cpp:72,96: stbi_set_flip_vertically_on_load(true); stbi_loadf(path, &w, &h, &c, 4).  out (may be NULL) receives w*h*4 floats.
 int ref_stbi_loadf(const char *path, int flip, float *out, size_t cap_floats, int *w, int *hgt)
 {

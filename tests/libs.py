@@ -101,6 +101,7 @@ def oracle():
         "orc_expf_model": (C.c_float, [C.c_float, C.c_int]),
         "orc_lcg_fill_grid": (None, [vp, C.c_float, C.c_int]),
         "orc_omp_threads": (C.c_int, []),
+        "orc_set_omp_threads": (None, [C.c_int]),
         "orc_ldr_to_hdr_rgba8": (None, [vp, C.c_uint32, C.c_uint32, C.c_int, c_fp]),
         "orc_bmp_bytes": (C.c_size_t, [c_u32p, C.c_int, C.c_int, vp]),
     }
@@ -161,6 +162,7 @@ def ref(kind="O3"):
         "ref_expf": (C.c_float, [C.c_float]),
         "ref_logf": (C.c_float, [C.c_float]),
         "ref_omp_threads": (C.c_int, []),
+        "ref_set_omp_threads": (None, [C.c_int]),
         "ref_stbi_loadf": (C.c_int, [C.c_char_p, C.c_int, c_fp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "ref_save_bmp": (C.c_int, [C.c_char_p, c_u32p, C.c_int, C.c_int]),
     }
