@@ -88,6 +88,15 @@ void lrf_mat4_mul(const float a16[16], const float b16[16], float out16[16]);
 int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t width, uint32_t height, int greyscale);
 /* same, output left in DEVICE memory (out_dev), asynchronous on the context stream */
 int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t width, uint32_t height, int greyscale);
+/* The two calls above render dense colour grids of 8..512 nodes per axis with the TMA-staged kernel (lrf_staged.cuh) and
+ * everything else (greyscale, sparse box sets, tiny grids) with the thread-per-ray gather kernel; option "staged_render" = 0
+ * forces the latter.  Parity tap of the staged kernel: the frame and, per pixel, the number of samples it shaded before the
+ * reference's `throughput < 0.1` break (ref example_tracer.cpp:131) — 0xffffffff where the pixel was handed to the exact
+ * kernel (break too close to call on the approximate throughput, tie events, axis-aligned rays).  HOST arrays, may be NULL. */
+int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_host, uint32_t width, uint32_t height);
+/* counters since the last reset: [0] rays re-rendered by the exact kernel because the break was too close to call,
+ * [1] other rays sent there, [2] pixel tiles whose footprint did not fit the staged box, [3] 1 if the last render was staged */
+int lrf_render_stats(lrf_ctx *h, uint32_t out4[4], int reset);
 /* parity taps (no reference counterpart; what RayIntersectedAll + RayGridIntersection compute per
  * ray, example_tracer.cpp:641-651).  Host arrays, any may be NULL: n_hit[w*h], n_shaded[w*h],
  * rgbtc[w*h*5] = {r,g,b,T,cauchy}, vox_xyz[w*h*keep*3] first `keep` hit voxels (-1 padded). */
@@ -204,6 +213,8 @@ int lrf_timer_stop_ms(lrf_ctx *h, float *ms);
 /* device pointers of the parameter / gradient storage in DEVICE layout (density plane [gs^3] followed by
  * colour plane [gs^3 x 12]) for NCCL all-reduce by the multi-GPU harness; n_floats = 13*gs^3 */
 float *lrf_param_device_ptr(lrf_ctx *h);
+/* a caller that WRITES the parameters through that pointer (or through peer memory) says so here: derived copies are stale */
+int lrf_params_touched(lrf_ctx *h);
 float *lrf_grad_device_ptr(lrf_ctx *h);
 size_t lrf_param_count(lrf_ctx *h);
 void *lrf_stream(lrf_ctx *h);              /* cudaStream_t the context launches on */

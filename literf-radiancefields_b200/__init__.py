@@ -49,6 +49,9 @@ SIGNATURES = {
     "lrf_mat4_mul": (None, [_c_fp, _c_fp, _c_fp]),
     "lrf_render": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
+    "lrf_render_staged_debug": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
+    "lrf_render_stats": (C.c_int, [_vp, _vp, C.c_int]),
+    "lrf_params_touched": (C.c_int, [_vp]),
     "lrf_render_debug": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, _c_u32p, _c_u32p, _c_fp, _c_i32p, C.c_uint32]),
     "lrf_trace_rays": (C.c_int, [_vp, C.c_size_t, _c_fp, _c_fp, C.c_int, _c_u32p, _c_u32p, _c_fp, _c_i32p, C.c_uint32]),
     "lrf_render_grad": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_int]),
@@ -353,6 +356,22 @@ class RayMarcherExample:
 
     def render_dev_async(self, out_dev_ptr, width, height, greyscale=False):
         self._ck(self.lib.lrf_render_dev_async(self.h, out_dev_ptr, width, height, int(greyscale)))
+
+    def render_staged_debug(self, width, height):
+        """frame + per-pixel shaded-sample count of the TMA-staged kernel (0xffffffff: pixel rendered by the exact kernel)"""
+        out = np.zeros(width * height, np.uint32)
+        ns = np.zeros(width * height, np.uint32)
+        self._ck(self.lib.lrf_render_staged_debug(self.h, out.ctypes.data, ns.ctypes.data, width, height))
+        return out, ns
+
+    def render_stats(self, reset=False):
+        """[ambiguous-break rays, other rays sent to the exact kernel, tiles that did not fit the staged box, last render staged?]"""
+        st = np.zeros(4, np.uint32)
+        self._ck(self.lib.lrf_render_stats(self.h, st.ctypes.data, int(reset)))
+        return st
+
+    def params_touched(self):
+        self._ck(self.lib.lrf_params_touched(self.h))
 
     def render_debug(self, width, height, greyscale=False, keep=0):
         n = width * height

@@ -59,6 +59,17 @@ struct lrf_ctx
   uint32_t *flags = nullptr;          // own barrier flag array: [0..8) one slot per rank, [16] = time-out marker
   uint32_t *peer_flags[8] = {nullptr};
   uint32_t peer_epoch = 0;
+  // staged forward render (lrf_staged.cuh): baked 64-byte node records + what was learnt while baking
+  float4 *rec = nullptr;              // N records
+  size_t rec_N = 0;
+  bool rec_dirty = true;              // parameters changed since the last bake
+  float *dmax_dev = nullptr;          // largest |density| of the baked grid (device), and its host copy
+  float dmax = 0.0f;
+  uint32_t *st_stats = nullptr;       // 4 counters, see StagedArgs::stats
+  int staged = 1;                     // option "staged_render": 0 = the thread-per-ray gather kernel for every render
+  int staged_nw = 4;                  // option "staged_warps": consumer warps per CTA (4: 16x8 pixel tiles, 8: 16x16)
+  int staged_box_w = 0, staged_box_h = 0;   // options "staged_box_w/h": override the footprint box (0 = from the camera)
+  int last_render_staged = 0;
 };
 
 static thread_local std::string g_err;
@@ -119,6 +130,156 @@ static SceneDev scene_of(const lrf_ctx *h)
   return S;
 }
 
+
+// ---- staged forward render: records, footprint box, tensor maps (device side: lrf_staged.cuh) ----
+#ifndef LRF_ST_SWZ
+#define LRF_ST_SWZ 0
+#endif
+typedef CUresult (*lrf_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                        const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static lrf_encode_tiled_fn encode_tiled()
+{
+  // taken from the driver at run time: the library keeps no link-time dependency on libcuda (it must load on a box without a GPU)
+  static lrf_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<lrf_encode_tiled_fn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+static void params_changed(lrf_ctx *h) { h->rec_dirty = true; }
+
+// ray of a pixel centre, the arithmetic of gen_ray (lrf_device.cuh) — only used to size the footprint box, rounding is immaterial here
+static void host_gen_ray(const float *view_inv, const float *proj_inv, double x, double y, uint32_t w, uint32_t hgt, double *o, double *d)
+{
+  auto mv = [](double *res, const float *B, const double *V) {
+    for (int r = 0; r < 4; r++) res[r] = V[0] * B[r] + V[1] * B[4 + r] + V[2] * B[8 + r] + V[3] * B[12 + r];
+  };
+  const double u = (x + 0.5) / w, v = (y + 0.5) / hgt;
+  double pos[4] = {2 * u - 1, 2 * v - 1, 0, 1}, p2[4];
+  mv(p2, proj_inv, pos);
+  for (int i = 0; i < 3; i++) p2[i] /= p2[3];
+  double len = std::sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+  double rd[4] = {p2[0] / len, p2[1] / len, p2[2] / len, 0}, rp[4] = {0, 0, 0, 1}, rpt[4], rdt[4];
+  mv(rpt, view_inv, rp);
+  mv(rdt, view_inv, rd);
+  len = std::sqrt(rdt[0] * rdt[0] + rdt[1] * rdt[1] + rdt[2] * rdt[2] + rdt[3] * rdt[3]);
+  for (int i = 0; i < 3; i++) { o[i] = rpt[i]; d[i] = rdt[i] / len; }
+}
+
+// Footprint box (nodes) a tile of tw x th pixels needs on a node plane: the same corner-ray construction as the producer warp of
+// render_staged_kernel, evaluated on a 5 x 5 sample of tiles.  A tile that needs more than this sends its pixels to the exact kernel,
+// so the estimate only has to be good, not safe.
+static void staged_box_need(const lrf_ctx *h, uint32_t w, uint32_t hgt, int tw, int th, int &Wn, int &Hn)
+{
+  Wn = 4; Hn = 4;
+  const int gs = h->gs;
+  const uint32_t ntx = (w + tw - 1) / tw, nty = (hgt + th - 1) / th;
+  for (int iy = 0; iy < 5; iy++)
+    for (int ix = 0; ix < 5; ix++) {
+      const uint32_t tx = (uint32_t)((uint64_t)(ntx - 1) * ix / 4), ty = (uint32_t)((uint64_t)(nty - 1) * iy / 4);
+      const double x0 = (double)tx * tw, y0 = (double)ty * th;
+      double oc[3], dc[3];
+      host_gen_ray(h->view_inv, h->proj_inv, std::min<double>(x0 + tw / 2, w - 1), std::min<double>(y0 + th / 2, hgt - 1), w, hgt, oc, dc);
+      const double ax = std::fabs(dc[0]), ay = std::fabs(dc[1]), az = std::fabs(dc[2]);
+      const int A = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2), U = A == 0 ? 1 : 0, V = A == 2 ? 1 : 2;
+      double lo_u[2] = {1e30, 1e30}, hi_u[2] = {-1e30, -1e30}, lo_v[2] = {1e30, 1e30}, hi_v[2] = {-1e30, -1e30};
+      bool ok = true;
+      for (int c = 0; c < 4; c++) {
+        double o[3], d[3];
+        host_gen_ray(h->view_inv, h->proj_inv, std::min<double>(x0 + ((c & 1) ? tw - 1 : 0), w - 1), std::min<double>(y0 + ((c & 2) ? th - 1 : 0), hgt - 1), w,
+                     hgt, o, d);
+        if (!(std::fabs(d[A]) >= 0.25) || (d[A] > 0) != (dc[A] > 0)) { ok = false; break; }
+        const double su = d[U] / d[A], sv = d[V] / d[A], cu = o[U] * gs - o[A] * gs * su, cv = o[V] * gs - o[A] * gs * sv;
+        for (int e = 0; e < 2; e++) {
+          const double k = e ? gs - 1 : 0, fu = cu + k * su, fv = cv + k * sv;
+          lo_u[e] = std::min(lo_u[e], std::floor(fu - std::fabs(su) - 0.03125)); hi_u[e] = std::max(hi_u[e], std::floor(fu + std::fabs(su) + 0.03125) + 1);
+          lo_v[e] = std::min(lo_v[e], std::floor(fv - std::fabs(sv) - 0.03125)); hi_v[e] = std::max(hi_v[e], std::floor(fv + std::fabs(sv) + 0.03125) + 1);
+        }
+      }
+      if (!ok) continue;
+      for (int e = 0; e < 2; e++) {
+        Wn = std::max(Wn, (int)std::min(1e6, hi_u[e] - lo_u[e] + 1));
+        Hn = std::max(Hn, (int)std::min(1e6, hi_v[e] - lo_v[e] + 1));
+      }
+    }
+}
+
+// 0 = T is ready and the staged kernel can run; 1 = error (g_err set); 2 = this render is not eligible (caller uses the gather kernel)
+static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
+{
+  if (!h->dense || h->gs < 8 || h->gs > 512) return 2;   // 10-bit step counters; tiny grids gain nothing
+  lrf_encode_tiled_fn enc = encode_tiled();
+  if (!enc) return 2;
+  const int nw = h->staged_nw == 8 ? 8 : 4;
+  int Wn, Hn;
+  staged_box_need(h, w, hgt, 16, 2 * nw, Wn, Hn);
+  int W = h->staged_box_w > 0 ? h->staged_box_w : Wn + 1, H = h->staged_box_h > 0 ? h->staged_box_h : Hn + 1;
+  if (h->staged_box_w <= 0)
+    while ((W & 7) == 0 || (W & 7) == 1 || (W & 7) == 7 || (W & 7) == 4) W++;   // row pitch in records: neighbours within +-2 rows / columns land in different bank groups
+  if (W > 64 || H > 64) return 2;
+  const uint32_t plane = (uint32_t)W * H * 64u, slot = (plane + 511u) & ~511u;
+  if (1024 + 512 + 8 * (size_t)slot > 200 * 1024) return 2;
+  // records
+  if (!h->rec || h->rec_N != h->N) {
+    cudaFree(h->rec);
+    h->rec = nullptr; h->rec_N = 0;
+    if (cudaMalloc(&h->rec, h->N * 64) != cudaSuccess) { cudaGetLastError(); return 2; }   // no room for the second copy: gather kernel
+    h->rec_N = h->N;
+    h->rec_dirty = true;
+  }
+  if (!h->dmax_dev) CK(cudaMalloc(&h->dmax_dev, sizeof(float)));
+  if (!h->st_stats) { CK(cudaMalloc(&h->st_stats, 4 * sizeof(uint32_t))); CK(cudaMemsetAsync(h->st_stats, 0, 4 * sizeof(uint32_t), h->stream)); }
+  if (h->rec_dirty) {
+    launch_bake_records(scene_of(h), h->rec, h->dmax_dev, h->stream);
+    h->launches++;
+    CK(cudaMemcpyAsync(&h->dmax, h->dmax_dev, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->rec_dirty = false;
+  }
+  T.W = W; T.H = H;
+  T.plane_bytes = plane; T.slot_bytes = slot;
+  T.err_sigma = 16.0f * 0x1p-24f * h->dmax;   // NaN / inf densities make every break ambiguous: the exact kernel then renders those rays
+  T.stats = h->st_stats;
+  const cuuint64_t gs = (cuuint64_t)h->gs;
+  const cuuint64_t dims[4] = {16, gs, gs, gs}, strides[3] = {64, 64 * gs, 64 * gs * gs};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int A = 0; A < 3; A++) {
+    const cuuint32_t box[4] = {16, (cuuint32_t)(A == 0 ? 1 : W), (cuuint32_t)(A == 0 ? W : (A == 1 ? 1 : H)), (cuuint32_t)(A == 2 ? 1 : H)};
+    const CUresult r = enc(&T.tm[A], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h->rec, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           LRF_ST_SWZ ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed: CUresult " + std::to_string((int)r));
+  }
+  return 0;
+}
+static int render_dispatch(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt, int grey, uint32_t *tap_shaded)
+{
+  h->last_render_staged = 0;
+  if (h->staged && !grey) {
+    StagedArgs T;
+    const int r = staged_prepare(h, w, hgt, T);
+    if (r == 1) return 1;
+    if (r == 0) {
+      const int e = launch_render_staged(scene_of(h), T, h->staged_nw == 8 ? 8 : 4, out_dev, w, hgt, h->fb, h->fb + kFbHeader, tap_shaded, h->stream);
+      if (e) return fail(std::string("staged render: ") + cudaGetErrorString((cudaError_t)e));
+      h->launches += 2;   // render_staged_kernel + render_list_kernel
+      h->last_render_staged = 1;
+      return 0;
+    }
+  }
+  if (tap_shaded) return fail("the staged render is not available for this configuration (dense grids of 8..512 nodes per axis, colour mode)");
+  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream);
+  h->launches += 2;   // render_image_kernel + render_fallback_kernel
+  return 0;
+}
+
 static void peer_detach(lrf_ctx *h)
 {
   if (h->peer_ipc)
@@ -137,6 +298,8 @@ static void free_grid(lrf_ctx *h)
   peer_detach(h);   // the attached pointers describe replicas of the grid that is going away
   cudaFree(h->params); cudaFree(h->grad); cudaFree(h->V); cudaFree(h->S); cudaFree(h->tv_tmp);
   cudaFree(h->boxes); cudaFree(h->occ); cudaFree(h->vox2id); cudaFree(h->occ8);
+  cudaFree(h->rec);
+  h->rec = nullptr; h->rec_N = 0; h->rec_dirty = true;
   h->params = h->grad = h->V = h->S = h->tv_tmp = nullptr;
   h->boxes = nullptr; h->occ = h->vox2id = h->occ8 = nullptr;
 }
@@ -165,6 +328,7 @@ static int alloc_grid(lrf_ctx *h, int gs)
   CK(cudaMemsetAsync(h->S, 0, bytes, h->stream));
   h->dense = true;
   h->n_boxes = (size_t)(gs - 1) * (gs - 1) * (gs - 1);
+  h->rec_dirty = true;
   return 0;
 }
 
@@ -213,6 +377,8 @@ int lrf_destroy(lrf_ctx *h)
   cudaFree(h->hit_scratch);
   cudaFree(h->targets);
   cudaFree(h->gamma_lut);
+  cudaFree(h->dmax_dev);
+  cudaFree(h->st_stats);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
   cudaFree(h->flags);
   cudaStreamDestroy(h->side);
@@ -242,6 +408,7 @@ int lrf_fill_synthetic(lrf_ctx *h, float density_scale, int mode)
   NEED_GRID(h);
   if (mode < 0 || mode > 2) return fail("mode must be 0 (LCG), 1 (LCG x Gaussian blob) or 2 (sphere: positive inside r = 0.288, negative outside)");
   launch_fill_synthetic(h->gs, density_scale, mode, h->params, h->stream);
+  params_changed(h);
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -288,7 +455,12 @@ static int download13(lrf_ctx *h, const float *src_planes, float *dst_host)
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
-int lrf_grid_upload(lrf_ctx *h, const float *c) { return h ? upload13(h, h->params, c) : fail("null context"); }
+int lrf_grid_upload(lrf_ctx *h, const float *c)
+{
+  if (!h) return fail("null context");
+  params_changed(h);
+  return upload13(h, h->params, c);
+}
 int lrf_grid_download(lrf_ctx *h, float *c) { return h ? download13(h, h->params, c) : fail("null context"); }
 int lrf_grad_upload(lrf_ctx *h, const float *c) { return h ? upload13(h, h->grad, c) : fail("null context"); }
 int lrf_grad_download(lrf_ctx *h, float *c) { return h ? download13(h, h->grad, c) : fail("null context"); }
@@ -364,11 +536,45 @@ int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt
   NEED_GRID(h);
   if (w == 0 || hgt == 0) return 0;
   if (ensure_fb(h, (size_t)w * hgt)) return 1;
-  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream);
-  h->launches += 2;   // render_image_kernel + render_fallback_kernel
+  if (render_dispatch(h, out_dev, w, hgt, grey, nullptr)) return 1;
   CK(cudaGetLastError());
   return 0;
 }
+// parity tap of the staged kernel: frame + per-pixel shaded-sample counts (0xffffffff where the exact kernel rendered the pixel), host buffers
+int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_host, uint32_t w, uint32_t hgt)
+{
+  NEED_GRID(h);
+  if (w == 0 || hgt == 0) return 0;
+  const size_t bytes = (size_t)w * hgt * 4;
+  if (ensure_stage(h, 2 * bytes)) return 1;
+  if (ensure_fb(h, (size_t)w * hgt)) return 1;
+  uint32_t *frame = (uint32_t *)h->stage, *tap = frame + (size_t)w * hgt;
+  const int was = h->staged;
+  h->staged = 1;
+  const int rc = render_dispatch(h, frame, w, hgt, 0, tap);
+  h->staged = was;
+  if (rc) return 1;
+  CK(cudaGetLastError());
+  if (out_host) CK(cudaMemcpyAsync(out_host, frame, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (n_shaded_host) CK(cudaMemcpyAsync(n_shaded_host, tap, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+// counters of the staged render since the last reset: [0] rays re-rendered by the exact kernel because the throughput break was too close
+// to call, [1] other rays sent there, [2] tiles whose footprint did not fit the staged box, [3] 1 if the last render used the staged kernel
+int lrf_render_stats(lrf_ctx *h, uint32_t out[4], int reset)
+{
+  NEED(h);
+  out[0] = out[1] = out[2] = 0;
+  out[3] = (uint32_t)h->last_render_staged;
+  if (!h->st_stats) return 0;
+  CK(cudaMemcpyAsync(out, h->st_stats, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (reset) CK(cudaMemsetAsync(h->st_stats, 0, 4 * sizeof(uint32_t), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+// for callers that write the parameters through lrf_param_device_ptr / peer memory: derived copies (the render records) are stale now
+int lrf_params_touched(lrf_ctx *h) { NEED(h); params_changed(h); return 0; }
 int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t w, uint32_t hgt, int grey)
 {
   NEED_GRID(h);
@@ -717,6 +923,7 @@ static void adam_launch(lrf_ctx *h, int iter, int which, int zero, cudaStream_t 
   if (which == 1) count = h->N;                            // density plane
   else if (which == 2) { off = h->N; count = h->N * 12; }  // everything but density (i % CellSize != 0)
   launch_adam(h->params, h->grad, h->V, h->S, off, count, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, zero, st ? st : h->stream);
+  params_changed(h);
   h->launches++;
 }
 int lrf_adam_step(lrf_ctx *h, int iter, int which)
@@ -885,6 +1092,7 @@ int lrf_adam_peer_async(lrf_ctx *h, int iter)
   const double b1 = std::pow(h->beta1, iter + 1), b2 = std::pow(h->beta2, iter + 1);   // example_tracer.h:152-153 (double)
   const size_t n = (size_t)h->peer_world, r = (size_t)h->peer_rank;
   // own slab of the density plane and of the colour plane (contiguous z-slabs of both)
+  params_changed(h);   // every rank runs this pass and every replica is rewritten by it
   launch_adam_peer(h->peer_world, h->peer_rank, h->peer_grad, h->peer_param, h->V, h->S, h->N / n * r, h->N / n, h->lr, h->beta1, h->beta2, h->eps,
                    1 - b1, 1 - b2, h->stream);
   launch_adam_peer(h->peer_world, h->peer_rank, h->peer_grad, h->peer_param, h->V, h->S, h->N + h->N * 12 / n * r, h->N * 12 / n, h->lr, h->beta1,
@@ -921,6 +1129,7 @@ int lrf_upsample_grid(lrf_ctx *h)
   h->params = nullptr; h->boxes = nullptr;
   if (alloc_grid(h, old_gs * 2)) { cudaFree(old_params); cudaFree(old_boxes); return 1; }
   launch_upsample_grid(old_gs, old_params, h->params, h->stream);
+  params_changed(h);
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(old_params);
@@ -1008,7 +1217,7 @@ int lrf_timer_stop_ms(lrf_ctx *h, float *ms)
   CK(cudaEventElapsedTime(ms, h->tm0, h->tm1));
   return 0;
 }
-float *lrf_param_device_ptr(lrf_ctx *h) { return h ? h->params : nullptr; }
+float *lrf_param_device_ptr(lrf_ctx *h) { return h ? h->params : nullptr; }   // writers must call lrf_params_touched afterwards
 float *lrf_grad_device_ptr(lrf_ctx *h) { return h ? h->grad : nullptr; }
 size_t lrf_param_count(lrf_ctx *h) { return h ? h->N * kCell : 0; }
 void *lrf_stream(lrf_ctx *h) { return h ? (void *)h->stream : nullptr; }
@@ -1034,6 +1243,10 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   const std::string s(name ? name : "");
   if (s == "force_generic_march") h->force_generic = value ? 1 : 0;
   else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
+  else if (s == "staged_render") h->staged = value ? 1 : 0;
+  else if (s == "staged_warps") { if (value != 4 && value != 8) return fail("staged_warps must be 4 or 8"); h->staged_nw = value; }
+  else if (s == "staged_box_w") h->staged_box_w = value;
+  else if (s == "staged_box_h") h->staged_box_h = value;
   else return fail("unknown option: " + s);
   return 0;
 }

@@ -11,6 +11,7 @@
 #include "lrf_kernels.cuh"
 #include "lrf_fast.cuh"
 #include "lrf_wray.cuh"
+#include "lrf_staged.cuh"
 
 namespace lrf {
 
@@ -370,6 +371,35 @@ __global__ void __launch_bounds__(kBlock) render_fallback_kernel(const __grid_co
     uint32_t pix = 0;
     if (vis.n_hit)
       pix = pack_color(lm_clamp(vis.col[0], 0.0f, 1.0f), lm_clamp(vis.col[1], 0.0f, 1.0f), lm_clamp(vis.col[2], 0.0f, 1.0f), 1.0f);
+    out[pixel] = pix;
+  }
+}
+
+// Exact render of the rays the staged kernel (lrf_staged.cuh) did not decide: the streamlined exact march where it applies, the
+// generic fp64 march for the rest (axis-aligned rays).  Dense sets only.
+__global__ void __launch_bounds__(kBlock) render_list_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
+                                                             const uint32_t *__restrict__ fb_count, const uint32_t *__restrict__ fb_list)
+{
+  __shared__ uint64_t etab[32];
+  __shared__ float ysm[9 * kFastBlock];
+  __shared__ float4 csm[8 * kFastBlock];
+  load_exp_table(etab);
+  const uint32_t n = *fb_count;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const uint32_t pixel = fb_list[i], px = pixel % w, py = pixel / w;
+    float o[3], d[3];
+    gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
+    uint32_t pix = 0;
+    if (fast_path_ok(d)) {
+      FastMarch<0, false, false> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
+      fm.run(o, d);
+      if (fm.n_hit) pix = pack_color(lm_clamp(fm.col[0], 0.0f, 1.0f), lm_clamp(fm.col[1], 0.0f, 1.0f), lm_clamp(fm.col[2], 0.0f, 1.0f), 1.0f);
+    } else {
+      ShadeVisitor<0> vis(S, etab, false);
+      ray_ctx_init(vis.R, o, d, false);
+      march(S, o, d, vis);
+      if (vis.n_hit) pix = pack_color(lm_clamp(vis.col[0], 0.0f, 1.0f), lm_clamp(vis.col[1], 0.0f, 1.0f), lm_clamp(vis.col[2], 0.0f, 1.0f), 1.0f);
+    }
     out[pixel] = pix;
   }
 }
@@ -1440,6 +1470,32 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
     else render_image_kernel<false, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
   }
   render_fallback_kernel<<<148, kBlock, 0, st>>>(S, out_dev, w, h, grey, fb_count, fb_list);
+}
+void launch_bake_records(const SceneDev &S, float4 *rec, float *max_abs_density, cudaStream_t st)
+{
+  const size_t N = (size_t)S.gs * S.gs * S.gs;
+  cudaMemsetAsync(max_abs_density, 0, sizeof(float), st);
+  bake_records_kernel<<<148 * 8, 256, 0, st>>>(S.dens, S.col, rec, N, max_abs_density);
+}
+size_t staged_smem_bytes(const StagedArgs &T) { return 1024 + kStCtl + (size_t)kStR * T.slot_bytes; }
+int launch_render_staged(const SceneDev &S, const StagedArgs &T, int nw, uint32_t *out_dev, uint32_t w, uint32_t h, uint32_t *fb_count,
+                         uint32_t *fb_list, uint32_t *tap_shaded, cudaStream_t st)
+{
+  const size_t smem = staged_smem_bytes(T);
+  cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
+  const uint32_t tiles_x = (w + 15) / 16;
+  cudaError_t e;
+  if (nw == 8) {
+    e = cudaFuncSetAttribute(render_staged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    render_staged_kernel<8><<<tiles_x * ((h + 15) / 16), 9 * 32, smem, st>>>(S, T, out_dev, w, h, fb_count, fb_list, tap_shaded);
+  } else {
+    e = cudaFuncSetAttribute(render_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    render_staged_kernel<4><<<tiles_x * ((h + 7) / 8), 5 * 32, smem, st>>>(S, T, out_dev, w, h, fb_count, fb_list, tap_shaded);
+  }
+  render_list_kernel<<<148 * 2, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+  return 0;
 }
 void launch_debug_image(const SceneDev &S, uint32_t w, uint32_t h, int grey, const DebugTaps &taps, int force_generic, cudaStream_t st)
 {

@@ -1,6 +1,7 @@
 // lrf_kernels.cuh — launch interface between the C-ABI layer (lrf_capi.cu) and the sm_100a
 // kernels (lrf_kernels.cu).  Plain pointers and sizes only.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "lrf_device.cuh"
@@ -16,6 +17,26 @@ struct DebugTaps  // device pointers, any may be null
   uint32_t keep;
   uint8_t *touched;  // [gs^3] node-read marks (lrf_count_touched_nodes)
 };
+
+
+// staged forward render (lrf_staged.cuh): launch description built by the C-ABI layer
+struct alignas(64) StagedArgs
+{
+  CUtensorMap tm[3];        // by march axis A: box {16, 1, W, H} / {16, W, 1, H} / {16, W, H, 1} over {16 floats, x, y, z}
+  int W, H;                 // footprint box in nodes: W along the first lateral axis in memory order, H along the second
+  uint32_t plane_bytes;     // W * H * 64 (what one TMA delivers)
+  uint32_t slot_bytes;      // ring slot stride, plane_bytes rounded up to kStSlotAlign
+  float err_sigma;          // bound on |weight-form density - reference nested-lerp density|: 16 ulp of the largest |density| in the grid
+  uint32_t *stats;          // [0] rays sent to the exact kernel because the break was ambiguous, [1] other rays sent there (ties, entry on a
+                            // plane, axis-aligned / unfit lanes), [2] CTAs whose footprint did not fit the box
+};
+
+// forward, staged: bake the 64-byte node records from the planes; render through the TMA-staged kernel (nw = 4 or 8 consumer warps per
+// CTA) followed by the exact kernel over the fallback list; tap_shaded optional (w*h uint32)
+void launch_bake_records(const SceneDev &S, float4 *rec, float *max_abs_density, cudaStream_t st);
+size_t staged_smem_bytes(const StagedArgs &T);
+int launch_render_staged(const SceneDev &S, const StagedArgs &T, int nw, uint32_t *out_dev, uint32_t w, uint32_t h, uint32_t *fb_count,
+                         uint32_t *fb_list, uint32_t *tap_shaded, cudaStream_t st);   // returns 0, or a cudaError_t from the attribute call
 
 // forward
 // fb_count (1 uint32) / fb_list (w*h uint32): fallback queue for rays that need the generic march; 2 kernel launches

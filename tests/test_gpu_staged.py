@@ -1,0 +1,130 @@
+"""GPU parity of the TMA-staged forward kernel (lrf_staged.cuh; ref kernel2D_RayMarch example_tracer.cpp:627-663).
+
+The staged kernel decides the reference's `throughput < 0.1` break (ref :131) on an approximate throughput with an error band and
+hands every ray it cannot decide to the exact kernel.  So the bar is: for every pixel it DID decide, the shaded-sample count equals
+the oracle's bit for bit; every pixel of the finished frame (both kernels together) is the oracle's up to the 1e-4 colour
+tolerance (<= 1 LSB after the reference's (uint)(c*255) truncation); the undecided fraction stays small."""
+import numpy as np
+import pytest
+
+import libs
+from scenes import OracleScene, cameras
+
+pytestmark = pytest.mark.gpu
+
+UNDECIDED = 0xFFFFFFFF
+
+
+def _channels(img):
+    return np.stack([(img >> s) & 255 for s in (0, 8, 16, 24)]).astype(np.int32)
+
+
+def _check(t, S, w, h, max_exact_frac):
+    nh_o, ns_o, rg_o, _ = S.render_debug(w, h, False, 0)
+    img_o = S.render(w, h, False)
+    t.render_stats(reset=True)
+    img_g, ns_g = t.render_staged_debug(w, h)
+    st = t.render_stats()
+    assert st[3] == 1, "the staged kernel did not run"
+    assert st[2] == 0, "%d tiles did not fit the staged footprint box" % st[2]
+    dec = ns_g != UNDECIDED
+    assert np.array_equal(ns_g[dec], ns_o[dec]), "shaded counts differ on %d decided rays" % (ns_g[dec] != ns_o[dec]).sum()
+    assert (~dec).sum() == st[0] + st[1]
+    assert (~dec).mean() <= max_exact_frac, "%.3f of the rays went to the exact kernel" % (~dec).mean()
+    ch_o, ch_g = _channels(img_o), _channels(img_g)
+    assert np.abs(ch_o - ch_g).max() <= 1
+    assert np.array_equal(ch_o[3], ch_g[3])           # alpha: 255 on rays with a hit, 0 otherwise
+    assert (ch_o != ch_g).mean() < 2e-3
+    assert np.array_equal(img_g == 0, nh_o == 0) or np.array_equal((img_g >> 24) == 0, nh_o == 0)
+    return st
+
+
+@pytest.mark.parametrize("gs,D,wh", [(16, 20.0, 96), (32, 20.0, 96), (32, 2.0, 64), (64, 20.0, 64), (128, 20.0, 48)])
+def test_staged_against_oracle(pkg, gs, D, wh):
+    grid = libs.lcg_grid(gs, D)
+    S = OracleScene(gs, grid)
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.SetBoundingBox([0, 0, 0], [1, 1, 1])
+    t.set_grid(grid)
+    for k in range(7):
+        vi, pi = cameras(pkg, k, 7)
+        S.set_cam(vi, pi)
+        t.set_view_inv(vi)
+        t.set_proj_inv(pi)
+        _check(t, S, wh, wh, 0.10)
+    t.close()
+    S.close()
+
+
+def test_staged_ragged_wide_and_16x16_tiles(pkg):
+    gs = 32
+    grid = libs.lcg_grid(gs, 20.0)
+    S = OracleScene(gs, grid)
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.set_grid(grid)
+    for nw in (4, 8):
+        t.set_option("staged_warps", nw)
+        for k, (w, h, aspect) in enumerate([(33, 17, 1.0), (160, 90, 16.0 / 9.0), (1, 1, 1.0), (50, 7, 1.0)]):
+            vi, pi = cameras(pkg, 2 * k + 1, 9, aspect=aspect)
+            S.set_cam(vi, pi)
+            t.set_view_inv(vi)
+            t.set_proj_inv(pi)
+            _check(t, S, w, h, 1.0 if w * h < 64 else 0.15)
+    t.close()
+    S.close()
+
+
+def test_staged_records_follow_the_parameters(pkg):
+    """the render reads a baked copy of the grid: it has to be rebuilt after every call that changes the parameters"""
+    gs = 16
+    S = OracleScene(gs, libs.lcg_grid(gs, 20.0))
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.set_grid(S.grid.copy())
+    vi, pi = cameras(pkg, 3, 7)
+    S.set_cam(vi, pi)
+    t.set_view_inv(vi)
+    t.set_proj_inv(pi)
+    _check(t, S, 64, 64, 0.15)
+    S.grid[:] = libs.lcg_grid(gs, 5.0)             # upload
+    t.set_grid(S.grid.copy())
+    _check(t, S, 64, 64, 0.15)
+    g = (np.random.default_rng(5).standard_normal(S.grid.shape) * 0.05).astype(np.float32)
+    t.optimizerInit(); S.O.orc_adam_init(S.h)      # one Adam step on both sides
+    t.set_grad(g); S.grad[:] = g
+    t.optimizerStep(0); S.O.orc_adam_step(S.h, 0, 0)
+    _check(t, S, 64, 64, 0.15)
+    t.UpsampleGrid(); S.O.orc_upsample_grid(S.h)   # level transition
+    _check(t, S, 64, 64, 0.15)
+    t.close()
+    S.close()
+
+
+def test_staged_equals_gather_kernel_at_256(pkg):
+    """bench size: both forward kernels on the same 256^3 grid and camera (the gather kernel is the one pinned bit-exactly against
+    the oracle and the compiled reference at every size the oracle can run)"""
+    gs, w, h = 256, 400, 400
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.fill_synthetic(20.0, 0)
+    for k in (0, 13, 37):
+        vi = pkg.inverse4x4(pkg.orbit_view(k, 100))
+        t.set_view_inv(vi)
+        t.set_proj_inv(pkg.inverse4x4(pkg.perspective(45.0, 1.0, 0.1, 100.0)))
+        t.set_option("staged_render", 0)
+        ref = np.zeros(w * h, np.uint32)
+        t.kernel2D_RayMarch(ref, w, h)
+        _, ns_e, _, _ = t.render_debug(w, h, False, 0)
+        t.set_option("staged_render", 1)
+        t.render_stats(reset=True)
+        img, ns = t.render_staged_debug(w, h)
+        st = t.render_stats()
+        assert st[3] == 1 and st[2] == 0
+        dec = ns != UNDECIDED
+        assert np.array_equal(ns[dec], ns_e[dec])
+        assert (~dec).mean() < 0.05
+        d = np.abs(_channels(ref) - _channels(img))
+        assert d.max() <= 1 and (d != 0).mean() < 2e-3
+    t.close()
