@@ -70,6 +70,7 @@ struct lrf_ctx
   int staged_nw = 4;                  // option "staged_warps": consumer warps per CTA (4: 16x8 pixel tiles, 8: 16x16)
   int staged_box_w = 0, staged_box_h = 0;   // options "staged_box_w/h": override the footprint box (0 = from the camera)
   int last_render_staged = 0;
+  uint32_t *diag_host = nullptr, *diag_dev = nullptr;   // watchdog record of the staged kernel (host-mapped pinned memory)
 };
 
 static thread_local std::string g_err;
@@ -154,6 +155,20 @@ static lrf_encode_tiled_fn encode_tiled()
 }
 
 static void params_changed(lrf_ctx *h) { h->rec_dirty = true; }
+static int sync_with_diag(lrf_ctx *h)
+{
+  const cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) return 0;
+  std::string m = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+  if (h->diag_host && h->diag_host[0]) {
+    const uint32_t *d = h->diag_host;
+    const char *what = d[0] == 1 ? "producer: ring never freed (q, qmin, p0)" : d[0] == 2 ? "producer: drain (plane, issued, parity)"
+                       : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : "?";
+    m += " | staged-render watchdog: " + std::string(what) + " block " + std::to_string(d[1]) + " thread " + std::to_string(d[2]) + " values " +
+         std::to_string((int)d[3]) + " " + std::to_string((int)d[4]) + " " + std::to_string((int)d[5]);
+  }
+  return fail(m);
+}
 
 // ray of a pixel centre, the arithmetic of gen_ray (lrf_device.cuh) — only used to size the footprint box, rounding is immaterial here
 static void host_gen_ray(const float *view_inv, const float *proj_inv, double x, double y, uint32_t w, uint32_t hgt, double *o, double *d)
@@ -247,6 +262,12 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
   T.plane_bytes = plane; T.slot_bytes = slot;
   T.err_sigma = 16.0f * 0x1p-24f * h->dmax;   // NaN / inf densities make every break ambiguous: the exact kernel then renders those rays
   T.stats = h->st_stats;
+  if (!h->diag_host) {
+    CK(cudaHostAlloc((void **)&h->diag_host, 16 * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(h->diag_host, 0, 16 * sizeof(uint32_t));
+    CK(cudaHostGetDevicePointer((void **)&h->diag_dev, h->diag_host, 0));
+  }
+  T.diag = h->diag_dev;
   const cuuint64_t gs = (cuuint64_t)h->gs;
   const cuuint64_t dims[4] = {16, gs, gs, gs}, strides[3] = {64, 64 * gs, 64 * gs * gs};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -379,6 +400,7 @@ int lrf_destroy(lrf_ctx *h)
   cudaFree(h->gamma_lut);
   cudaFree(h->dmax_dev);
   cudaFree(h->st_stats);
+  if (h->diag_host) cudaFreeHost(h->diag_host);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->tm0); cudaEventDestroy(h->tm1);
   cudaFree(h->flags);
   cudaStreamDestroy(h->side);
@@ -388,7 +410,7 @@ int lrf_destroy(lrf_ctx *h)
   return 0;
 }
 
-int lrf_sync(lrf_ctx *h) { NEED(h); CK(cudaStreamSynchronize(h->stream)); return 0; }
+int lrf_sync(lrf_ctx *h) { NEED(h); return sync_with_diag(h); }
 
 int lrf_init_grid(lrf_ctx *h, int gs)
 {
@@ -557,8 +579,7 @@ int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_h
   CK(cudaGetLastError());
   if (out_host) CK(cudaMemcpyAsync(out_host, frame, bytes, cudaMemcpyDeviceToHost, h->stream));
   if (n_shaded_host) CK(cudaMemcpyAsync(n_shaded_host, tap, bytes, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return sync_with_diag(h);
 }
 // counters of the staged render since the last reset: [0] rays re-rendered by the exact kernel because the throughput break was too close
 // to call, [1] other rays sent there, [2] tiles whose footprint did not fit the staged box, [3] 1 if the last render used the staged kernel
@@ -585,7 +606,7 @@ int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t w, uint32_t hgt, int gre
   if (lrf_render_dev_async(h, (uint32_t *)h->stage, w, hgt, grey)) return 1;
   cudaEventRecord(h->ev1, h->stream);
   CK(cudaMemcpyAsync(out_host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  if (sync_with_diag(h)) return 1;
   cudaEventElapsedTime(&h->t_march, h->ev0, h->ev1);
   return 0;
 }

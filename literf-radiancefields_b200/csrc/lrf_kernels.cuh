@@ -27,6 +27,7 @@ struct alignas(64) StagedArgs
   uint32_t plane_bytes;     // W * H * 64 (what one TMA delivers)
   uint32_t slot_bytes;      // ring slot stride, plane_bytes rounded up to kStSlotAlign
   float err_sigma;          // bound on |weight-form density - reference nested-lerp density|: 16 ulp of the largest |density| in the grid
+  uint32_t *diag;           // host-mapped: watchdog record {code, block, thread, a, b, c} written before a stuck wait traps the kernel
   uint32_t *stats;          // [0] rays sent to the exact kernel because the break was ambiguous, [1] other rays sent there (ties, entry on a
                             // plane, axis-aligned / unfit lanes), [2] CTAs whose footprint did not fit the box
 };

@@ -68,15 +68,31 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)   // no
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)   // blocking (try_wait suspends the warp in hardware)
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)   // suspends the warp in hardware for a bounded time
 {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "LRF_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra LRF_DONE_%=;\n\t"
-      "bra LRF_WAIT_%=;\n\t"
-      "LRF_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Watchdog: a wait that lasts longer than ~2 s is a protocol bug or a lost TMA, never a slow one.  The lane leaves a record in
+// host-mapped memory (it survives the trap) and kills the kernel instead of hanging the GPU.
+constexpr long long kStWatchdogCycles = 4000000000LL;
+__device__ __noinline__ void staged_die(uint32_t *diag, uint32_t code, uint32_t a, uint32_t b, uint32_t c)
+{
+  if (diag) {
+    if (atomicCAS(diag, 0u, code) == 0u) {
+      diag[1] = blockIdx.x; diag[2] = threadIdx.x; diag[3] = a; diag[4] = b; diag[5] = c;
+      __threadfence_system();
+    }
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t *diag, uint32_t code, uint32_t a, uint32_t b)
+{
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > kStWatchdogCycles) staged_die(diag, code, a, b, parity);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3)
 {
@@ -269,6 +285,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
     int q = 0, qmin = 0;
     for (; q < q_end; q++) {
       // ring flow control: slot (q & R-1) is free once every consumer lane has left plane q - R behind
+      long long t0 = 0;
       while (q >= qmin + kStR) {
         int m = kStDone;
 #pragma unroll
@@ -276,6 +293,8 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
         qmin = m;
         if (qmin == kStDone || q < qmin + kStR) break;
         __nanosleep(64);
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > kStWatchdogCycles) staged_die(T.diag, 1u, (uint32_t)q, (uint32_t)qmin, (uint32_t)p0);
       }
       if (qmin == kStDone) break;
       const int p = p0 + q, k = a_pos ? p : gs - 1 - p, slot = q & (kStR - 1);
@@ -293,7 +312,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
       __syncwarp();
     }
     // no TMA may be in flight into this CTA's shared memory when the CTA retires: wait for the last min(q, R) planes issued
-    for (int j = max(0, q - kStR); j < q; j++) mbar_wait(a_full + 8 * (j & (kStR - 1)), (uint32_t)(j / kStR) & 1u);
+    for (int j = max(0, q - kStR); j < q; j++) mbar_wait(a_full + 8 * (j & (kStR - 1)), (uint32_t)(j / kStR) & 1u, T.diag, 2u, (uint32_t)j, (uint32_t)q);
     return;
   }
 
@@ -402,7 +421,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
     }
     const bool can = alive && (qe + 3 <= qready);
     if (!__any_sync(FULL, can)) {
-      mbar_wait(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u);
+      mbar_wait(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u, T.diag, 3u, (uint32_t)qready, (uint32_t)qmin);
       qready++;
       continue;
     }
