@@ -15,6 +15,7 @@ FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",   # IEEE fp32, no contraction: parity with the reference's x86 build
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-Xptxas", "-v",
+] + [("-D" + d) for d in os.environ.get("LRF_DEFINES", "").split() if d] + [
 ]
 
 

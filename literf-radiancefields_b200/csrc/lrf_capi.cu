@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -155,19 +156,29 @@ static lrf_encode_tiled_fn encode_tiled()
 }
 
 static void params_changed(lrf_ctx *h) { h->rec_dirty = true; }
-static int sync_with_diag(lrf_ctx *h)
+static int fail_with_diag(lrf_ctx *h, const char *what_call, cudaError_t e)
 {
-  const cudaError_t e = cudaStreamSynchronize(h->stream);
-  if (e == cudaSuccess) return 0;
-  std::string m = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+  std::string m = std::string(what_call) + ": " + cudaGetErrorString(e);
   if (h->diag_host && h->diag_host[0]) {
     const uint32_t *d = h->diag_host;
     const char *what = d[0] == 1 ? "producer: ring never freed (q, qmin, p0)" : d[0] == 2 ? "producer: drain (plane, issued, parity)"
-                       : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : "?";
+                       : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : d[0] == 4 ? "producer: own TMA never completed (q, k, parity)" : "?";
     m += " | staged-render watchdog: " + std::string(what) + " block " + std::to_string(d[1]) + " thread " + std::to_string(d[2]) + " values " +
          std::to_string((int)d[3]) + " " + std::to_string((int)d[4]) + " " + std::to_string((int)d[5]);
+    m += " | dump:";
+    for (int i = 8; i < 96; i++) m += " " + std::to_string((int)d[i]);
   }
   return fail(m);
+}
+#define CKD(h, call)                                                  \
+  do {                                                                \
+    cudaError_t e_ = (call);                                          \
+    if (e_ != cudaSuccess) return fail_with_diag(h, #call, e_);       \
+  } while (0)
+static int sync_with_diag(lrf_ctx *h)
+{
+  CKD(h, cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 // ray of a pixel centre, the arithmetic of gen_ray (lrf_device.cuh) — only used to size the footprint box, rounding is immaterial here
@@ -238,6 +249,7 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
   int W = h->staged_box_w > 0 ? h->staged_box_w : Wn + 1, H = h->staged_box_h > 0 ? h->staged_box_h : Hn + 1;
   if (h->staged_box_w <= 0)
     while ((W & 7) == 0 || (W & 7) == 1 || (W & 7) == 7 || (W & 7) == 4) W++;   // row pitch in records: neighbours within +-2 rows / columns land in different bank groups
+  if (std::getenv("LRF_DEBUG")) std::fprintf(stderr, "[lrf] staged box: need %d x %d -> W %d H %d (nw %d, %ux%u)\n", Wn, Hn, W, H, nw, w, hgt);
   if (W > 64 || H > 64) return 2;
   const uint32_t plane = (uint32_t)W * H * 64u, slot = (plane + 511u) & ~511u;
   if (1024 + 512 + 8 * (size_t)slot > 200 * 1024) return 2;
@@ -263,8 +275,8 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
   T.err_sigma = 16.0f * 0x1p-24f * h->dmax;   // NaN / inf densities make every break ambiguous: the exact kernel then renders those rays
   T.stats = h->st_stats;
   if (!h->diag_host) {
-    CK(cudaHostAlloc((void **)&h->diag_host, 16 * sizeof(uint32_t), cudaHostAllocMapped));
-    std::memset(h->diag_host, 0, 16 * sizeof(uint32_t));
+    CK(cudaHostAlloc((void **)&h->diag_host, 128 * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(h->diag_host, 0, 128 * sizeof(uint32_t));
     CK(cudaHostGetDevicePointer((void **)&h->diag_dev, h->diag_host, 0));
   }
   T.diag = h->diag_dev;
@@ -577,8 +589,8 @@ int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_h
   h->staged = was;
   if (rc) return 1;
   CK(cudaGetLastError());
-  if (out_host) CK(cudaMemcpyAsync(out_host, frame, bytes, cudaMemcpyDeviceToHost, h->stream));
-  if (n_shaded_host) CK(cudaMemcpyAsync(n_shaded_host, tap, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (out_host) CKD(h, cudaMemcpyAsync(out_host, frame, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (n_shaded_host) CKD(h, cudaMemcpyAsync(n_shaded_host, tap, bytes, cudaMemcpyDeviceToHost, h->stream));
   return sync_with_diag(h);
 }
 // counters of the staged render since the last reset: [0] rays re-rendered by the exact kernel because the throughput break was too close
@@ -605,7 +617,7 @@ int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t w, uint32_t hgt, int gre
   cudaEventRecord(h->ev0, h->stream);
   if (lrf_render_dev_async(h, (uint32_t *)h->stage, w, hgt, grey)) return 1;
   cudaEventRecord(h->ev1, h->stream);
-  CK(cudaMemcpyAsync(out_host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CKD(h, cudaMemcpyAsync(out_host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
   if (sync_with_diag(h)) return 1;
   cudaEventElapsedTime(&h->t_march, h->ev0, h->ev1);
   return 0;
@@ -1234,7 +1246,7 @@ int lrf_timer_stop_ms(lrf_ctx *h, float *ms)
 {
   NEED(h);
   CK(cudaEventRecord(h->tm1, h->stream));
-  CK(cudaEventSynchronize(h->tm1));
+  CKD(h, cudaEventSynchronize(h->tm1));
   CK(cudaEventElapsedTime(ms, h->tm0, h->tm1));
   return 0;
 }

@@ -36,6 +36,12 @@
 #ifndef LRF_ST_SWZ
 #define LRF_ST_SWZ 0          // 1: CU_TENSOR_MAP_SWIZZLE_64B on the staged planes (records 2 apart in a row stop sharing banks)
 #endif
+#ifndef LRF_ST_DEBUG
+#define LRF_ST_DEBUG 0        // 1: every consumer warp leaves its ring state in shared memory; the producer's watchdog copies it out
+#endif
+#ifndef LRF_ST_INFLIGHT
+#define LRF_ST_INFLIGHT 8     // planes the producer keeps in flight (<= ring size)
+#endif
 #ifndef LRF_ST_MINB
 #define LRF_ST_MINB 3         // resident CTAs per SM the register allocation is sized for
 #endif
@@ -89,10 +95,12 @@ __device__ __noinline__ void staged_die(uint32_t *diag, uint32_t code, uint32_t 
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t *diag, uint32_t code, uint32_t a, uint32_t b)
 {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity))
-    if (clock64() - t0 > kStWatchdogCycles) staged_die(diag, code, a, b, parity);
+  if (!mbar_try(bar, parity)) {
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+      if (clock64() - t0 > kStWatchdogCycles) staged_die(diag, code, a, b, parity);
+  }
+  __syncwarp();   // callers are warp-uniform: every lane has seen the phase complete before any goes on
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3)
 {
@@ -290,29 +298,90 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
         int m = kStDone;
 #pragma unroll
         for (int i = 0; i < NW; i++) m = min(m, lds_acquire_s32(a_prog + 4 * i));
-        qmin = m;
+        // ONE view of the progress words for the whole warp: the lanes of a warp-wide load of a word another warp is storing to
+        // need not all see the same value, and lanes that disagree on q would split the warp for good
+        qmin = __shfl_sync(FULL, m, 0);
         if (qmin == kStDone || q < qmin + kStR) break;
         __nanosleep(64);
         if (t0 == 0) t0 = clock64();
-        else if (clock64() - t0 > kStWatchdogCycles) staged_die(T.diag, 1u, (uint32_t)q, (uint32_t)qmin, (uint32_t)p0);
+        else if (clock64() - t0 > kStWatchdogCycles) {
+#if LRF_ST_DEBUG
+          if (lane == 0 && T.diag && atomicCAS(T.diag + 7, 0u, 1u) == 0u) {   // one CTA's picture, not a mixture
+            for (int i = 0; i < NW; i++) T.diag[8 + i] = (uint32_t)lds_acquire_s32(a_prog + 4 * i);
+            for (int i = 0; i < NW * 8; i++) T.diag[16 + i] = (uint32_t)lds_acquire_s32(sbase + 192 + 4 * i);
+            for (int i = 0; i < kStR; i++) T.diag[16 + NW * 8 + i] = (uint32_t)mbar_test(a_full + 8 * i, 0) | ((uint32_t)mbar_test(a_full + 8 * i, 1) << 1);
+            for (int i = 0; i < 2 * kStR; i++) T.diag[24 + NW * 8 + i] = (uint32_t)lds_s32(sbase + 448 + 4 * i);
+            T.diag[40 + NW * 8] = (uint32_t)W; T.diag[41 + NW * 8] = (uint32_t)T.H; T.diag[42 + NW * 8] = T.plane_bytes; T.diag[43 + NW * 8] = T.slot_bytes;
+            T.diag[44 + NW * 8] = (uint32_t)q; T.diag[45 + NW * 8] = (uint32_t)qmin; T.diag[46 + NW * 8] = blockIdx.x;
+            __threadfence_system();
+            __nanosleep(100000);
+          }
+#endif
+          staged_die(T.diag, 1u, (uint32_t)q, (uint32_t)qmin, (uint32_t)p0);
+        }
       }
       if (qmin == kStDone) break;
       const int p = p0 + q, k = a_pos ? p : gs - 1 - p, slot = q & (kStR - 1);
       const uint32_t bar = a_full + 8 * slot, dst = a_ring + (uint32_t)slot * T.slot_bytes;
-      if (p < gs) {
-        int u0, v0, u1, v1;
+      // at most LRF_ST_INFLIGHT planes in flight; with the default (= ring size) this is the producer's own check that the slot's
+      // previous plane has landed before its barrier is armed again
+      if (q >= LRF_ST_INFLIGHT) {
+        const int j = q - LRF_ST_INFLIGHT;
+        mbar_wait(a_full + 8 * (j & (kStR - 1)), (uint32_t)(j / kStR) & 1u, T.diag, 4u, (uint32_t)j, (uint32_t)q);
+      }
+      int u0 = 0, v0 = 0, u1, v1;
+      bool real = p < gs;
+      if (real) {
         box_of(k, u0, v0, u1, v1);
+        // a box that lies entirely outside the lattice holds no node any lane will read: no TMA for it (the plane just counts as landed)
+        real = u0 < gs && v0 < gs && u0 + W > 0 && v0 + T.H > 0;
+      }
+      if (real) {
         if (lane == 0) {
           sts_s32(a_base + 4 * slot, (int)dst - (v0 * W + u0) * kStRecB);
+#if LRF_ST_DEBUG
+          sts_s32(sbase + 448 + 8 * slot, k | (A << 16) | (q << 20));
+          sts_s32(sbase + 452 + 8 * slot, (u0 & 0xffff) | (v0 << 16));
+#endif
           mbar_expect_tx(bar, T.plane_bytes);
           const int c1 = A == 0 ? k : u0, c2 = A == 0 ? u0 : (A == 1 ? k : v0), c3 = A == 2 ? k : v0;
           tma_load_4d(dst, &T.tm[A], bar, 0, c1, c2, c3);
         }
-      } else if (lane == 0) mbar_arrive(bar);
+      } else if (lane == 0) {
+#if LRF_ST_DEBUG
+        sts_s32(sbase + 448 + 8 * slot, k | (A << 16) | (q << 20) | (1 << 19));
+        sts_s32(sbase + 452 + 8 * slot, (u0 & 0xffff) | (v0 << 16));
+#endif
+        mbar_arrive(bar);
+      }
       __syncwarp();
+
     }
     // no TMA may be in flight into this CTA's shared memory when the CTA retires: wait for the last min(q, R) planes issued
-    for (int j = max(0, q - kStR); j < q; j++) mbar_wait(a_full + 8 * (j & (kStR - 1)), (uint32_t)(j / kStR) & 1u, T.diag, 2u, (uint32_t)j, (uint32_t)q);
+    for (int j = max(0, q - kStR); j < q; j++) {
+#if LRF_ST_DEBUG
+      const uint32_t bar = a_full + 8 * (j & (kStR - 1)), par = (uint32_t)(j / kStR) & 1u;
+      if (!mbar_try(bar, par)) {
+        const long long t0 = clock64();
+        while (!mbar_try(bar, par))
+          if (clock64() - t0 > kStWatchdogCycles) {
+            if (lane == 0 && T.diag && atomicCAS(T.diag + 7, 0u, 1u) == 0u) {
+              for (int i = 0; i < NW; i++) T.diag[8 + i] = (uint32_t)lds_acquire_s32(a_prog + 4 * i);
+              for (int i = 0; i < kStR; i++) T.diag[16 + i] = (uint32_t)mbar_test(a_full + 8 * i, 0) | ((uint32_t)mbar_test(a_full + 8 * i, 1) << 1);
+              for (int i = 0; i < 2 * kStR; i++) T.diag[24 + i] = (uint32_t)lds_s32(sbase + 448 + 4 * i);
+              T.diag[40] = (uint32_t)W; T.diag[41] = (uint32_t)T.H; T.diag[42] = (uint32_t)q; T.diag[43] = (uint32_t)q_end; T.diag[44] = (uint32_t)p0; T.diag[45] = (uint32_t)j;
+              T.diag[46] = blockIdx.x; T.diag[47] = (uint32_t)gs;
+              __threadfence_system();
+              __nanosleep(200000);
+            }
+            __syncwarp();
+            staged_die(T.diag, 2u, (uint32_t)j, (uint32_t)q, par);
+          }
+      }
+#else
+      mbar_wait(a_full + 8 * (j & (kStR - 1)), (uint32_t)(j / kStR) & 1u, T.diag, 2u, (uint32_t)j, (uint32_t)q);
+#endif
+    }
     return;
   }
 
@@ -420,13 +489,24 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
       if (lane == 0) sts_release_s32(a_prog + 4 * warp, pr);
     }
     const bool can = alive && (qe + 3 <= qready);
+#if LRF_ST_DEBUG
+    {
+      const uint32_t ba = __ballot_sync(FULL, alive), bc = __ballot_sync(FULL, can);
+      if (lane == 0) {
+        const uint32_t d = sbase + 192 + 32 * warp;
+        sts_s32(d, qmin); sts_s32(d + 4, qready); sts_s32(d + 8, (int)ba); sts_s32(d + 12, (int)bc); sts_s32(d + 16, qpub);
+        sts_s32(d + 20, lds_s32(d + 20) + 1);
+      }
+    }
+#endif
     if (!__any_sync(FULL, can)) {
       mbar_wait(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u, T.diag, 3u, (uint32_t)qready, (uint32_t)qmin);
       qready++;
       continue;
     }
     // look-ahead (result first used by the next trip): keep the ready pointer ahead of the fastest lane
-    if (qready < qmin + kStR && mbar_test(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u)) qready++;
+    // (the vote makes the answer the same in every lane: a phase that completes while the warp's test is in flight may be seen by some lanes only)
+    if (qready < qmin + kStR && __all_sync(FULL, mbar_test(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u))) qready++;
     if (can) {
       if (phase == 0) {
         // seed the slot addresses of the first cell: slot s holds corner c = s ^ odd
