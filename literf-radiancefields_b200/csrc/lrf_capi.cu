@@ -164,7 +164,7 @@ static int fail_with_diag(lrf_ctx *h, const char *what_call, cudaError_t e)
     const char *what = d[0] == 1 ? "producer: ring never freed (q, qmin, p0)" : d[0] == 2 ? "producer: drain (plane, issued, parity)"
                        : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : d[0] == 4 ? "producer: own TMA never completed (q, k, parity)" : "?";
     m += " | staged-render watchdog: " + std::string(what) + " block " + std::to_string(d[1]) + " thread " + std::to_string(d[2]) + " values " +
-         std::to_string((int)d[3]) + " " + std::to_string((int)d[4]) + " " + std::to_string((int)d[5]);
+         std::to_string((int)d[3]) + " " + std::to_string((int)d[4]) + " " + std::to_string((int)d[5]) + " active-mask " + std::to_string(d[6]);
     m += " | dump:";
     for (int i = 8; i < 96; i++) m += " " + std::to_string((int)d[i]);
   }

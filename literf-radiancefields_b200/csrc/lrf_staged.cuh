@@ -87,7 +87,7 @@ __device__ __noinline__ void staged_die(uint32_t *diag, uint32_t code, uint32_t 
 {
   if (diag) {
     if (atomicCAS(diag, 0u, code) == 0u) {
-      diag[1] = blockIdx.x; diag[2] = threadIdx.x; diag[3] = a; diag[4] = b; diag[5] = c;
+      diag[1] = blockIdx.x; diag[2] = threadIdx.x; diag[3] = a; diag[4] = b; diag[5] = c; diag[6] = __activemask();
       __threadfence_system();
     }
   }
@@ -95,12 +95,22 @@ __device__ __noinline__ void staged_die(uint32_t *diag, uint32_t code, uint32_t 
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t *diag, uint32_t code, uint32_t a, uint32_t b)
 {
-  if (!mbar_try(bar, parity)) {
+  // Called by whole warps only.  ONE lane watches the barrier and the warp meets at an explicit warp barrier: a per-lane wait loop
+  // lets the lanes leave at different times, nothing reconverges them afterwards, and the code that follows (convergent warp
+  // reductions, the elected TMA issue) was then run by partial warps on their own (profiles/r2_staged_debug.txt).
+  if ((threadIdx.x & 31) == 0 && !mbar_try(bar, parity)) {
     const long long t0 = clock64();
     while (!mbar_try(bar, parity))
       if (clock64() - t0 > kStWatchdogCycles) staged_die(diag, code, a, b, parity);
   }
-  __syncwarp();   // callers are warp-uniform: every lane has seen the phase complete before any goes on
+  __syncwarp();
+}
+// non-blocking, same answer in every lane
+__device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok = 0;
+  if ((threadIdx.x & 31) == 0) ok = mbar_test(bar, parity) ? 1u : 0u;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3)
 {
@@ -294,13 +304,14 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
     for (; q < q_end; q++) {
       // ring flow control: slot (q & R-1) is free once every consumer lane has left plane q - R behind
       long long t0 = 0;
+      __syncwarp();
       while (q >= qmin + kStR) {
         int m = kStDone;
+        if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < NW; i++) m = min(m, lds_acquire_s32(a_prog + 4 * i));
-        // ONE view of the progress words for the whole warp: the lanes of a warp-wide load of a word another warp is storing to
-        // need not all see the same value, and lanes that disagree on q would split the warp for good
-        qmin = __shfl_sync(FULL, m, 0);
+          for (int i = 0; i < NW; i++) m = min(m, lds_acquire_s32(a_prog + 4 * i));
+        }
+        qmin = __shfl_sync(FULL, m, 0);   // ONE view of the progress words for the whole warp
         if (qmin == kStDone || q < qmin + kStR) break;
         __nanosleep(64);
         if (t0 == 0) t0 = clock64();
@@ -358,30 +369,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
 
     }
     // no TMA may be in flight into this CTA's shared memory when the CTA retires: wait for the last min(q, R) planes issued
-    for (int j = max(0, q - kStR); j < q; j++) {
-#if LRF_ST_DEBUG
-      const uint32_t bar = a_full + 8 * (j & (kStR - 1)), par = (uint32_t)(j / kStR) & 1u;
-      if (!mbar_try(bar, par)) {
-        const long long t0 = clock64();
-        while (!mbar_try(bar, par))
-          if (clock64() - t0 > kStWatchdogCycles) {
-            if (lane == 0 && T.diag && atomicCAS(T.diag + 7, 0u, 1u) == 0u) {
-              for (int i = 0; i < NW; i++) T.diag[8 + i] = (uint32_t)lds_acquire_s32(a_prog + 4 * i);
-              for (int i = 0; i < kStR; i++) T.diag[16 + i] = (uint32_t)mbar_test(a_full + 8 * i, 0) | ((uint32_t)mbar_test(a_full + 8 * i, 1) << 1);
-              for (int i = 0; i < 2 * kStR; i++) T.diag[24 + i] = (uint32_t)lds_s32(sbase + 448 + 4 * i);
-              T.diag[40] = (uint32_t)W; T.diag[41] = (uint32_t)T.H; T.diag[42] = (uint32_t)q; T.diag[43] = (uint32_t)q_end; T.diag[44] = (uint32_t)p0; T.diag[45] = (uint32_t)j;
-              T.diag[46] = blockIdx.x; T.diag[47] = (uint32_t)gs;
-              __threadfence_system();
-              __nanosleep(200000);
-            }
-            __syncwarp();
-            staged_die(T.diag, 2u, (uint32_t)j, (uint32_t)q, par);
-          }
-      }
-#else
-      mbar_wait(a_full + 8 * (j & (kStR - 1)), (uint32_t)(j / kStR) & 1u, T.diag, 2u, (uint32_t)j, (uint32_t)q);
-#endif
-    }
+    for (int j = max(0, q - kStR); j < q; j++) mbar_wait(a_full + 8 * (j & (kStR - 1)), (uint32_t)(j / kStR) & 1u, T.diag, 2u, (uint32_t)j, (uint32_t)q);
     return;
   }
 
@@ -506,7 +494,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
     }
     // look-ahead (result first used by the next trip): keep the ready pointer ahead of the fastest lane
     // (the vote makes the answer the same in every lane: a phase that completes while the warp's test is in flight may be seen by some lanes only)
-    if (qready < qmin + kStR && __all_sync(FULL, mbar_test(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u))) qready++;
+    if (qready < qmin + kStR && mbar_test_warp(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u)) qready++;
     if (can) {
       if (phase == 0) {
         // seed the slot addresses of the first cell: slot s holds corner c = s ^ odd
