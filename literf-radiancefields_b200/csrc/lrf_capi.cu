@@ -162,7 +162,7 @@ static int fail_with_diag(lrf_ctx *h, const char *what_call, cudaError_t e)
   if (h->diag_host && h->diag_host[0]) {
     const uint32_t *d = h->diag_host;
     const char *what = d[0] == 1 ? "producer: ring never freed (q, qmin, p0)" : d[0] == 2 ? "producer: drain (plane, issued, parity)"
-                       : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : d[0] == 4 ? "producer: own TMA never completed (q, k, parity)" : "?";
+                       : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : d[0] == 4 ? "producer: own TMA never completed (plane, q, parity)" : d[0] == 5 ? "dynamic shared memory is not 1024-byte aligned (address)" : "?";
     m += " | staged-render watchdog: " + std::string(what) + " block " + std::to_string(d[1]) + " thread " + std::to_string(d[2]) + " values " +
          std::to_string((int)d[3]) + " " + std::to_string((int)d[4]) + " " + std::to_string((int)d[5]) + " active-mask " + std::to_string(d[6]);
     m += " | dump:";
@@ -200,16 +200,17 @@ static void host_gen_ray(const float *view_inv, const float *proj_inv, double x,
 }
 
 // Footprint box (nodes) a tile of tw x th pixels needs on a node plane: the same corner-ray construction as the producer warp of
-// render_staged_kernel, evaluated on a 5 x 5 sample of tiles.  A tile that needs more than this sends its pixels to the exact kernel,
+// render_staged_kernel, evaluated on a 13 x 13 sample of tiles.  A tile that needs more than this sends its pixels to the exact kernel,
 // so the estimate only has to be good, not safe.
-static void staged_box_need(const lrf_ctx *h, uint32_t w, uint32_t hgt, int tw, int th, int &Wn, int &Hn)
+static void staged_box_need(const lrf_ctx *h, uint32_t w, uint32_t hgt, int tw, int th, int Wn[3], int Hn[3])
 {
-  Wn = 4; Hn = 4;
+  for (int a = 0; a < 3; a++) { Wn[a] = 0; Hn[a] = 0; }
   const int gs = h->gs;
   const uint32_t ntx = (w + tw - 1) / tw, nty = (hgt + th - 1) / th;
-  for (int iy = 0; iy < 5; iy++)
-    for (int ix = 0; ix < 5; ix++) {
-      const uint32_t tx = (uint32_t)((uint64_t)(ntx - 1) * ix / 4), ty = (uint32_t)((uint64_t)(nty - 1) * iy / 4);
+  const int NS = 12;
+  for (int iy = 0; iy <= NS; iy++)
+    for (int ix = 0; ix <= NS; ix++) {
+      const uint32_t tx = (uint32_t)((uint64_t)(ntx - 1) * ix / NS), ty = (uint32_t)((uint64_t)(nty - 1) * iy / NS);
       const double x0 = (double)tx * tw, y0 = (double)ty * th;
       double oc[3], dc[3];
       host_gen_ray(h->view_inv, h->proj_inv, std::min<double>(x0 + tw / 2, w - 1), std::min<double>(y0 + th / 2, hgt - 1), w, hgt, oc, dc);
@@ -231,8 +232,8 @@ static void staged_box_need(const lrf_ctx *h, uint32_t w, uint32_t hgt, int tw, 
       }
       if (!ok) continue;
       for (int e = 0; e < 2; e++) {
-        Wn = std::max(Wn, (int)std::min(1e6, hi_u[e] - lo_u[e] + 1));
-        Hn = std::max(Hn, (int)std::min(1e6, hi_v[e] - lo_v[e] + 1));
+        Wn[A] = std::max(Wn[A], (int)std::min(1e6, hi_u[e] - lo_u[e] + 1));
+        Hn[A] = std::max(Hn[A], (int)std::min(1e6, hi_v[e] - lo_v[e] + 1));
       }
     }
 }
@@ -244,14 +245,20 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
   lrf_encode_tiled_fn enc = encode_tiled();
   if (!enc) return 2;
   const int nw = h->staged_nw == 8 ? 8 : 4;
-  int Wn, Hn;
+  int Wn[3], Hn[3];
   staged_box_need(h, w, hgt, 16, 2 * nw, Wn, Hn);
-  int W = h->staged_box_w > 0 ? h->staged_box_w : Wn + 1, H = h->staged_box_h > 0 ? h->staged_box_h : Hn + 1;
-  if (h->staged_box_w <= 0)
-    while ((W & 7) == 0 || (W & 7) == 1 || (W & 7) == 7 || (W & 7) == 4) W++;   // row pitch in records: neighbours within +-2 rows / columns land in different bank groups
-  if (std::getenv("LRF_DEBUG")) std::fprintf(stderr, "[lrf] staged box: need %d x %d -> W %d H %d (nw %d, %ux%u)\n", Wn, Hn, W, H, nw, w, hgt);
-  if (W > 64 || H > 64) return 2;
-  const uint32_t plane = (uint32_t)W * H * 64u, slot = (plane + 511u) & ~511u;
+  uint32_t slot = 0;
+  for (int A = 0; A < 3; A++) {
+    // an axis no sampled tile marches along still gets a (small) box: a tile that does use it and does not fit goes to the exact kernel
+    int W = h->staged_box_w > 0 ? h->staged_box_w : std::max(4, Wn[A] + 1), H = h->staged_box_h > 0 ? h->staged_box_h : std::max(4, Hn[A] + 1);
+    if (h->staged_box_w <= 0)
+      while ((W & 7) == 0 || (W & 7) == 1 || (W & 7) == 7 || (W & 7) == 4) W++;   // row pitch in records: neighbours within +-2 rows / columns land in different bank groups
+    if (std::getenv("LRF_DEBUG")) std::fprintf(stderr, "[lrf] staged box A=%d: need %d x %d -> W %d H %d (nw %d, %ux%u)\n", A, Wn[A], Hn[A], W, H, nw, w, hgt);
+    if (W > 64 || H > 64) return 2;
+    T.W[A] = W; T.H[A] = H;
+    T.plane_bytes[A] = (uint32_t)W * H * 64u;
+    slot = std::max(slot, (T.plane_bytes[A] + 511u) & ~511u);
+  }
   if (1024 + 512 + 8 * (size_t)slot > 200 * 1024) return 2;
   // records
   if (!h->rec || h->rec_N != h->N) {
@@ -270,8 +277,7 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
     CK(cudaStreamSynchronize(h->stream));
     h->rec_dirty = false;
   }
-  T.W = W; T.H = H;
-  T.plane_bytes = plane; T.slot_bytes = slot;
+  T.slot_bytes = slot;
   T.err_sigma = 16.0f * 0x1p-24f * h->dmax;   // NaN / inf densities make every break ambiguous: the exact kernel then renders those rays
   T.stats = h->st_stats;
   if (!h->diag_host) {
@@ -284,7 +290,8 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
   const cuuint64_t dims[4] = {16, gs, gs, gs}, strides[3] = {64, 64 * gs, 64 * gs * gs};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   for (int A = 0; A < 3; A++) {
-    const cuuint32_t box[4] = {16, (cuuint32_t)(A == 0 ? 1 : W), (cuuint32_t)(A == 0 ? W : (A == 1 ? 1 : H)), (cuuint32_t)(A == 2 ? 1 : H)};
+    const cuuint32_t W = (cuuint32_t)T.W[A], H = (cuuint32_t)T.H[A];
+    const cuuint32_t box[4] = {16, A == 0 ? 1u : W, A == 0 ? W : (A == 1 ? 1u : H), A == 2 ? 1u : H};
     const CUresult r = enc(&T.tm[A], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h->rec, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            LRF_ST_SWZ ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -395,6 +402,11 @@ int lrf_create(int device, lrf_ctx **out)
   CK(cudaEventCreate(&h->tm1));
   // defaults of the reference constructor (example_tracer.h:43-49): caller overrides through the setters
   for (int i = 0; i < 16; i++) h->view_inv[i] = h->proj_inv[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  // experiment knobs (tools/variants.py): the same switches as lrf_set_option
+  if (const char *e = std::getenv("LRF_STAGED")) h->staged = std::atoi(e) ? 1 : 0;
+  if (const char *e = std::getenv("LRF_STAGED_WARPS")) h->staged_nw = std::atoi(e) == 8 ? 8 : 4;
+  if (const char *e = std::getenv("LRF_STAGED_BOX_W")) h->staged_box_w = std::atoi(e);
+  if (const char *e = std::getenv("LRF_STAGED_BOX_H")) h->staged_box_h = std::atoi(e);
   *out = h;
   return 0;
 }

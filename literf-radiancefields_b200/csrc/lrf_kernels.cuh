@@ -23,9 +23,9 @@ struct DebugTaps  // device pointers, any may be null
 struct alignas(64) StagedArgs
 {
   CUtensorMap tm[3];        // by march axis A: box {16, 1, W, H} / {16, W, 1, H} / {16, W, H, 1} over {16 floats, x, y, z}
-  int W, H;                 // footprint box in nodes: W along the first lateral axis in memory order, H along the second
-  uint32_t plane_bytes;     // W * H * 64 (what one TMA delivers)
-  uint32_t slot_bytes;      // ring slot stride, plane_bytes rounded up to kStSlotAlign
+  int W[3], H[3];           // footprint box in nodes by march axis: W along the first lateral axis in memory order, H along the second
+  uint32_t plane_bytes[3];  // W * H * 64 (what one TMA delivers)
+  uint32_t slot_bytes;      // ring slot stride: the largest plane rounded up to kStSlotAlign
   float err_sigma;          // bound on |weight-form density - reference nested-lerp density|: 16 ulp of the largest |density| in the grid
   uint32_t *diag;           // host-mapped: watchdog record {code, block, thread, a, b, c} written before a stuck wait traps the kernel
   uint32_t *stats;          // [0] rays sent to the exact kernel because the break was ambiguous, [1] other rays sent there (ties, entry on a

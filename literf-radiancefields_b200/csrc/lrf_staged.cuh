@@ -39,6 +39,9 @@
 #ifndef LRF_ST_DEBUG
 #define LRF_ST_DEBUG 0        // 1: every consumer warp leaves its ring state in shared memory; the producer's watchdog copies it out
 #endif
+#ifndef LRF_ST_RELOAD
+#define LRF_ST_RELOAD 1       // 1: {density, R, G, B} of all 8 corners re-read from the staged planes every sample (window = q only: 32 registers less);
+#endif                        // 0: kept in the register window, committed by predicated loads
 #ifndef LRF_ST_INFLIGHT
 #define LRF_ST_INFLIGHT 8     // planes the producer keeps in flight (<= ring size)
 #endif
@@ -133,6 +136,31 @@ __device__ __forceinline__ void lds_slot(uint32_t a, uint32_t toA, float4 &A, fl
       "@!p ld.shared.v4.f32 {%4, %5, %6, %7}, [%9];\n\t}"
       : "+f"(A.x), "+f"(A.y), "+f"(A.z), "+f"(A.w), "+f"(B.x), "+f"(B.y), "+f"(B.z), "+f"(B.w)
       : "r"(toA), "r"(a));
+}
+// same with one address register per member (what the march uses)
+__device__ __forceinline__ void lds_slot2(uint32_t aA, uint32_t aB, uint32_t toA, float4 &A, float4 &B)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %8, 0;\n\t"
+      "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%9];\n\t"
+      "@!p ld.shared.v4.f32 {%4, %5, %6, %7}, [%10];\n\t}"
+      : "+f"(A.x), "+f"(A.y), "+f"(A.z), "+f"(A.w), "+f"(B.x), "+f"(B.y), "+f"(B.z), "+f"(B.w)
+      : "r"(toA), "r"(aA), "r"(aB));
+}
+// rare paths of the march, kept out of line (they would otherwise be if-converted into the hot loop)
+// exact comparison of the three exit-plane times, the reference's own fp64 quotients (ref octree.h:449-488): the crossing mask
+static __device__ __noinline__ int staged_exact_cross(const float *pa, const float *o, const float *d)
+{
+  double te[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) te[a] = ((double)pa[a] - (double)o[a]) / (double)d[a];
+  const double em = fmin(te[0], fmin(te[1], te[2]));
+  return (te[0] == em ? 1 : 0) | (te[1] == em ? 2 : 0) | (te[2] == em ? 4 : 0);
+}
+// ref example_tracer.cpp:145-146
+static __device__ __noinline__ float staged_long_step(float delta, double step)
+{
+  return (float)((double)delta - (double)((int)((double)delta / step) - 1) * step);
 }
 // q = fma(s8, y8, part) into the stale member of the pair
 __device__ __forceinline__ void fma_slot(uint32_t toA, float s8, float y8, float part, float &qA, float &qB)
@@ -234,7 +262,8 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
   constexpr int kTileW = 16, kTileH = 2 * NW;
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sbase = smem_u32(smem_raw);                        // 1024-aligned: dynamic shared memory starts the CTA's window
+  if (sbase & 1023u) staged_die(T.diag, 5u, sbase, 0u, 0u);
   const uint32_t a_full = sbase, a_base = sbase + 64, a_first = sbase + 96, a_prog = sbase + 128, a_ovf = sbase + 160, a_ring = sbase + kStCtl;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles_x = (w + kTileW - 1) / kTileW;
@@ -252,7 +281,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
     a_pos = pick3(dc, A) > 0.0f;
   }
   const int U = (A == 0) ? 1 : 0, V = (A == 2) ? 1 : 2;
-  const int W = T.W;
+  const int W = T.W[A], H = T.H[A];
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -288,9 +317,9 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
       int u0, v0, u1, v1;
       bool fits = __all_sync(FULL, corner_ok);
       box_of(0, u0, v0, u1, v1);
-      fits = fits && (u1 - u0 + 1 <= W) && (v1 - v0 + 1 <= T.H);
+      fits = fits && (u1 - u0 + 1 <= W) && (v1 - v0 + 1 <= H);
       box_of(gs - 1, u0, v0, u1, v1);
-      fits = fits && (u1 - u0 + 1 <= W) && (v1 - v0 + 1 <= T.H);
+      fits = fits && (u1 - u0 + 1 <= W) && (v1 - v0 + 1 <= H);
       if (lane == 0) sts_s32(a_ovf, fits ? 0 : 1);
     }
     __syncthreads();
@@ -313,7 +342,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
         }
         qmin = __shfl_sync(FULL, m, 0);   // ONE view of the progress words for the whole warp
         if (qmin == kStDone || q < qmin + kStR) break;
-        __nanosleep(64);
+        __nanosleep(200);
         if (t0 == 0) t0 = clock64();
         else if (clock64() - t0 > kStWatchdogCycles) {
 #if LRF_ST_DEBUG
@@ -322,7 +351,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
             for (int i = 0; i < NW * 8; i++) T.diag[16 + i] = (uint32_t)lds_acquire_s32(sbase + 192 + 4 * i);
             for (int i = 0; i < kStR; i++) T.diag[16 + NW * 8 + i] = (uint32_t)mbar_test(a_full + 8 * i, 0) | ((uint32_t)mbar_test(a_full + 8 * i, 1) << 1);
             for (int i = 0; i < 2 * kStR; i++) T.diag[24 + NW * 8 + i] = (uint32_t)lds_s32(sbase + 448 + 4 * i);
-            T.diag[40 + NW * 8] = (uint32_t)W; T.diag[41 + NW * 8] = (uint32_t)T.H; T.diag[42 + NW * 8] = T.plane_bytes; T.diag[43 + NW * 8] = T.slot_bytes;
+            T.diag[40 + NW * 8] = (uint32_t)W; T.diag[41 + NW * 8] = (uint32_t)H; T.diag[42 + NW * 8] = T.plane_bytes[A]; T.diag[43 + NW * 8] = T.slot_bytes;
             T.diag[44 + NW * 8] = (uint32_t)q; T.diag[45 + NW * 8] = (uint32_t)qmin; T.diag[46 + NW * 8] = blockIdx.x;
             __threadfence_system();
             __nanosleep(100000);
@@ -345,7 +374,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
       if (real) {
         box_of(k, u0, v0, u1, v1);
         // a box that lies entirely outside the lattice holds no node any lane will read: no TMA for it (the plane just counts as landed)
-        real = u0 < gs && v0 < gs && u0 + W > 0 && v0 + T.H > 0;
+        real = u0 < gs && v0 < gs && u0 + W > 0 && v0 + H > 0;
       }
       if (real) {
         if (lane == 0) {
@@ -354,7 +383,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
           sts_s32(sbase + 448 + 8 * slot, k | (A << 16) | (q << 20));
           sts_s32(sbase + 452 + 8 * slot, (u0 & 0xffff) | (v0 << 16));
 #endif
-          mbar_expect_tx(bar, T.plane_bytes);
+          mbar_expect_tx(bar, T.plane_bytes[A]);
           const int c1 = A == 0 ? k : u0, c2 = A == 0 ? u0 : (A == 1 ? k : v0), c3 = A == 2 ? k : v0;
           tma_load_4d(dst, &T.tm[A], bar, 0, c1, c2, c3);
         }
@@ -387,7 +416,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
   uint32_t to_exact = (valid && !alive) ? 2u : 0u;                // 1: ambiguous break, 2: anything else the exact kernel has to do
   bool hit = false;
   // per-ray state, axes permuted to (U, V, A)
-  float o_[3], d_[3], idir_[3], pa[3], tf[3], dpa[3], boff[3];
+  float o_[3], d_[3], idir_[3], pa[3], tf[3], dpa[3];
   float M = 0.0f;
   uint32_t odd = 0, negm = 0, cnt = 0, seed_off = 0;
   int qe = 0;
@@ -408,7 +437,6 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
       o_[a] = ov; d_[a] = dv;
       idir_[a] = 1.0f / dv;                                       // ref example_tracer.cpp:20-22
       dpa[a] = pos ? S.inv_gs_f : -S.inv_gs_f;
-      boff[a] = pos ? -S.inv_gs_f : 0.0f;
       pa[a] = (float)(c + (pos ? 1 : 0)) * S.inv_gs_f;            // exit plane of the first cell (exact: multiples of 2^-k)
       tf[a] = idir_[a] * (pa[a] - ov);
       const float tn = idir_[a] * ((float)(c + (pos ? 0 : 1)) * S.inv_gs_f - ov);
@@ -448,11 +476,18 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
   const int dU2 = (negm & 1u) ? -2 * kStRecB : 2 * kStRecB, dV2 = ((negm & 2u) ? -2 * kStRecB : 2 * kStRecB) * W;
 
   // window: slot s = parity bits (U, V, A) of the node coordinates
+#if !LRF_ST_RELOAD
   float4 wv[8];
+#endif
   float wq[8];
   uint32_t AD[8];
 #pragma unroll
-  for (int s = 0; s < 8; s++) { wv[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); wq[s] = 0.0f; AD[s] = 0u; }
+  for (int s = 0; s < 8; s++) {
+#if !LRF_ST_RELOAD
+    wv[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#endif
+    wq[s] = 0.0f; AD[s] = 0u;
+  }
   int EA0 = 0, EA1 = 0;                                           // ring base of the window's plane with even / odd A coordinate
   uint32_t stale = 0x0fu;
   int phase = 0;                                                  // 0: window empty, 1: members J loaded, 2: steady state
@@ -461,6 +496,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
   const float band_d = 0.11f * T.err_sigma;                       // per unit of delta
   uint32_t n_shaded = 0;
   int qready = 0, qpub = 0;
+  uint32_t trip = 0;
 
   for (;;) {
     // ---- ring bookkeeping (warp-uniform) ----
@@ -468,6 +504,9 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
     // slot of plane q - R for plane q only when every live warp has BOTH seen q - R complete and marched past it.  So a slot's
     // barrier is never armed twice in one phase, and the parity a warp waits for always names the slot's current or previous use
     // (a warp whose rays enter the lattice late just walks through the earlier planes in the wait below).
+    const bool can = alive && (qe + 3 <= qready);
+    const bool any_can = __any_sync(FULL, can);
+    if (!any_can || (trip++ & 1u) == 0u) {
     const int qmin = __reduce_min_sync(FULL, alive ? qe : kStDone);
     if (qmin == kStDone) break;
     const int pr = min(qmin, qready);
@@ -476,7 +515,6 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
       __syncwarp();
       if (lane == 0) sts_release_s32(a_prog + 4 * warp, pr);
     }
-    const bool can = alive && (qe + 3 <= qready);
 #if LRF_ST_DEBUG
     {
       const uint32_t ba = __ballot_sync(FULL, alive), bc = __ballot_sync(FULL, can);
@@ -487,7 +525,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
       }
     }
 #endif
-    if (!__any_sync(FULL, can)) {
+    if (!any_can) {
       mbar_wait(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u, T.diag, 3u, (uint32_t)qready, (uint32_t)qmin);
       qready++;
       continue;
@@ -495,6 +533,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
     // look-ahead (result first used by the next trip): keep the ready pointer ahead of the fastest lane
     // (the vote makes the answer the same in every lane: a phase that completes while the warp's test is in flight may be seen by some lanes only)
     if (qready < qmin + kStR && mbar_test_warp(a_full + 8 * (qready & (kStR - 1)), (uint32_t)(qready / kStR) & 1u)) qready++;
+    }
     if (can) {
       if (phase == 0) {
         // seed the slot addresses of the first cell: slot s holds corner c = s ^ odd
@@ -510,22 +549,34 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
         stale = 0x0fu;
       }
       // ---- (1) gather: pair J = slots {J, 7-J}; its stale member is J when bit J of `stale` is set, else 7-J ----
+      // Chunk 0 {density, R, G, B} goes straight into the stale member's registers: two predicated loads from the two members'
+      // OWN address registers (with one shared address ptxas folds them into one load + 8 predicated moves).
+#if LRF_ST_RELOAD
+      uint32_t ADc[8];                                             // chunk-0 addresses of the current cell's corners (the advance below moves AD on)
+#pragma unroll
+      for (int s8 = 0; s8 < 8; s8++) ADc[s8] = rec_chunk0(AD[s8]);
+#endif
       const uint32_t st = stale;
-      uint32_t t0[4];
+      const uint32_t t0[4] = {st & 1u, (st >> 1) & 1u, (st >> 2) & 1u, (st >> 3) & 1u};
       float4 c1[4], c2[4];
       float c3[4];
 #pragma unroll
       for (int J = 0; J < 4; J++) {
-        t0[J] = (st >> J) & 1u;
+#if !LRF_ST_RELOAD
+        lds_slot2(rec_chunk0(AD[J]), rec_chunk0(AD[7 - J]), t0[J], wv[J], wv[7 - J]);
+#endif
+#if LRF_ST_RELOAD
+        const uint32_t r = t0[J] ? ADc[J] : ADc[7 - J];
+#else
         const uint32_t r = rec_chunk0(t0[J] ? AD[J] : AD[7 - J]);
-        lds_slot(r, t0[J], wv[J], wv[7 - J]);
+#endif
         c1[J] = lds_f4(rec_chunk(r, 1));
         c2[J] = lds_f4(rec_chunk(r, 2));
         c3[J] = lds_f1(rec_chunk(r, 3));
       }
       const bool shade = phase != 0;
       float lf0 = 0.0f, lf1 = 0.0f, lf2 = 0.0f, delta = 0.0f;
-      uint32_t odd_cur = odd;
+      const uint32_t odd_cur = odd;
       if (shade) {
         // ---- (2) which face does the ray leave through?  fp32 filter, exact fp64 when close (as lrf_fast.cuh) ----
         const float m = fminf(fminf(tf[0], tf[1]), tf[2]);
@@ -533,11 +584,7 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
         const bool c0 = tf[0] - m <= gate, cc1 = tf[1] - m <= gate, cc2 = tf[2] - m <= gate;
         bool is0 = c0, is1 = !c0 && cc1;
         if ((c0 && cc1) || (c0 && cc2) || (cc1 && cc2)) {
-          double te[3];
-#pragma unroll
-          for (int a = 0; a < 3; a++) te[a] = ((double)pa[a] - (double)o_[a]) / (double)d_[a];
-          const double em = fmin(te[0], fmin(te[1], te[2]));
-          const int cross = (te[0] == em ? 1 : 0) | (te[1] == em ? 2 : 0) | (te[2] == em ? 4 : 0);
+          const int cross = staged_exact_cross(pa, o_, d_);
           if (cross & (cross - 1)) { alive = false; to_exact = 2u; }   // edge / corner grazing: 3 or 7 boxes at the same distance
           is0 = (cross & 1) != 0;
           is1 = !is0 && (cross & 2) != 0;
@@ -549,17 +596,17 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
           if (tPrev < 0.0f) tPrev = tmin;                          // :139
           const float t = (tmin + tmax) * 0.5f;                    // :142
           delta = t - tPrev;                                       // :144
-          if (delta > S.step_gate_f)                               // :145-146
-            delta = (float)((double)delta - (double)((int)((double)delta / S.step) - 1) * S.step);
+          if (delta > S.step_gate_f) delta = staged_long_step(delta, S.step);   // :145-146
           tPrev = t;                                               // :190
-          lf0 = ((o_[0] + t * d_[0]) - (pa[0] + boff[0])) * S.gs_f;   // :148-150
-          lf1 = ((o_[1] + t * d_[1]) - (pa[1] + boff[1])) * S.gs_f;
-          lf2 = ((o_[2] + t * d_[2]) - (pa[2] + boff[2])) * S.gs_f;
+          // lower plane of the cell: the exit plane for a ray going down, one cell before it for a ray going up (exact either way)
+          lf0 = ((o_[0] + t * d_[0]) - (pa[0] + fminf(-dpa[0], 0.0f))) * S.gs_f;   // :148-150
+          lf1 = ((o_[1] + t * d_[1]) - (pa[1] + fminf(-dpa[1], 0.0f))) * S.gs_f;
+          lf2 = ((o_[2] + t * d_[2]) - (pa[2] + fminf(-dpa[2], 0.0f))) * S.gs_f;
         }
         // ---- (4) advance to the next cell ----
         {
           const float e = is0 ? tf[0] : (is1 ? tf[1] : tf[2]);
-          M = fmaxf(M, e);                                         // entry time of the next cell (see the note on tmin in DESIGN.md)
+          M = fmaxf(M, e);                                         // entry time of the next cell
           const bool sel[3] = {is0, is1, isA};
 #pragma unroll
           for (int a = 0; a < 3; a++) {
@@ -571,8 +618,6 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
           const uint32_t abit = is0 ? 1u : (is1 ? 2u : 4u);
           const bool pst = ((odd ^ negm) & abit) != 0;             // parity of the node plane that enters the window
           odd ^= abit;
-          const uint32_t m0 = is0 ? 0x55u : (is1 ? 0x33u : 0x0fu);
-          const uint32_t mask8 = pst ? (m0 ^ 0xffu) : m0;          // slots whose node changes
           cnt -= is0 ? 1u : (is1 ? (1u << 10) : (1u << 20));
           if ((cnt & 0x20080200u) != 0x20080200u) alive = false;   // left the lattice
           int dl = is0 ? dU2 : dV2;
@@ -582,9 +627,17 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
             dl = nb - (pst ? EA1 : EA0);
             EA0 = pst ? EA0 : nb; EA1 = pst ? nb : EA1;
           }
-#pragma unroll
-          for (int s = 0; s < 8; s++) AD[s] += ((mask8 >> s) & 1u) ? (uint32_t)dl : 0u;
-          stale = mask8 & 0x0fu;
+          // slot s changes iff its parity bit along the step axis equals pst; with exactly one axis stepping that is
+          //   s = 0: !pst   s = 7: pst   s = 1: (is0 == pst)   s = 6: the opposite   s = 2 / 5: (is1 == pst)   s = 4 / 3: (isA == pst)
+          const bool x1 = is0 == pst, x2 = is1 == pst, x4 = isA == pst;
+          {
+            const uint32_t d0 = pst ? 0u : (uint32_t)dl, d1 = x1 ? (uint32_t)dl : 0u, d2 = x2 ? (uint32_t)dl : 0u, d4 = x4 ? (uint32_t)dl : 0u;
+            AD[0] += d0; AD[7] += (uint32_t)dl - d0;
+            AD[1] += d1; AD[6] += (uint32_t)dl - d1;
+            AD[2] += d2; AD[5] += (uint32_t)dl - d2;
+            AD[4] += d4; AD[3] += (uint32_t)dl - d4;
+          }
+          stale = (pst ? 0u : 1u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x4 ? 0u : 8u);
         }
       } else stale = 0x00u;                                        // next: the other member of every pair
       // ---- (5) contract the gathered nodes with the ray's SH basis into the stale slots ----
@@ -596,7 +649,9 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
         q2 = fma2(pk2(c2[J].z, c2[J].w), Y67, q2);
         float ql, qh;
         upk2(q2, ql, qh);
-        fma_slot(t0[J], c3[J], Y8, ql + qh, wq[J], wq[7 - J]);
+        const float qn = fmaf(c3[J], Y8, ql + qh);
+        wq[J] = t0[J] ? qn : wq[J];
+        wq[7 - J] = t0[J] ? wq[7 - J] : qn;
       }
       if (shade) {
         // ---- (6) interpolation weights per slot (the parity permutation applied to the weights) ----
@@ -609,6 +664,11 @@ render_staged_kernel(const __grid_constant__ SceneDev S, const __grid_constant__
         const u64 w00 = mul2(pu0, pv0), w10 = mul2(pu1, pv0), w01 = mul2(pu0, pv1), w11 = mul2(pu1, pv1);
         const u64 w8[8] = {mul2(w00, pa0), mul2(w10, pa0), mul2(w01, pa0), mul2(w11, pa0), mul2(w00, pa1), mul2(w10, pa1), mul2(w01, pa1), mul2(w11, pa1)};
         // ---- (7) {density, R}, {G, B} as packed pairs, q scalar; two chains each ----
+#if LRF_ST_RELOAD
+        float4 wv[8];
+#pragma unroll
+        for (int s8 = 0; s8 < 8; s8++) wv[s8] = lds_f4(ADc[s8]);
+#endif
         u64 dr0 = mul2(w8[0], pk2(wv[0].x, wv[0].y)), gb0 = mul2(w8[0], pk2(wv[0].z, wv[0].w));
         u64 dr1 = mul2(w8[1], pk2(wv[1].x, wv[1].y)), gb1 = mul2(w8[1], pk2(wv[1].z, wv[1].w));
         float ws[8], dump;
