@@ -67,7 +67,8 @@ struct lrf_ctx
   float *dmax_dev = nullptr;          // largest |density| of the baked grid (device), and its host copy
   float dmax = 0.0f;
   uint32_t *st_stats = nullptr;       // 4 counters, see StagedArgs::stats
-  int staged = 1;                     // option "staged_render": 0 = the thread-per-ray gather kernel for every render
+  int staged = 0;                     // option "staged_render": 1 = dense colour renders by the TMA-staged kernel (lrf_staged.cuh), 0 = by the gather kernel
+  int baked = 0;                      // option "baked_records": 1 = the gather kernel reads the 64-byte node records instead of the planes (measured slower: 2.48 vs 2.30 ms per view)
   int staged_nw = 4;                  // option "staged_warps": consumer warps per CTA (4: 16x8 pixel tiles, 8: 16x16)
   int staged_box_w = 0, staged_box_h = 0;   // options "staged_box_w/h": override the footprint box (0 = from the camera)
   int last_render_staged = 0;
@@ -238,6 +239,28 @@ static void staged_box_need(const lrf_ctx *h, uint32_t w, uint32_t hgt, int tw, 
     }
 }
 
+// the baked 64-byte node records both forward kernels can read (lrf_staged.cuh), rebuilt when the parameters changed.
+// 0 = ready, 1 = error, 2 = no room for the second copy of the grid (the caller renders from the planes)
+static int ensure_records(lrf_ctx *h)
+{
+  if (!h->rec || h->rec_N != h->N) {
+    cudaFree(h->rec);
+    h->rec = nullptr; h->rec_N = 0;
+    if (cudaMalloc(&h->rec, h->N * 64) != cudaSuccess) { cudaGetLastError(); return 2; }
+    h->rec_N = h->N;
+    h->rec_dirty = true;
+  }
+  if (!h->dmax_dev) CK(cudaMalloc(&h->dmax_dev, sizeof(float)));
+  if (h->rec_dirty) {
+    launch_bake_records(scene_of(h), h->rec, h->dmax_dev, h->stream);
+    h->launches++;
+    CK(cudaMemcpyAsync(&h->dmax, h->dmax_dev, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->rec_dirty = false;
+  }
+  return 0;
+}
+
 // 0 = T is ready and the staged kernel can run; 1 = error (g_err set); 2 = this render is not eligible (caller uses the gather kernel)
 static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
 {
@@ -260,23 +283,8 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
     slot = std::max(slot, (T.plane_bytes[A] + 511u) & ~511u);
   }
   if (1024 + 512 + 8 * (size_t)slot > 200 * 1024) return 2;
-  // records
-  if (!h->rec || h->rec_N != h->N) {
-    cudaFree(h->rec);
-    h->rec = nullptr; h->rec_N = 0;
-    if (cudaMalloc(&h->rec, h->N * 64) != cudaSuccess) { cudaGetLastError(); return 2; }   // no room for the second copy: gather kernel
-    h->rec_N = h->N;
-    h->rec_dirty = true;
-  }
-  if (!h->dmax_dev) CK(cudaMalloc(&h->dmax_dev, sizeof(float)));
+  { const int r = ensure_records(h); if (r) return r; }
   if (!h->st_stats) { CK(cudaMalloc(&h->st_stats, 4 * sizeof(uint32_t))); CK(cudaMemsetAsync(h->st_stats, 0, 4 * sizeof(uint32_t), h->stream)); }
-  if (h->rec_dirty) {
-    launch_bake_records(scene_of(h), h->rec, h->dmax_dev, h->stream);
-    h->launches++;
-    CK(cudaMemcpyAsync(&h->dmax, h->dmax_dev, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->rec_dirty = false;
-  }
   T.slot_bytes = slot;
   T.err_sigma = 16.0f * 0x1p-24f * h->dmax;   // NaN / inf densities make every break ambiguous: the exact kernel then renders those rays
   T.stats = h->st_stats;
@@ -315,7 +323,13 @@ static int render_dispatch(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t h
     }
   }
   if (tap_shaded) return fail("the staged render is not available for this configuration (dense grids of 8..512 nodes per axis, colour mode)");
-  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream);
+  SceneDev S = scene_of(h);
+  if (h->baked && h->dense && !grey) {   // gather kernel over the baked records (fewer L1 wavefronts per node); from the planes if they do not fit
+    const int r = ensure_records(h);
+    if (r == 1) return 1;
+    if (r == 0) S.rec = h->rec;
+  }
+  launch_render_image(S, out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream);
   h->launches += 2;   // render_image_kernel + render_fallback_kernel
   return 0;
 }
@@ -404,6 +418,7 @@ int lrf_create(int device, lrf_ctx **out)
   for (int i = 0; i < 16; i++) h->view_inv[i] = h->proj_inv[i] = (i % 5 == 0) ? 1.0f : 0.0f;
   // experiment knobs (tools/variants.py): the same switches as lrf_set_option
   if (const char *e = std::getenv("LRF_STAGED")) h->staged = std::atoi(e) ? 1 : 0;
+  if (const char *e = std::getenv("LRF_BAKED")) h->baked = std::atoi(e) ? 1 : 0;
   if (const char *e = std::getenv("LRF_STAGED_WARPS")) h->staged_nw = std::atoi(e) == 8 ? 8 : 4;
   if (const char *e = std::getenv("LRF_STAGED_BOX_W")) h->staged_box_w = std::atoi(e);
   if (const char *e = std::getenv("LRF_STAGED_BOX_H")) h->staged_box_h = std::atoi(e);
@@ -1289,6 +1304,7 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   if (s == "force_generic_march") h->force_generic = value ? 1 : 0;
   else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
   else if (s == "staged_render") h->staged = value ? 1 : 0;
+  else if (s == "baked_records") h->baked = value ? 1 : 0;
   else if (s == "staged_warps") { if (value != 4 && value != 8) return fail("staged_warps must be 4 or 8"); h->staged_nw = value; }
   else if (s == "staged_box_w") h->staged_box_w = value;
   else if (s == "staged_box_h") h->staged_box_h = value;

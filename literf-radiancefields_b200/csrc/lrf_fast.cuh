@@ -76,7 +76,10 @@ constexpr int kFastBlock = 128;   // threads per block of the kernels that use F
 #define LRF_SEARCH_TRIPS 4   // sparse render: traversal events per lane between two shading slots of the warp (see run())
 #endif
 
-template <int MODE, bool SPARSE, bool GREY> struct FastMarch
+// BAKED: the render reads the 64-byte node records {density, R, G, B | sh0..sh3 | sh4..sh7 | sh8, 0, 0, 0} (S.rec, lrf_staged.cuh) instead of the
+// density + colour planes: a node is half a 128-byte line (the 48-byte colour records straddle lines) and its density comes with
+// the first chunk, so a gather costs fewer L1 wavefronts (the pipe this kernel is bound by)
+template <int MODE, bool SPARSE, bool GREY, bool BAKED = false> struct FastMarch
 {
   const SceneDev &S;
   const uint64_t *etab;
@@ -224,7 +227,8 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   struct NodeLoad
   {
     float td;
-    float4 a, b, e;   // {R,G,B,sh0}, {sh1..sh4}, {sh5..sh8}
+    float4 a, b, e;   // {R,G,B,sh0}, {sh1..sh4}, {sh5..sh8};  BAKED: {density,R,G,B}, {sh0..sh3}, {sh4..sh7} and s8
+    float s8;
     uint32_t node;    // MODE 3: the node these values belong to (the gradient window needs it when the slot is flushed)
   };
   // bit J of the result: member 7-J of pair J is stale
@@ -238,14 +242,25 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   __device__ __forceinline__ void issue_colour(uint32_t node, NodeLoad &L) const
   {
     if (!GREY) {
-      const float4 *pc = S.col + (size_t)node * kColF4;
-      L.a = __ldg(pc); L.b = __ldg(pc + 1); L.e = __ldg(pc + 2);
+      if (BAKED) {
+        const float4 *pc = S.rec + (size_t)node * 4;
+        L.b = __ldg(pc + 1); L.e = __ldg(pc + 2); L.s8 = __ldg(reinterpret_cast<const float *>(pc + 3));
+      } else {
+        const float4 *pc = S.col + (size_t)node * kColF4;
+        L.a = __ldg(pc); L.b = __ldg(pc + 1); L.e = __ldg(pc + 2);
+      }
     }
+  }
+  // the part of a node the density interpolation needs (BAKED: chunk 0, which carries R, G, B as well)
+  __device__ __forceinline__ void issue_density(uint32_t node, NodeLoad &L) const
+  {
+    if (BAKED) L.a = __ldg(S.rec + (size_t)node * 4);
+    else L.td = __ldg(S.dens + node);
   }
   template <int J> __device__ __forceinline__ void issue_pair(uint32_t stale, NodeLoad &L) const
   {
     const uint32_t node = pair_node<J>(stale);
-    L.td = __ldg(S.dens + node);
+    issue_density(node, L);
     if (MODE == 3) L.node = node;
     issue_colour(node, L);
   }
@@ -338,11 +353,17 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   }
   struct Basis
   {
-    float Y0;
-    u64 Y12, Y34, Y56, Y78;
+    float Y0;                 // BAKED: Y8
+    u64 Y12, Y34, Y56, Y78;   // BAKED: Y01, Y23, Y45, Y67
   };
   __device__ __forceinline__ void load_basis(Basis &Y) const
   {
+    if (BAKED) {
+      Y.Y0 = ysm[8 * kFastBlock];
+      Y.Y12 = pk2(ysm[0], ysm[1 * kFastBlock]); Y.Y34 = pk2(ysm[2 * kFastBlock], ysm[3 * kFastBlock]);
+      Y.Y56 = pk2(ysm[4 * kFastBlock], ysm[5 * kFastBlock]); Y.Y78 = pk2(ysm[6 * kFastBlock], ysm[7 * kFastBlock]);
+      return;
+    }
     Y.Y0 = ysm[0];
     Y.Y12 = pk2(ysm[1 * kFastBlock], ysm[2 * kFastBlock]); Y.Y34 = pk2(ysm[3 * kFastBlock], ysm[4 * kFastBlock]);
     Y.Y56 = pk2(ysm[5 * kFastBlock], ysm[6 * kFastBlock]); Y.Y78 = pk2(ysm[7 * kFastBlock], ysm[8 * kFastBlock]);
@@ -368,7 +389,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
   template <int J> __device__ __forceinline__ void commit_pair(uint32_t stale, uint32_t hi, const NodeLoad &L, const Basis &Y)
   {
     if (MODE == 3) grad_window_turn<J>(stale, hi, L.node);
-    commit_density<J>(stale, hi, L.td);
+    commit_density<J>(stale, hi, BAKED ? L.a.x : L.td);
     commit_colour<J>(stale, L, Y);
   }
   template <int J> __device__ __forceinline__ void commit_colour(uint32_t stale, const NodeLoad &L, const Basis &Y)
@@ -381,6 +402,10 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
     q2 = fma2(pk2(L.e.z, L.e.w), Y.Y78, q2);
     float ql, qh;
     upk2(q2, ql, qh);
+    if (BAKED) {   // b, e hold sh0..sh7 (pairs with Y01..Y67 above), s8 the last coefficient; R, G, B ride in chunk 0 behind the density
+      csm[(wA ? J : 7 - J) * kFastBlock] = make_float4(L.a.y, L.a.z, L.a.w, fmaf(L.s8, Y.Y0, ql + qh));
+      return;
+    }
     const float q = fmaf(L.a.w, Y.Y0, ql + qh);
     csm[(wA ? J : 7 - J) * kFastBlock] = make_float4(L.a.x, L.a.y, L.a.z, q);
   }
@@ -741,7 +766,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       }
       P.node2 = pair_node<2>(P.stale); P.node3 = pair_node<3>(P.stale);
       issue_pair<0>(P.stale, P.L0); issue_pair<1>(P.stale, P.L1);
-      P.L2.td = __ldg(S.dens + P.node2); P.L3.td = __ldg(S.dens + P.node3);
+      issue_density(P.node2, P.L2); issue_density(P.node3, P.L3);
       dirty = 0;
       geometry(P.g);
     };
@@ -750,7 +775,7 @@ template <int MODE, bool SPARSE, bool GREY> struct FastMarch
       if (!GREY) load_basis(Y);
       commit_pair<0>(P.stale, P.hi, P.L0, Y); commit_pair<1>(P.stale, P.hi, P.L1, Y);
       if (MODE == 3) { grad_window_turn<2>(P.stale, P.hi, P.node2); grad_window_turn<3>(P.stale, P.hi, P.node3); }
-      commit_density<2>(P.stale, P.hi, P.L2.td); commit_density<3>(P.stale, P.hi, P.L3.td);
+      commit_density<2>(P.stale, P.hi, BAKED ? P.L2.a.x : P.L2.td); commit_density<3>(P.stale, P.hi, BAKED ? P.L3.a.x : P.L3.td);
       issue_colour(P.node2, P.L2); issue_colour(P.node3, P.L3);   // in flight across the density lerps + expf chain
       const Sig sg = shade_sigma(P.g);
       commit_colour<2>(P.stale, P.L2, Y); commit_colour<3>(P.stale, P.L3, Y);

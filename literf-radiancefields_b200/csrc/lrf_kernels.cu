@@ -320,7 +320,7 @@ inline uint32_t tile_grid(uint32_t w, uint32_t h)
 // hardware's in-order block dispatch keeps the whole GPU on one compact band of the image, and that L2 locality is worth
 // more than the L1 locality or the finer load balance.
 // executed by all 32 lanes of a warp together (valid = the lane has a pixel): the sparse march votes among the lanes that run it
-template <bool SPARSE, bool GREY>
+template <bool SPARSE, bool GREY, bool BAKED = false>
 __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *etab, float *ysm, float4 *csm, uint32_t *__restrict__ out, uint32_t w,
                                              uint32_t h, uint32_t px, uint32_t py, bool valid, uint32_t *__restrict__ fb_count,
                                              uint32_t *__restrict__ fb_list)
@@ -334,7 +334,7 @@ __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *
     fb_list[atomicAdd(fb_count, 1u)] = py * w + px;
     return;
   }
-  FastMarch<0, SPARSE, GREY> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
+  FastMarch<0, SPARSE, GREY, BAKED> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
   fm.run(o, d, mask);
   uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
   if (fm.n_hit)
@@ -342,7 +342,7 @@ __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *
   out[(size_t)py * w + px] = pix;
 }
 
-template <bool SPARSE, bool GREY>
+template <bool SPARSE, bool GREY, bool BAKED = false>
 __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
                                                                  uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list)
 {
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(c
   load_exp_table(etab);
   uint32_t px, py;
   const bool valid = tile_pixel(w, h, px, py);
-  render_pixel<SPARSE, GREY>(S, etab, ysm, csm, out, w, h, px, py, valid, fb_count, fb_list);
+  render_pixel<SPARSE, GREY, BAKED>(S, etab, ysm, csm, out, w, h, px, py, valid, fb_count, fb_list);
 }
 
 __global__ void __launch_bounds__(kBlock) render_fallback_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h, int grey,
@@ -1467,6 +1467,7 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
     else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
   } else {
     if (grey) render_image_kernel<false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+    else if (S.rec) render_image_kernel<false, false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
     else render_image_kernel<false, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
   }
   render_fallback_kernel<<<148, kBlock, 0, st>>>(S, out_dev, w, h, grey, fb_count, fb_list);
