@@ -124,6 +124,133 @@ def io_case():
     return out
 
 
+# ---- backward pin: directional finite differences of the COMPILED REFERENCE's own loss -----------------------------------------
+# The reference's gradient is generated by Enzyme, which cannot be built here.  Its loss function can: RayGridLoss
+# (example_tracer.cpp:258-268) and TVRegularisation (:196-248, -O0 object) are executed from oracle/_ref.  A central difference of
+# the executed function along a direction v equals <grad, v> for ANY correct gradient — no restatement is involved on the
+# reference side.  The fixture stores, per ray, (L(g + h v) - L(g - h v)) / 2h from the reference and the rays for which that
+# quotient is a derivative at all: a ray whose shaded-sample count differs between g - h v, g and g + h v crossed the
+# `throughput < 0.1` break (a jump of the loss, ref :131) and is left out.
+BWD_CASES = {  # name -> (gs, density scale, view k, image size, greyscale)
+    "opaque": (16, 20.0, 2, 24, False),
+    "thin": (16, 2.0, 5, 24, False),
+    "grey": (16, 20.0, 1, 20, True),
+}
+BWD_H = 1.0 / 64.0                     # exact in fp32
+BWD_DIRS = ("all", "density", "colour")
+
+
+def fd_direction(gs, which, seed_k):
+    """direction over the gs^3 x 13 parameters, reproducible from the repo's own LCG (no numpy RNG stream involved)"""
+    u = libs.lcg_grid(gs, 1.0, seed=0x9E3779B97F4A7C15 ^ (0x1234567 * (seed_k + 1)))   # col 0: (u - .25), 1..3: u, 4: 1 + 2u, 5..: u - .5
+    v = np.empty_like(u)
+    v[:, 0] = (u[:, 0] + np.float32(0.25) - np.float32(0.5)) * np.float32(2.0)      # density: +-1
+    v[:, 1:4] = (u[:, 1:4] - np.float32(0.5)) * np.float32(0.125)                 # RGB: +-1/16
+    v[:, 4] = (u[:, 4] - np.float32(2.0)) * np.float32(0.0625)                     # sh0
+    v[:, 5:] = u[:, 5:] * np.float32(0.125)                                        # sh1..8
+    if which == "density":
+        v[:, 1:] = 0
+    elif which == "colour":
+        v[:, 0] = 0
+    return v
+
+
+def backward_fd_case():
+    from libs import u64p
+    out = {"h": np.array([BWD_H]), "cases": np.array(list(BWD_CASES)), "dirs": np.array(BWD_DIRS)}
+    for name, (gs, D, k, wh, grey) in BWD_CASES.items():
+        grid = libs.lcg_grid(gs, D)
+        Rf = RefScene(gs, grid)
+        vi, pi = Rf.set_cam(k, 7)
+        n = wh * wh
+        o, d = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        hits = []
+        ids = np.zeros(1024, np.uint64)
+        for pix in range(n):
+            Rf.R.ref_gen_ray(Rf.h, pix % wh, pix // wh, wh, wh, fp(o[pix]), fp(d[pix]))
+            m = Rf.R.ref_ray_hits(Rf.h, fp(o[pix]), fp(d[pix]), u64p(ids), 1024)
+            hits.append(ids[:m].copy())
+        # target colours from the repo LCG as well
+        big = libs.lcg_grid(8, 1.0, seed=0xABCDEF ^ (gs + k))[:, 1:4].reshape(-1)   # 1536 uniforms in [0, 1)
+        ref = np.ones((n, 4), np.float32)
+        ref[:, :3] = np.resize(big, n * 3).reshape(n, 3)
+        _, ns0, _, _ = Rf.render_debug(wh, wh, grey, 0)
+        out.update({name + "_gs": np.array([gs]), name + "_D": np.array([D]), name + "_wh": np.array([wh]), name + "_grey": np.array([int(grey)]),
+                    name + "_view_inv": vi, name + "_proj_inv": pi, name + "_o": o, name + "_d": d, name + "_ref": ref,
+                    name + "_n_hit": np.array([len(hh) for hh in hits], np.uint32)})
+
+        def losses():
+            L = np.zeros(n, np.float64)
+            for pix in range(n):
+                if hits[pix].size:
+                    L[pix] = Rf.R.ref_ray_loss(Rf.h, fp(ref[pix]), fp(o[pix]), fp(d[pix]), u64p(hits[pix]), hits[pix].size, int(grey))
+            return L
+
+        L0 = losses()
+        for di, which in enumerate(BWD_DIRS):
+            if grey and which == "colour":
+                continue
+            v = fd_direction(gs, which, di)
+            Rf.grid[:] = grid + np.float32(BWD_H) * v
+            Lp = losses()
+            _, nsp, _, _ = Rf.render_debug(wh, wh, grey, 0)
+            Rf.grid[:] = grid - np.float32(BWD_H) * v
+            Lm = losses()
+            _, nsm, _, _ = Rf.render_debug(wh, wh, grey, 0)
+            Rf.grid[:] = grid
+            has = np.array([hh.size > 0 for hh in hits])
+            # ... and a ray whose two one-sided quotients disagree crossed a kink of the loss inside [g - h v, g + h v] (a clamp of
+            # ref :181-184, the relu :170, |C - ref| :265): there the central quotient is not the derivative at g either.  Both
+            # filters use the reference's outputs only; they drop < 5 % of the rays.
+            smooth = np.abs((Lp - L0) - (L0 - Lm)) <= 2e-6 + 0.01 * np.abs(Lp - Lm)
+            kept = has & (nsp == ns0) & (nsm == ns0) & smooth
+            out["%s_%s_kept" % (name, which)] = kept
+            out["%s_%s_fd" % (name, which)] = np.where(kept, (Lp - Lm) / (2 * BWD_H), 0.0)
+        Rf.close()
+    if libs.have_ref("O0"):
+        gs = 8
+        grid = libs.lcg_grid(gs, 20.0)
+        Rf = RefScene(gs, grid, kind="O0", boxes=False)
+        v = fd_direction(gs, "density", 7)
+
+        def tv_total():
+            t = 0.0
+            for z in range(gs - 1):
+                for y in range(gs - 1):
+                    for x in range(gs - 1):
+                        t += float(Rf.R.ref_tv(Rf.h, x, y, z))
+            return t
+
+        hh = 1.0 / 256.0
+        Rf.grid[:] = grid + np.float32(hh) * v
+        tp = tv_total()
+        Rf.grid[:] = grid - np.float32(hh) * v
+        tm = tv_total()
+        out.update({"tv_gs": np.array([gs]), "tv_h": np.array([hh]), "tv_fd": np.array([(tp - tm) / (2 * hh)])})
+        Rf.close()
+    return out
+
+
+def bench_size_case():
+    """the bench's own size: 256^3 dense grid, orbit views of the 100-view bench orbit, a 32 x 32 frame = every 25th pixel centre of
+    the 800 x 800 frame ((i + .5) / 32 == (25 i + 12.5) / 800), opaque (D = 20) and thin (D = 2) density.  Octree build ~20 s."""
+    gs, wh, keep = 256, 32, 12
+    out = {"gs": gs, "wh": wh, "keep": keep, "views": np.array([0, 13, 37]), "n_views": 100, "Ds": np.array([20.0, 2.0])}
+    Rf = RefScene(gs, None)
+    for D in (20.0, 2.0):
+        Rf.grid[:] = libs.lcg_grid(gs, D)
+        for k in (0, 13, 37):
+            vi, pi = Rf.set_cam(k, 100)
+            nh, ns, rg, ids = Rf.render_debug(wh, wh, False, keep)
+            img = np.zeros(wh * wh, np.uint32)
+            Rf.R.ref_render(Rf.h, u32p(img), wh, wh, 0)
+            tag = "D%d_v%d" % (int(D), k)
+            out.update({"view_inv_" + tag: vi, "proj_inv_" + tag: pi, "n_hit_" + tag: nh.astype(np.uint16), "n_shaded_" + tag: ns.astype(np.uint16),
+                        "rgbtc_" + tag: rg, "ids_" + tag: ids.astype(np.int32), "pixels_" + tag: img})
+    Rf.close()
+    return out
+
+
 def main():
     assert libs.have_ref("O3"), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(OUT, exist_ok=True)
@@ -132,6 +259,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sparse_upsampled.npz"), **sparse_case())
     np.savez_compressed(os.path.join(OUT, "percell.npz"), **percell_case())
     np.savez_compressed(os.path.join(OUT, "io.npz"), **io_case())
+    np.savez_compressed(os.path.join(OUT, "backward_fd.npz"), **backward_fd_case())
+    np.savez_compressed(os.path.join(OUT, "bench256.npz"), **bench_size_case())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

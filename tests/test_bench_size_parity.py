@@ -1,0 +1,132 @@
+"""Parity at the BENCH's own sizes ("parity at the bench's own sizes is thin").
+
+  * tests/golden/bench256.npz — produced by the UNMODIFIED reference (oracle/_ref/libref_O3.so, tests/gen_golden.py::bench_size_case)
+    on the 256^3 grid of BASELINE.json configs[1]: three views of the bench's 100-view orbit, a 32 x 32 frame whose pixel centres
+    are every 25th pixel centre of the 800 x 800 bench frame, opaque (D = 20) and thin (D = 2) density.  Replayed against
+      - the CPU oracle (its large-grid exact DDA; not gpu), and
+      - the CUDA path through the C-ABI (gpu): parity taps on the 32 x 32 frame AND the pixels of the full 800 x 800 frame, from both
+        forward kernels (gather and TMA-staged), at the positions the fixture covers.
+  * configs[3] at full size (sparse 512^3): the CUDA hit lists of sampled rays, incl. a row of a 4K-aspect frame, against the oracle's
+    brute-force statement of IsRayHit + sort over the 13 M boxes (ref external/Octree/octree.h:449-488, 3278-3301).
+Bars: hit counts, shaded counts, voxel lists, transmittance bits exact; RGB within 1e-4; pixels within 1 LSB."""
+import os
+
+import numpy as np
+import pytest
+
+import libs
+from libs import dp, fp, i64p, u32p, u64p
+from scenes import OracleScene, cameras
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench256.npz")
+RGB_TOL = 1e-4
+
+
+def _tags(G):
+    for D in G["Ds"]:
+        for k in G["views"]:
+            yield float(D), int(k), "D%d_v%d" % (int(D), int(k))
+
+
+def _xyz_of_ids(ids, gs):
+    n = gs - 1
+    xyz = np.stack([ids % n, (ids // n) % n, ids // (n * n)], axis=-1).astype(np.int32)
+    return np.where(ids[..., None] >= 0, xyz, -1)
+
+
+def test_oracle_matches_reference_at_256(orc):
+    """one density scale on the CPU (the grid alone is 872 MB): the oracle's large-grid DDA against the reference's octree"""
+    G = np.load(GOLD)
+    gs, wh, keep = int(G["gs"]), int(G["wh"]), int(G["keep"])
+    S = OracleScene(gs, libs.lcg_grid(gs, 20.0))
+    for D, k, tag in _tags(G):
+        if D != 20.0:
+            continue
+        S.set_cam(G["view_inv_" + tag], G["proj_inv_" + tag])
+        n = wh * wh
+        nh, ns = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        rg, ids = np.zeros((n, 5), np.float32), np.zeros((n, keep), np.int64)
+        orc.orc_render_debug(S.h, wh, wh, 0, u32p(nh), u32p(ns), fp(rg), i64p(ids), keep)
+        assert np.array_equal(nh, G["n_hit_" + tag]) and np.array_equal(ns, G["n_shaded_" + tag])
+        assert np.array_equal(ids, G["ids_" + tag])
+        assert np.array_equal(rg.view(np.uint32), G["rgbtc_" + tag].view(np.uint32))
+    S.close()
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_at_256(pkg):
+    G = np.load(GOLD)
+    gs, wh, keep = int(G["gs"]), int(G["wh"]), int(G["keep"])
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.SetBoundingBox([0, 0, 0], [1, 1, 1])
+    W = 800
+    assert W % wh == 25 * wh % wh and W // wh == 25
+    sub = (25 * np.arange(wh) + 12)
+    for D in G["Ds"]:
+        t.fill_synthetic(float(D), 0)            # == libs.lcg_grid bit for bit (tests/test_gpu_configs.py)
+        for k in G["views"]:
+            tag = "D%d_v%d" % (int(D), int(k))
+            t.set_view_inv(G["view_inv_" + tag])
+            t.set_proj_inv(G["proj_inv_" + tag])
+            nh, ns, rg, vox = t.render_debug(wh, wh, False, keep)
+            assert np.array_equal(nh, G["n_hit_" + tag]), "hit counts differ on %d rays" % (nh != G["n_hit_" + tag]).sum()
+            assert np.array_equal(ns, G["n_shaded_" + tag]), "shaded counts differ on %d rays" % (ns != G["n_shaded_" + tag]).sum()
+            assert np.array_equal(vox.reshape(-1, keep, 3), _xyz_of_ids(G["ids_" + tag].astype(np.int64), gs))
+            ref = G["rgbtc_" + tag]
+            assert np.abs(rg[:, :3] - ref[:, :3]).max() <= RGB_TOL
+            assert np.array_equal(rg[:, 3].view(np.uint32), ref[:, 3].view(np.uint32)), "transmittance not bit-exact"
+            # the full bench frame, both forward kernels: the fixture's pixels sit at every 25th pixel centre
+            want = np.stack([(G["pixels_" + tag] >> s) & 255 for s in (0, 8, 16, 24)]).astype(np.int32)
+            for staged in (0, 1):
+                t.set_option("staged_render", staged)
+                img = np.zeros(W * W, np.uint32)
+                t.kernel2D_RayMarch(img, W, W)
+                got = img.reshape(W, W)[np.ix_(sub, sub)].reshape(-1)
+                ch = np.stack([(got >> s) & 255 for s in (0, 8, 16, 24)]).astype(np.int32)
+                assert np.abs(ch - want).max() <= 1, "kernel %d, %s" % (staged, tag)
+                assert np.array_equal(ch[3], want[3]) and (ch != want).mean() < 2e-3
+            t.set_option("staged_render", 0)
+    t.close()
+
+
+@pytest.mark.gpu
+def test_sparse512_hit_lists_against_oracle(pkg, orc):
+    """configs[3] at full size; replaces the CUDA-vs-CUDA comparison of round 1 for the hit lists"""
+    gs = 512
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.fill_synthetic(20.0, 2)
+    t.RebuildOctree()
+    xyz = t.get_boxes()
+    n = gs - 1
+    assert 0.095 < xyz.shape[0] / float(n ** 3) < 0.105
+    # boxes exactly as the reference stores them: float planes widened to double (example_tracer.h:77-83)
+    mn = (xyz.astype(np.float32) / np.float32(gs)).astype(np.float64)
+    mx = ((xyz + 1).astype(np.float32) / np.float32(gs)).astype(np.float64)
+    boxes = np.ascontiguousarray(np.concatenate([mn, mx], axis=1))
+    lin = xyz[:, 0].astype(np.int64) + xyz[:, 1].astype(np.int64) * n + xyz[:, 2].astype(np.int64) * n * n
+    rays_o, rays_d = [], []
+    o, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    S = OracleScene(8)                         # camera arithmetic only
+    for (w, h, aspect, k, nv, pix) in ((800, 800, 1.0, 2, 7, [(400, 400), (250, 333), (610, 222), (97, 701), (0, 0), (799, 799), (399, 123), (512, 640)]),
+                                       (3840, 2160, 16.0 / 9.0, 3, 8, [(x, 1080) for x in range(600, 3300, 300)])):
+        vi, pi = cameras(pkg, k, nv, aspect=aspect)
+        S.set_cam(vi, pi)
+        for (x, y) in pix:
+            orc.orc_gen_ray(S.h, x, y, w, h, fp(o), fp(d))
+            rays_o.append(o.copy()); rays_d.append(d.copy())
+    S.close()
+    ro, rd = np.stack(rays_o), np.stack(rays_d)
+    keep = 1024
+    nh, ns, rg, vox = t.trace_rays(ro, rd, False, keep)
+    ids = np.zeros(4096, np.uint64)
+    some = 0
+    for i in range(ro.shape[0]):
+        m = orc.orc_ray_hits_generic(3, dp(boxes), boxes.shape[0], dp(ro[i].astype(np.float64)), dp(rd[i].astype(np.float64)), u64p(ids), 4096)
+        assert m == nh[i], "ray %d: %d hits on the GPU, %d by the oracle" % (i, nh[i], m)
+        got = vox[i, :min(m, keep)].astype(np.int64)
+        assert np.array_equal(got[:, 0] + got[:, 1] * n + got[:, 2] * n * n, lin[ids[:min(m, keep)].astype(np.int64)]), "ray %d: order" % i
+        some += int(m > 0)
+    assert some >= 10
+    t.close()
