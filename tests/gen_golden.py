@@ -131,12 +131,11 @@ def io_case():
 # reference side.  The fixture stores, per ray, (L(g + h v) - L(g - h v)) / 2h from the reference and the rays for which that
 # quotient is a derivative at all: a ray whose shaded-sample count differs between g - h v, g and g + h v crossed the
 # `throughput < 0.1` break (a jump of the loss, ref :131) and is left out.
-BWD_CASES = {  # name -> (gs, density scale, view k, image size, greyscale)
-    "opaque": (16, 20.0, 2, 24, False),
-    "thin": (16, 2.0, 5, 24, False),
-    "grey": (16, 20.0, 1, 20, True),
-}
-BWD_H = 1.0 / 64.0                     # exact in fp32
+BWD_CASES = {  # name -> (gs, density scale, view k, image size, greyscale, 1 / step)
+    "opaque": (16, 20.0, 2, 24, False, 64),
+    "thin": (16, 2.0, 5, 24, False, 64),
+    "grey": (16, 20.0, 1, 20, True, 32),
+}   # steps are powers of two (exact in fp32), chosen where rounding noise of the fp32 loss over 2h and curvature balance
 BWD_DIRS = ("all", "density", "colour")
 
 
@@ -157,8 +156,10 @@ def fd_direction(gs, which, seed_k):
 
 def backward_fd_case():
     from libs import u64p
-    out = {"h": np.array([BWD_H]), "cases": np.array(list(BWD_CASES)), "dirs": np.array(BWD_DIRS)}
-    for name, (gs, D, k, wh, grey) in BWD_CASES.items():
+    out = {"cases": np.array(list(BWD_CASES)), "dirs": np.array(BWD_DIRS)}
+    for name, (gs, D, k, wh, grey, hdiv) in BWD_CASES.items():
+        BWD_H = 1.0 / hdiv
+        out[name + "_h"] = np.array([BWD_H])
         grid = libs.lcg_grid(gs, D)
         Rf = RefScene(gs, grid)
         vi, pi = Rf.set_cam(k, 7)
@@ -174,6 +175,9 @@ def backward_fd_case():
         big = libs.lcg_grid(8, 1.0, seed=0xABCDEF ^ (gs + k))[:, 1:4].reshape(-1)   # 1536 uniforms in [0, 1)
         ref = np.ones((n, 4), np.float32)
         ref[:, :3] = np.resize(big, n * 3).reshape(n, 3)
+        if grey:   # kernel2D_RayMarchGrad mixes the target to luminance first (ref :696-704); equal channels make that the identity (to 1 ulp)
+            ref[:, 1] = ref[:, 0]
+            ref[:, 2] = ref[:, 0]
         _, ns0, _, _ = Rf.render_debug(wh, wh, grey, 0)
         out.update({name + "_gs": np.array([gs]), name + "_D": np.array([D]), name + "_wh": np.array([wh]), name + "_grey": np.array([int(grey)]),
                     name + "_view_inv": vi, name + "_proj_inv": pi, name + "_o": o, name + "_d": d, name + "_ref": ref,

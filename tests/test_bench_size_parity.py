@@ -109,8 +109,9 @@ def test_sparse512_hit_lists_against_oracle(pkg, orc):
     rays_o, rays_d = [], []
     o, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
     S = OracleScene(8)                         # camera arithmetic only
-    for (w, h, aspect, k, nv, pix) in ((800, 800, 1.0, 2, 7, [(400, 400), (250, 333), (610, 222), (97, 701), (0, 0), (799, 799), (399, 123), (512, 640)]),
-                                       (3840, 2160, 16.0 / 9.0, 3, 8, [(x, 1080) for x in range(600, 3300, 300)])):
+    # the sphere (radius 0.288 at distance 1.3) covers ~220 pixels around the centre of the 800^2 frame, ~590 of the 4K frame
+    for (w, h, aspect, k, nv, pix) in ((800, 800, 1.0, 2, 7, [(400, 400), (250, 333), (510, 322), (297, 501), (0, 0), (799, 799), (399, 223), (512, 540), (560, 400)]),
+                                       (3840, 2160, 16.0 / 9.0, 3, 8, [(x, 1080) for x in range(1400, 2500, 100)] + [(1920, 600), (0, 0)])):
         vi, pi = cameras(pkg, k, nv, aspect=aspect)
         S.set_cam(vi, pi)
         for (x, y) in pix:
