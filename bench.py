@@ -137,10 +137,11 @@ def sharding():
     return mod
 
 
-def cameras(pkg, rank, world):
-    """weak scaling: a VIEWS*world-view orbit dealt round-robin, VIEWS views per rank"""
+def cameras(pkg, rank, world, strong=False):
+    """weak scaling: a VIEWS*world-view orbit dealt round-robin, VIEWS views per rank; strong: the VIEWS-view orbit dealt round-robin"""
     proj_inv = pkg.inverse4x4(pkg.perspective(45.0, ASPECT, 0.1, 100.0))
-    views = [pkg.inverse4x4(pkg.orbit_view(k, VIEWS * world)) for k in sharding().shard_views(VIEWS * world, rank, world)]
+    total = VIEWS if strong else VIEWS * world
+    views = [pkg.inverse4x4(pkg.orbit_view(k, total)) for k in sharding().shard_views(total, rank, world)]
     return proj_inv, views
 
 
@@ -198,6 +199,45 @@ def cpu_reference_rate(grid, steps, warmup, quiet=False):
     return rates, info
 
 
+
+def cpu_config1_rates():
+    """BASELINE.json configs[0], the reference as it runs today (main.cpp:49,67-68,99-102): 128^3 grid, 256x256 frames of the 7-view
+    orbit, its own kernel2D_RayMarch — timed for the build the reference ships (-O0, CMakeLists.txt:62) and for -O3, on a bounded
+    sample (views 0 and 3 at -O3, view 0 at -O0)."""
+    import libs
+    from libs import fp, u32p, np_view
+    gs, w = 128, 256
+    grid = lcg_grid(gs, DENSITY_SCALE)
+    try:
+        host_cores = len(os.sched_getaffinity(0))
+    except Exception:
+        host_cores = os.cpu_count() or 1
+    out = {"workload": "128^3 synthetic LCG grid (D=%g), 256x256 frames, orbit of 7 views (BASELINE.json configs[0])" % DENSITY_SCALE}
+    for kind, views in (("O3", (0, 3)), ("O0", (0,))):
+        if not libs.have_ref(kind):
+            continue
+        R = libs.ref(kind)
+        R.ref_set_omp_threads(host_cores)
+        h = R.ref_create()
+        R.ref_init_grid(h, gs)
+        np_view(R.ref_grid_ptr(h), gs ** 3 * 13)[:] = grid.ravel()
+        proj, view = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        R.ref_make_perspective(45.0, 1.0, 0.1, 100.0, fp(proj))
+        R.ref_set_proj_matrix(h, fp(proj))
+        img = np.zeros(w * w, np.uint32)
+        secs = 0.0
+        for k in views:
+            R.ref_make_orbit_view(k, 7, fp(view))
+            R.ref_set_view_matrix(h, fp(view))
+            t0 = time.perf_counter()
+            R.ref_render(h, u32p(img), w, w, 0)
+            secs += time.perf_counter() - t0
+        R.ref_destroy(h)
+        out[kind] = {"value": w * w * len(views) / secs / 1e6, "unit": "Mrays/s", "cores": int(R.ref_omp_threads()), "views_timed": list(views),
+                     "build": "-O0 -fopenmp (as shipped, CMakeLists.txt:62)" if kind == "O0" else "-O3 -fopenmp -ffp-contract=off"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -221,9 +261,10 @@ def run_reference(args):
     return 0
 
 
-def workload_config(world):
+def workload_config(world, strong=False):
+    vpg = (VIEWS + world - 1) // world if strong else VIEWS
     return {"workload": WORKLOADS[WORKLOAD]["text"], "name": WORKLOAD,
-            "grid": GS, "width": W, "height": H, "views_per_gpu": VIEWS, "rays_per_step_per_gpu": W * H * VIEWS,
+            "grid": GS, "width": W, "height": H, "views_per_gpu": vpg, "rays_per_step_per_gpu": W * H * vpg,
             "density_scale": DENSITY_SCALE, "parallelism": "views sharded over %d GPU(s), grid replica per GPU, no collective" % world,
             "l2": "inputs exceed L2: the %d MB grid is re-read by every view (L2 = 126 MB); no explicit flush needed" % (52 * GS ** 3 // 10 ** 6)}
 
@@ -238,6 +279,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the (extra) training-iteration measurement")
     ap.add_argument("--workload", default="render256", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): VIEWS views per GPU; strong: the VIEWS views of ONE orbit dealt over the GPUs")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the short sparse512 / hires512 measurements appended to extra")
     args = ap.parse_args()
     select_workload(args.workload)
     if args.workload != "render256":
@@ -274,7 +318,8 @@ def main():
         t.fill_synthetic(DENSITY_SCALE, FILL_MODE)
     if SPARSE:
         t.RebuildOctree()              # keeps the boxes whose centre density is > 0 (ref example_tracer.cpp:449-489)
-    proj_inv, views = cameras(pkg, rank, world)
+    strong = args.scaling == "strong"
+    proj_inv, views = cameras(pkg, rank, world, strong)
     t.set_proj_inv(proj_inv)
     frame = pkg.DeviceBuffer(t, W * H * 4)
 
@@ -313,7 +358,7 @@ def main():
     launches = t.launch_count() - l0
     clocks = sampler.stop(tc0, tc1)
     ms = max_over_ranks(ms)
-    rays_per_step = W * H * VIEWS * world
+    rays_per_step = W * H * (VIEWS if strong else VIEWS * world)
     value = rays_per_step * steps / (ms * 1e-3) / 1e6
 
     # ---- e2e: host API, camera h2d + frame d2h per view inside the timed region ----
@@ -348,7 +393,8 @@ def main():
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                 "kernel": "render_image_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "n_touched_nodes_mean": n_touched, "n_touched_sampled_views": len(sel), "peak_source": peak_src}
+                "n_touched_nodes_mean": n_touched, "n_touched_sampled_views": len(sel), "peak_source": peak_src,
+                "traffic_source": "from file: profiles/roofline_traffic.json (dram__bytes_read + dram__bytes_write of this kernel in a committed ncu --set full capture); not measured in this run"}
     if WORKLOAD != "render256":
         roofline["traffic"] = None     # the committed ncu capture is of the default workload
 
@@ -356,17 +402,27 @@ def main():
     if SPARSE:
         extra["boxes"] = int(t.box_count())
         extra["occupancy"] = t.box_count() / float((GS - 1) ** 3)
+    if WORKLOAD == "render256":
+        try:
+            extra["latency_mode"] = latency_bench(pkg, t, frame, rank, world, dist, max_over_ranks, barrier)
+        except Exception as e:
+            extra["latency_mode"] = {"error": repr(e)}
     if not args.no_train:
         try:
             extra["train"] = train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier)
         except Exception as e:  # the headline line must still be printed
             extra["train"] = {"error": repr(e)}
+    if WORKLOAD == "render256" and not args.no_extra_configs:
+        try:
+            extra["configs"] = other_configs(pkg, t, local, rank, world, max_over_ranks, barrier)
+        except Exception as e:
+            extra["configs"] = {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world), "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": VIEWS * 2 * 64, "d2h_bytes_per_step": VIEWS * W * H * 4, "steps": e2e_steps},
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world, strong), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": len(views) * 2 * 64, "d2h_bytes_per_step": len(views) * W * H * 4, "steps": e2e_steps},
         "gpu_launches": int(launches), "roofline": roofline, "extra": extra,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -386,6 +442,10 @@ def main():
                                                    "note": "GPU render of the sample frame vs the CPU arm's own output; RGB tolerance 1e-4 allows +-1 of 255"}
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+        try:
+            line["cpu_baseline"]["config1"] = cpu_config1_rates()
+        except Exception as e:
+            line["cpu_baseline"]["config1"] = {"error": repr(e)}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     if rank == 0:
@@ -394,6 +454,110 @@ def main():
         os.dup2(2, 1)
         dist.destroy_process_group()
     return 0
+
+
+
+def latency_bench(pkg, t, frame, rank, world, dist, max_over_ranks, barrier, reps=10):
+    """strong scaling of the render (SURVEY 8e latency mode): (a) ONE 800x800 frame split over the GPUs in row bands (the reference
+    splits the rows of a frame over its OpenMP threads, example_tracer.cpp:630), bands gathered on rank 0 — the only collective;
+    (b) the VIEWS views of one orbit dealt over the GPUs.  Times are max over ranks, CUDA events around the whole loop."""
+    shard = sharding()
+    view = pkg.inverse4x4(pkg.orbit_view(7, 100))
+    t.set_view_inv(view)
+    y0, y1 = shard.shard_rows(H, rank, world)
+    ftensor = None
+    if dist is not None:
+        import torch
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (W * H,), "typestr": "<i4", "data": (frame.ptr, False), "version": 2}
+        ftensor = torch.as_tensor(_Arr(), device="cuda")
+        ext = torch.cuda.ExternalStream(t.lib.lrf_stream(t.h))
+
+    def one_frame():
+        t.render_rows_dev_async(frame.ptr, W, H, y0, y1)
+        if ftensor is not None:
+            import torch
+            with torch.cuda.stream(ext):
+                shard.gather_frame(ftensor, H, W, dist)
+
+    for _ in range(3):
+        one_frame()
+    barrier()
+    t.timer_start()
+    for _ in range(reps):
+        one_frame()
+    ms_frame = max_over_ranks(t.timer_stop_ms()) / reps
+    barrier()
+    # check on rank 0: the assembled frame equals the frame one GPU renders alone
+    ok = None
+    if rank == 0:
+        host = np.zeros(W * H, np.uint32)
+        frame.download(host)
+        alone = np.zeros(W * H, np.uint32)
+        t.kernel2D_RayMarch(alone, W, H)
+        ok = bool(np.array_equal(host, alone))
+    # (b) one orbit of VIEWS views over all GPUs
+    mine = [pkg.inverse4x4(pkg.orbit_view(k, VIEWS)) for k in shard.shard_views(VIEWS, rank, world)]
+    for vi in mine[:3]:
+        t.set_view_inv(vi)
+        t.render_dev_async(frame.ptr, W, H)
+    barrier()
+    t.timer_start()
+    for vi in mine:
+        t.set_view_inv(vi)
+        t.render_dev_async(frame.ptr, W, H)
+    ms_orbit = max_over_ranks(t.timer_stop_ms())
+    barrier()
+    return {"scaling": "strong", "n_gpus": world,
+            "one_frame_ms": ms_frame, "one_frame_Mrays_per_s": W * H / ms_frame / 1e3, "one_frame_rows_per_gpu": y1 - y0,
+            "one_frame_collective": "row bands gathered on rank 0 (NCCL send/recv of %d-row bands)" % (y1 - y0) if world > 1 else "none (1 GPU)",
+            "one_frame_equals_single_gpu_frame": ok,
+            "orbit_views": VIEWS, "orbit_ms": ms_orbit, "orbit_Mrays_per_s": W * H * VIEWS / ms_orbit / 1e3}
+
+
+def other_configs(pkg, t0, local, rank, world, max_over_ranks, barrier):
+    """the larger configurations of BASELINE.json, short measurements in the default run so that the driver sees them: configs[4]
+    (dense 512^3 at 1920x1080 and 3840x2160, 8 views per GPU, view-sharded) and configs[3] (sparse 512^3, ~10 % occupancy, 800x800).
+    value = aggregate Mrays/s over the GPUs, device-timed, max over ranks."""
+    out = {}
+    t = pkg.RayMarcherExample(local)
+    gs = 512
+    t.InitGrid(gs)
+    t.SetBoundingBox([0, 0, 0], [1, 1, 1])
+    shard = sharding()
+
+    def run(name, w, h, aspect, n_views, reps=2):
+        proj_inv = pkg.inverse4x4(pkg.perspective(45.0, aspect, 0.1, 100.0))
+        views = [pkg.inverse4x4(pkg.orbit_view(k, n_views * world)) for k in shard.shard_views(n_views * world, rank, world)]
+        t.set_proj_inv(proj_inv)
+        fr = pkg.DeviceBuffer(t, w * h * 4)
+        for vi in views[:2]:
+            t.set_view_inv(vi)
+            t.render_dev_async(fr.ptr, w, h)
+        barrier()
+        t.sync()
+        t.timer_start()
+        for _ in range(reps):
+            for vi in views:
+                t.set_view_inv(vi)
+                t.render_dev_async(fr.ptr, w, h)
+        ms = max_over_ranks(t.timer_stop_ms())
+        barrier()
+        fr.free()
+        out[name] = {"value": w * h * n_views * world * reps / ms / 1e3, "unit": "Mrays/s", "ms_per_view": ms / (reps * n_views), "width": w, "height": h,
+                     "views_per_gpu": n_views, "n_gpus": world, "grid": gs, "workload": WORKLOADS[name]["text"]}
+
+    t.fill_synthetic(20.0, 0)
+    run("hires512_1080p", 1920, 1080, 16.0 / 9.0, 8)
+    run("hires512_4k", 3840, 2160, 16.0 / 9.0, 8)
+    t.fill_synthetic(20.0, 2)
+    t.RebuildOctree()
+    run("sparse512", 800, 800, 1.0, 8)
+    out["sparse512"]["boxes"] = int(t.box_count())
+    out["sparse512"]["occupancy"] = t.box_count() / float((gs - 1) ** 3)
+    t.close()
+    return out
 
 
 def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier, iters=20, batch=4096):

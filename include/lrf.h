@@ -88,9 +88,12 @@ void lrf_mat4_mul(const float a16[16], const float b16[16], float out16[16]);
 int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t width, uint32_t height, int greyscale);
 /* same, output left in DEVICE memory (out_dev), asynchronous on the context stream */
 int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t width, uint32_t height, int greyscale);
-/* The two calls above render dense colour grids of 8..512 nodes per axis with the TMA-staged kernel (lrf_staged.cuh) and
- * everything else (greyscale, sparse box sets, tiny grids) with the thread-per-ray gather kernel; option "staged_render" = 0
- * forces the latter.  Parity tap of the staged kernel: the frame and, per pixel, the number of samples it shaded before the
+/* rows [y0, y1) of the frame only, written into the full-frame buffer out_dev: one frame split over several GPUs in row bands
+ * (ref: kernel2D_RayMarch parallelises the rows of a frame, example_tracer.cpp:630) */
+int lrf_render_rows_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, int greyscale);
+/* lrf_render / lrf_render_dev_async use the thread-per-ray gather kernel; with option "staged_render" = 1 dense colour grids of
+ * 8..512 nodes per axis are rendered by the TMA-staged kernel (lrf_staged.cuh) instead (fewer L1 wavefronts, more instructions: slower
+ * on the bench workload).  Parity tap of the staged kernel: the frame and, per pixel, the number of samples it shaded before the
  * reference's `throughput < 0.1` break (ref example_tracer.cpp:131) — 0xffffffff where the pixel was handed to the exact
  * kernel (break too close to call on the approximate throughput, tie events, axis-aligned rays).  HOST arrays, may be NULL. */
 int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_host, uint32_t width, uint32_t height);

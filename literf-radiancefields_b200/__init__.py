@@ -49,6 +49,7 @@ SIGNATURES = {
     "lrf_mat4_mul": (None, [_c_fp, _c_fp, _c_fp]),
     "lrf_render": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
+    "lrf_render_rows_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_staged_debug": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "lrf_render_stats": (C.c_int, [_vp, _vp, C.c_int]),
     "lrf_params_touched": (C.c_int, [_vp]),
@@ -356,6 +357,10 @@ class RayMarcherExample:
 
     def render_dev_async(self, out_dev_ptr, width, height, greyscale=False):
         self._ck(self.lib.lrf_render_dev_async(self.h, out_dev_ptr, width, height, int(greyscale)))
+
+    def render_rows_dev_async(self, out_dev_ptr, width, height, y0, y1, greyscale=False):
+        """rows [y0, y1) of the frame into the full-frame device buffer (latency mode: row bands over GPUs)"""
+        self._ck(self.lib.lrf_render_rows_dev_async(self.h, out_dev_ptr, width, height, y0, y1, int(greyscale)))
 
     def render_staged_debug(self, width, height):
         """frame + per-pixel shaded-sample count of the TMA-staged kernel (0xffffffff: pixel rendered by the exact kernel)"""

@@ -601,6 +601,20 @@ int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt
   CK(cudaGetLastError());
   return 0;
 }
+// rows [y0, y1) of the frame into the full-frame buffer out_dev (latency mode: one frame split over several GPUs in row bands, the
+// way the reference splits the rows of a frame over its OpenMP threads, ref example_tracer.cpp:630); gather kernel
+int lrf_render_rows_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt, uint32_t y0, uint32_t y1, int grey)
+{
+  NEED_GRID(h);
+  if (w == 0 || hgt == 0 || y0 >= y1) return 0;
+  if (y1 > hgt) return fail("row band exceeds the frame");
+  if (ensure_fb(h, (size_t)w * hgt)) return 1;
+  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream, y0, y1);
+  h->launches += 2;
+  h->last_render_staged = 0;
+  CK(cudaGetLastError());
+  return 0;
+}
 // parity tap of the staged kernel: frame + per-pixel shaded-sample counts (0xffffffff where the exact kernel rendered the pixel), host buffers
 int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_host, uint32_t w, uint32_t hgt)
 {

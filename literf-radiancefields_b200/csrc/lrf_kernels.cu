@@ -342,16 +342,19 @@ __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *
   out[(size_t)py * w + px] = pix;
 }
 
+// Rows [y0, y0 + hb) of the w x h frame (the whole frame: y0 = 0, hb = h).  Row bands are how one frame is split over several GPUs
+// (latency mode; the reference splits the rows of a frame over its OpenMP threads, ref example_tracer.cpp:630).
 template <bool SPARSE, bool GREY, bool BAKED = false>
 __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
-                                                                 uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list)
+                                                                 uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb)
 {
   __shared__ uint64_t etab[32];
   __shared__ float ysm[9 * kFastBlock];
   __shared__ float4 csm[8 * kFastBlock];
   load_exp_table(etab);
   uint32_t px, py;
-  const bool valid = tile_pixel(w, h, px, py);
+  const bool valid = tile_pixel(w, hb, px, py);
+  py += y0;
   render_pixel<SPARSE, GREY, BAKED>(S, etab, ysm, csm, out, w, h, px, py, valid, fb_count, fb_list);
 }
 
@@ -1458,17 +1461,20 @@ inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) 
 
 // ------------------------------------------------------------------------------------------------
 void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, uint32_t *fb_count, uint32_t *fb_list,
-                         cudaStream_t st)
+                         cudaStream_t st, uint32_t y0, uint32_t y1)
 {
   cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
-  const dim3 g(tile_grid(w, h));
+  if (y1 > h) y1 = h;
+  if (y0 >= y1) return;
+  const uint32_t hb = y1 - y0;
+  const dim3 g(tile_grid(w, hb));
   if (S.occ) {
-    if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
-    else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+    if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
+    else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
   } else {
-    if (grey) render_image_kernel<false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
-    else if (S.rec) render_image_kernel<false, false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
-    else render_image_kernel<false, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list);
+    if (grey) render_image_kernel<false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
+    else if (S.rec) render_image_kernel<false, false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
+    else render_image_kernel<false, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
   }
   render_fallback_kernel<<<148, kBlock, 0, st>>>(S, out_dev, w, h, grey, fb_count, fb_list);
 }

@@ -21,6 +21,35 @@ def shard_views(n_views, rank, world):
     return list(range(rank, n_views, world))
 
 
+def shard_rows(height, rank, world, align=4):
+    """[y0, y1) of the row band of ONE frame that `rank` renders (latency mode).  Bands are multiples of `align` rows (a warp of the
+    render kernel covers an 8 x 4 pixel tile) except the last; every row belongs to exactly one rank; ranks may get an empty band."""
+    units = (height + align - 1) // align
+    base, extra = divmod(units, world)
+    u0 = rank * base + min(rank, extra)
+    u1 = u0 + base + (1 if rank < extra else 0)
+    return min(u0 * align, height), min(u1 * align, height)
+
+
+def gather_frame(frame, height, width, dist):
+    """latency mode: every rank has rendered its row band into its own full-frame tensor `frame` (uint32/int32 [height * width]);
+    rank 0 ends up with the complete frame.  One collective on the data path: a gather of the bands (all-gather into rank-ordered
+    slices when the bands are equal, point-to-point band copies otherwise)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return frame
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bands = [shard_rows(height, r, world) for r in range(world)]
+    if rank == 0:
+        reqs = [dist.irecv(frame[y0 * width:y1 * width], src=r) for r, (y0, y1) in enumerate(bands) if r != 0 and y1 > y0]
+        for q in reqs:
+            q.wait()
+    else:
+        y0, y1 = bands[rank]
+        if y1 > y0:
+            dist.send(frame[y0 * width:y1 * width], dst=0)
+    return frame
+
+
 def shard_rays(n_rays, rank, world):
     """[begin, end) of the contiguous slice of a packed ray batch that `rank` back-propagates"""
     base, extra = divmod(n_rays, world)

@@ -177,3 +177,27 @@ def test_fast_and_generic_march_agree(pkg):
             assert np.array_equal(a[2][:, 3].view(np.uint32), b[2][:, 3].view(np.uint32))
             assert np.abs(a[2][:, :3] - b[2][:, :3]).max() <= 2e-6
     t.close()
+
+
+def test_row_bands_tile_the_frame(pkg):
+    """latency mode: a frame rendered as row bands (lrf_render_rows_dev_async, one band per GPU) is the frame rendered at once"""
+    gs, w, h = 32, 70, 45
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.set_grid(libs.lcg_grid(gs, 20.0))
+    vi, pi = cameras(pkg, 2, 7)
+    t.set_view_inv(vi)
+    t.set_proj_inv(pi)
+    whole = np.zeros(w * h, np.uint32)
+    t.kernel2D_RayMarch(whole, w, h)
+    buf = pkg.DeviceBuffer(t, w * h * 4)
+    buf.upload(np.zeros(w * h, np.uint32))
+    for (y0, y1) in ((0, 12), (12, 16), (16, 44), (44, 45)):
+        t.render_rows_dev_async(buf.ptr, w, h, y0, y1)
+    got = np.zeros(w * h, np.uint32)
+    buf.download(got)
+    assert np.array_equal(got, whole)
+    with pytest.raises(pkg.LrfError):
+        t.render_rows_dev_async(buf.ptr, w, h, 40, 50)
+    buf.free()
+    t.close()

@@ -100,3 +100,52 @@ def test_shard_rays_partition():
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             assert max(e - b for b, e in cuts) - min(e - b for b, e in cuts) <= 1
+
+
+def _band_worker(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "1"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    import libs
+    from scenes import OracleScene, cameras
+    spec = importlib.util.spec_from_file_location("lrf_sharding", os.path.join(ROOT, "literf-radiancefields_b200", "sharding.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gs, w, h = 16, 40, 30                     # 30 rows: bands of 4-row units, the last one ragged
+    S = OracleScene(gs, libs.lcg_grid(gs, 20.0))
+    vi, pi = cameras(None, 3, 7)
+    S.set_cam(vi, pi)
+    full = S.render(w, h, False).astype(np.int64)
+    y0, y1 = mod.shard_rows(h, rank, world)
+    mine = np.full(w * h, -1, np.int64)       # this rank only "renders" its band
+    mine[y0 * w:y1 * w] = full[y0 * w:y1 * w]
+    frame = torch.from_numpy(mine)
+    mod.gather_frame(frame, h, w, dist)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "frame.npy"), frame.numpy())
+        np.save(os.path.join(out_dir, "full.npy"), full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_band_frame_gather(tmp_path, world):
+    """latency mode (one frame over several GPUs): bands tile the rows exactly once, rank 0 assembles the reference's frame"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lrf_sharding", os.path.join(ROOT, "literf-radiancefields_b200", "sharding.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for h in (1, 3, 4, 30, 800, 1080, 2160):
+        for wd in (1, 2, 3, 4, 8):
+            cover = np.zeros(h, np.int32)
+            for r in range(wd):
+                y0, y1 = mod.shard_rows(h, r, wd)
+                assert 0 <= y0 <= y1 <= h and (y0 % 4 == 0 or y0 == h)
+                cover[y0:y1] += 1
+            assert (cover == 1).all()
+    mp.spawn(_band_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert np.array_equal(np.load(os.path.join(str(tmp_path), "frame.npy")), np.load(os.path.join(str(tmp_path), "full.npy")))
