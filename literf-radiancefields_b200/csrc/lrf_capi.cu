@@ -68,6 +68,7 @@ struct lrf_ctx
   float dmax = 0.0f;
   uint32_t *st_stats = nullptr;       // 4 counters, see StagedArgs::stats
   int staged = 0;                     // option "staged_render": 1 = dense colour renders by the TMA-staged kernel (lrf_staged.cuh), 0 = by the gather kernel
+  int tv_sweep = 1;                   // option "tv_sweep": TV gradient by the TMA z-sweep kernel (lrf_tv.cuh) where it applies; 0 = the 8^3-tile kernel
   int baked = 0;                      // option "baked_records": 1 = the gather kernel reads the 64-byte node records instead of the planes (measured slower: 2.48 vs 2.30 ms per view)
   int staged_nw = 4;                  // option "staged_warps": consumer warps per CTA (4: 16x8 pixel tiles, 8: 16x16)
   int staged_box_w = 0, staged_box_h = 0;   // options "staged_box_w/h": override the footprint box (0 = from the camera)
@@ -163,7 +164,7 @@ static int fail_with_diag(lrf_ctx *h, const char *what_call, cudaError_t e)
   if (h->diag_host && h->diag_host[0]) {
     const uint32_t *d = h->diag_host;
     const char *what = d[0] == 1 ? "producer: ring never freed (q, qmin, p0)" : d[0] == 2 ? "producer: drain (plane, issued, parity)"
-                       : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : d[0] == 4 ? "producer: own TMA never completed (plane, q, parity)" : d[0] == 5 ? "dynamic shared memory is not 1024-byte aligned (address)" : "?";
+                       : d[0] == 3 ? "consumer: plane never arrived (qready, qmin, parity)" : d[0] == 4 ? "producer: own TMA never completed (plane, q, parity)" : d[0] == 5 ? "dynamic shared memory is not 1024-byte aligned (address)" : d[0] == 6 ? "tv_sweep_kernel: density plane never arrived (step, block, parity)" : "?";
     m += " | staged-render watchdog: " + std::string(what) + " block " + std::to_string(d[1]) + " thread " + std::to_string(d[2]) + " values " +
          std::to_string((int)d[3]) + " " + std::to_string((int)d[4]) + " " + std::to_string((int)d[5]) + " active-mask " + std::to_string(d[6]);
     m += " | dump:";
@@ -239,6 +240,37 @@ static void staged_box_need(const lrf_ctx *h, uint32_t w, uint32_t hgt, int tw, 
     }
 }
 
+// TV gradient of the nodes with z in [z0, z1) on stream st: the TMA z-sweep (lrf_tv.cuh) where it applies, else the 8^3-tile kernel
+static int ensure_diag(lrf_ctx *h)
+{
+  if (h->diag_host) return 0;
+  CK(cudaHostAlloc((void **)&h->diag_host, 128 * sizeof(uint32_t), cudaHostAllocMapped));
+  std::memset(h->diag_host, 0, 128 * sizeof(uint32_t));
+  CK(cudaHostGetDevicePointer((void **)&h->diag_dev, h->diag_host, 0));
+  return 0;
+}
+static bool tv_sweep_map(lrf_ctx *h, CUtensorMap &tm)
+{
+  if (!h->tv_sweep || h->gs < 64 || (h->gs % 32) != 0) return false;
+  lrf_encode_tiled_fn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t gs = (cuuint64_t)h->gs;
+  const cuuint64_t dims[3] = {gs, gs, gs}, strides[2] = {4 * gs, 4 * gs * gs};
+  const cuuint32_t box[3] = {36, 12, 1}, estr[3] = {1, 1, 1};
+  return enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->params, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static void tv_dispatch(lrf_ctx *h, int z0, int z1, int atomic, int max_blocks, bool whole, cudaStream_t st)
+{
+  CUtensorMap tm;
+  if (tv_sweep_map(h, tm) && ensure_diag(h) == 0) {
+    launch_tv_sweep(tm, h->gs, h->grad, z0, z1, atomic, h->diag_dev, st);
+    return;
+  }
+  if (whole) launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, st);
+  else launch_tv_grad_slab(h->gs, h->params, h->grad, z0, z1, atomic, max_blocks, st);
+}
+
 // the baked 64-byte node records both forward kernels can read (lrf_staged.cuh), rebuilt when the parameters changed.
 // 0 = ready, 1 = error, 2 = no room for the second copy of the grid (the caller renders from the planes)
 static int ensure_records(lrf_ctx *h)
@@ -288,11 +320,7 @@ static int staged_prepare(lrf_ctx *h, uint32_t w, uint32_t hgt, StagedArgs &T)
   T.slot_bytes = slot;
   T.err_sigma = 16.0f * 0x1p-24f * h->dmax;   // NaN / inf densities make every break ambiguous: the exact kernel then renders those rays
   T.stats = h->st_stats;
-  if (!h->diag_host) {
-    CK(cudaHostAlloc((void **)&h->diag_host, 128 * sizeof(uint32_t), cudaHostAllocMapped));
-    std::memset(h->diag_host, 0, 128 * sizeof(uint32_t));
-    CK(cudaHostGetDevicePointer((void **)&h->diag_dev, h->diag_host, 0));
-  }
+  if (ensure_diag(h)) return 1;
   T.diag = h->diag_dev;
   const cuuint64_t gs = (cuuint64_t)h->gs;
   const cuuint64_t dims[4] = {16, gs, gs, gs}, strides[3] = {64, 64 * gs, 64 * gs * gs};
@@ -967,8 +995,8 @@ int lrf_tv_grad(lrf_ctx *h)
   NEED_GRID(h);
   if (ensure_tv_tmp(h)) return 1;
   cudaEventRecord(h->ev0, h->stream);
-  launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
-  h->launches += (h->gs >= 8) ? 1 : 3;   // fused TV kernel (8^3 tiles), stage-by-stage below that
+  tv_dispatch(h, 0, h->gs, 0, 0, true, h->stream);
+  h->launches += (h->gs >= 8) ? 1 : 3;   // one TV kernel (z-sweep, or 8^3 tiles below 64^3), stage-by-stage below 8^3
   cudaEventRecord(h->ev1, h->stream);
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->t_tv, h->ev0, h->ev1);
@@ -1018,8 +1046,8 @@ int lrf_train_percell_async(lrf_ctx *h, int iter)
   // (Measured: running {TV -> Adam(density)} on the second stream beside Adam(colour) buys nothing — the TV kernel needs the
   // whole GPU to be fast (latency-bound shared-memory phases), throttled to a persistent grid it becomes the long pole:
   // 1.46 ms sequential vs 1.51-2.28 ms overlapped, tools/time_percell.py.)
-  launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, h->stream);
-  h->launches += (h->gs >= 8) ? 1 : 3;   // fused TV kernel (8^3 tiles), stage-by-stage below that
+  tv_dispatch(h, 0, h->gs, 0, 0, true, h->stream);
+  h->launches += (h->gs >= 8) ? 1 : 3;
   adam_launch(h, iter, 0, 1);
   CK(cudaGetLastError());
   return 0;
@@ -1042,7 +1070,7 @@ int lrf_rays_grad_tv_dev_async(lrf_ctx *h, size_t n, const float *o, const float
   CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
   int z0 = 0, z1 = h->gs;
   if (h->peer_world > 1) { const int zs = h->gs / h->peer_world; z0 = zs * h->peer_rank; z1 = z0 + zs; }
-  launch_tv_grad_slab(h->gs, h->params, h->grad, z0, z1, 1, 0, h->side);
+  tv_dispatch(h, z0, z1, 1, 0, false, h->side);
   h->launches++;
   CK(cudaEventRecord(h->ev_join, h->side));
   if (lrf_rays_grad_dev_async(h, n, o, d, ref, grey)) return 1;
@@ -1155,7 +1183,7 @@ int lrf_tv_grad_slab_async(lrf_ctx *h)
 {
   NEED_PEERS(h);
   const int zs = h->gs / h->peer_world;
-  launch_tv_grad_slab(h->gs, h->params, h->grad, zs * h->peer_rank, zs * (h->peer_rank + 1), 0, 0, h->stream);
+  tv_dispatch(h, zs * h->peer_rank, zs * (h->peer_rank + 1), 0, 0, false, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1319,6 +1347,7 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
   else if (s == "staged_render") h->staged = value ? 1 : 0;
   else if (s == "baked_records") h->baked = value ? 1 : 0;
+  else if (s == "tv_sweep") h->tv_sweep = value ? 1 : 0;
   else if (s == "staged_warps") { if (value != 4 && value != 8) return fail("staged_warps must be 4 or 8"); h->staged_nw = value; }
   else if (s == "staged_box_w") h->staged_box_w = value;
   else if (s == "staged_box_h") h->staged_box_h = value;

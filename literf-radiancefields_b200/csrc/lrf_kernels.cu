@@ -12,6 +12,7 @@
 #include "lrf_fast.cuh"
 #include "lrf_wray.cuh"
 #include "lrf_staged.cuh"
+#include "lrf_tv.cuh"
 
 namespace lrf {
 
@@ -1565,6 +1566,12 @@ void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_i
   SceneDev S{};
   for (int i = 0; i < 16; i++) S.proj_inv[i] = proj_inv_host16[i];
   gen_rays_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, view_inv_dev, picks, w, h, o, d, S);
+}
+void launch_tv_sweep(const CUtensorMap &tm, int gs, float *gdens, int z_begin, int z_end, int atomic, uint32_t *diag, cudaStream_t st)
+{
+  if (z_end <= z_begin) return;
+  const int chunks = (z_end - z_begin + kSwZChunk - 1) / kSwZChunk;
+  tv_sweep_kernel<<<(gs / kSwX) * (gs / kSwY) * chunks, 256, 0, st>>>(tm, gs, gdens, z_begin, z_end, atomic, diag);
 }
 void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float *tmp_g, cudaStream_t st)
 {

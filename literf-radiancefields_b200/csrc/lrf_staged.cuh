@@ -108,6 +108,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
   __syncwarp();
 }
+// the same for ONE calling thread (the caller publishes the result with a block / warp barrier)
+__device__ __forceinline__ void mbar_wait_one(uint32_t bar, uint32_t parity, uint32_t *diag, uint32_t code, uint32_t a, uint32_t b)
+{
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > kStWatchdogCycles) staged_die(diag, code, a, b, parity);
+}
 // non-blocking, same answer in every lane
 __device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity)
 {

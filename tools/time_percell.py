@@ -24,3 +24,17 @@ tm("adam dense moments", lambda: t.optimizerStep(1))
 tm("percell fused call", lambda: t._ck(t.lib.lrf_train_percell_async(t.h, 3)))
 tm("adam_zero_async", lambda: t._ck(t.lib.lrf_adam_zero_async(t.h, 4)))
 tm("zero_grad_async", lambda: t.zero_grad_async())
+# A/B of the TV kernels on the same box, and their agreement
+for sweep in (1, 0):
+    t.set_option("tv_sweep", sweep)
+    tm("tv_grad tv_sweep=%d" % sweep, lambda: t.kernel2D_TVGrad())
+    tm("percell fused tv_sweep=%d" % sweep, lambda: t._ck(t.lib.lrf_train_percell_async(t.h, 5)))
+t.fill_synthetic(20.0, 0)
+res = {}
+for sweep in (1, 0):
+    t.set_option("tv_sweep", sweep)
+    t.zeroGrad()
+    t.kernel2D_TVGrad()
+    res[sweep] = t.get_grad()[:, 0].astype(np.float64)
+d = np.abs(res[1] - res[0])
+print("tv sweep vs tile kernel: max abs diff %.3e, max |g| %.3e, nonzero %d" % (d.max(), np.abs(res[0]).max(), int((res[0] != 0).sum())))
