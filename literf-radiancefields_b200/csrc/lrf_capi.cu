@@ -68,6 +68,8 @@ struct lrf_ctx
   float dmax = 0.0f;
   uint32_t *st_stats = nullptr;       // 4 counters, see StagedArgs::stats
   int staged = 0;                     // option "staged_render": 1 = dense colour renders by the TMA-staged kernel (lrf_staged.cuh), 0 = by the gather kernel
+  int tv_blocks_per_sm = 2;           // option "tv_blocks_per_sm": resident TV blocks per SM while it overlaps the colour Adam pass (0 = no cap)
+  int percell_overlap = 1;            // option "percell_overlap": lrf_train_percell_async runs {TV -> Adam(density)} beside Adam(colour) on two streams
   int tv_sweep = 1;                   // option "tv_sweep": TV gradient by the TMA z-sweep kernel (lrf_tv.cuh) where it applies; 0 = the 8^3-tile kernel
   int baked = 0;                      // option "baked_records": 1 = the gather kernel reads the 64-byte node records instead of the planes (measured slower: 2.48 vs 2.30 ms per view)
   int staged_nw = 4;                  // option "staged_warps": consumer warps per CTA (4: 16x8 pixel tiles, 8: 16x16)
@@ -256,15 +258,15 @@ static bool tv_sweep_map(lrf_ctx *h, CUtensorMap &tm)
   if (!enc) return false;
   const cuuint64_t gs = (cuuint64_t)h->gs;
   const cuuint64_t dims[3] = {gs, gs, gs}, strides[2] = {4 * gs, 4 * gs * gs};
-  const cuuint32_t box[3] = {36, 12, 1}, estr[3] = {1, 1, 1};
+  const cuuint32_t box[3] = {40, 12, 1}, estr[3] = {1, 1, 1};   // kSwDX x kSwDY of lrf_tv.cuh
   return enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->params, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-static void tv_dispatch(lrf_ctx *h, int z0, int z1, int atomic, int max_blocks, bool whole, cudaStream_t st)
+static void tv_dispatch(lrf_ctx *h, int z0, int z1, int atomic, int max_blocks, bool whole, cudaStream_t st, int blocks_per_sm = 0)
 {
   CUtensorMap tm;
   if (tv_sweep_map(h, tm) && ensure_diag(h) == 0) {
-    launch_tv_sweep(tm, h->gs, h->grad, z0, z1, atomic, h->diag_dev, st);
+    launch_tv_sweep(tm, h->gs, h->grad, z0, z1, atomic, h->diag_dev, st, blocks_per_sm);
     return;
   }
   if (whole) launch_tv_grad(h->gs, h->params, h->grad, h->tv_tmp, h->tv_tmp + h->N, st);
@@ -433,7 +435,13 @@ int lrf_create(int device, lrf_ctx **out)
   lrf_ctx *h = new lrf_ctx();
   h->device = device;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  {
+    // the second stream carries the light kernels that run BESIDE an HBM-bound one (the TV gradient next to Adam or next to the ray
+    // backward): highest priority, so that its blocks are placed as soon as an SM has room instead of behind the other kernel's queue
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, greatest));
+  }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaMalloc(&h->flags, 32 * sizeof(uint32_t)));
@@ -1043,9 +1051,23 @@ int lrf_train_percell_async(lrf_ctx *h, int iter)
 {
   NEED_GRID(h);
   if (ensure_tv_tmp(h)) return 1;
-  // (Measured: running {TV -> Adam(density)} on the second stream beside Adam(colour) buys nothing — the TV kernel needs the
-  // whole GPU to be fast (latency-bound shared-memory phases), throttled to a persistent grid it becomes the long pole:
-  // 1.46 ms sequential vs 1.51-2.28 ms overlapped, tools/time_percell.py.)
+  // Measured at 256^3 (tools/time_percell.py): the 8^3-tile TV kernel beside Adam bought nothing (1.41 ms either way: it needs the whole
+  // GPU to be fast); the z-sweep kernel does — 1.35 ms in sequence, 1.27 ms overlapped, 1.24 ms with its grid capped at 2 blocks per SM.
+  if (h->percell_overlap && h->gs >= 64) {
+    // {TV -> Adam(density plane)} beside Adam(colour planes) on the second stream: the z-sweep TV kernel is light enough on the SMs
+    // (32 registers, 18 KB of shared memory, no index arithmetic) to hide behind the HBM-bound colour pass
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (h->percell_overlap == 2) adam_launch(h, iter, 2, 1);          // order experiment: the colour pass queued first
+    tv_dispatch(h, 0, h->gs, 0, 0, true, h->side, h->tv_blocks_per_sm);
+    h->launches++;
+    adam_launch(h, iter, 1, 1, h->side);
+    CK(cudaEventRecord(h->ev_join, h->side));
+    if (h->percell_overlap != 2) adam_launch(h, iter, 2, 1);
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    CK(cudaGetLastError());
+    return 0;
+  }
   tv_dispatch(h, 0, h->gs, 0, 0, true, h->stream);
   h->launches += (h->gs >= 8) ? 1 : 3;
   adam_launch(h, iter, 0, 1);
@@ -1348,6 +1370,8 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   else if (s == "staged_render") h->staged = value ? 1 : 0;
   else if (s == "baked_records") h->baked = value ? 1 : 0;
   else if (s == "tv_sweep") h->tv_sweep = value ? 1 : 0;
+  else if (s == "percell_overlap") h->percell_overlap = value;
+  else if (s == "tv_blocks_per_sm") h->tv_blocks_per_sm = value;
   else if (s == "staged_warps") { if (value != 4 && value != 8) return fail("staged_warps must be 4 or 8"); h->staged_nw = value; }
   else if (s == "staged_box_w") h->staged_box_w = value;
   else if (s == "staged_box_h") h->staged_box_h = value;

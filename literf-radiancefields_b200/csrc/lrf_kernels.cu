@@ -8,6 +8,7 @@
 // One thread per ray; a warp covers an 8x4 pixel tile so that its 32 rays walk neighbouring voxels.
 // Built with -fmad=false (see lrf_device.cuh): decision-critical arithmetic is IEEE op-for-op the
 // reference's; explicit fmaf() only on the colour path (RGB tolerance 1e-4).
+#include <algorithm>
 #include "lrf_kernels.cuh"
 #include "lrf_fast.cuh"
 #include "lrf_wray.cuh"
@@ -1567,11 +1568,14 @@ void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_i
   for (int i = 0; i < 16; i++) S.proj_inv[i] = proj_inv_host16[i];
   gen_rays_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, view_inv_dev, picks, w, h, o, d, S);
 }
-void launch_tv_sweep(const CUtensorMap &tm, int gs, float *gdens, int z_begin, int z_end, int atomic, uint32_t *diag, cudaStream_t st)
+void launch_tv_sweep(const CUtensorMap &tm, int gs, float *gdens, int z_begin, int z_end, int atomic, uint32_t *diag, cudaStream_t st, int blocks_per_sm)
 {
   if (z_end <= z_begin) return;
   const int chunks = (z_end - z_begin + kSwZChunk - 1) / kSwZChunk;
-  tv_sweep_kernel<<<(gs / kSwX) * (gs / kSwY) * chunks, 256, 0, st>>>(tm, gs, gdens, z_begin, z_end, atomic, diag);
+  const int n_work = (gs / kSwX) * (gs / kSwY) * chunks;
+  // blocks_per_sm > 0: the kernel runs beside an HBM-bound one and must leave it room on every SM: a persistent grid of that many blocks
+  const int grid = blocks_per_sm > 0 ? std::min(n_work, 148 * blocks_per_sm) : n_work;
+  tv_sweep_kernel<<<grid, 256, 0, st>>>(tm, gs, gdens, z_begin, z_end, atomic, diag);
 }
 void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float *tmp_g, cudaStream_t st)
 {

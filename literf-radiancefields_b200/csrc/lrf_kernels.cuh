@@ -60,9 +60,10 @@ void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_i
                      float *o, float *d, cudaStream_t st);
 // per-cell
 void launch_tv_grad(int gs, const float *dens, float *gdens, float *tmp_v, float *tmp_g, cudaStream_t st);
-// z-sweep TV gradient over TMA-fed density planes (lrf_tv.cuh): tm = 3-D tensor map over the density plane array with box {36, 12, 1};
+// z-sweep TV gradient over TMA-fed density planes (lrf_tv.cuh): tm = 3-D tensor map over the density plane array with box {40, 12, 1};
 // gs a multiple of 32; nodes with z in [z_begin, z_end); diag = host-mapped watchdog record (may be null)
-void launch_tv_sweep(const CUtensorMap &tm, int gs, float *gdens, int z_begin, int z_end, int atomic, uint32_t *diag, cudaStream_t st);
+void launch_tv_sweep(const CUtensorMap &tm, int gs, float *gdens, int z_begin, int z_end, int atomic, uint32_t *diag, cudaStream_t st,
+                     int blocks_per_sm = 0);   // > 0: cap the resident blocks per SM (when it shares the GPU with an HBM-bound kernel)
 void launch_adam(float *p, float *g, float *V, float *S, size_t off, size_t count, float lr, float beta1, float beta2, float eps,
                  double om_b1, double om_b2, int zero_grad, cudaStream_t st);
 void launch_fill(float *p, size_t count, float v, cudaStream_t st);

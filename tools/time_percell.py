@@ -28,7 +28,14 @@ tm("zero_grad_async", lambda: t.zero_grad_async())
 for sweep in (1, 0):
     t.set_option("tv_sweep", sweep)
     tm("tv_grad tv_sweep=%d" % sweep, lambda: t.kernel2D_TVGrad())
-    tm("percell fused tv_sweep=%d" % sweep, lambda: t._ck(t.lib.lrf_train_percell_async(t.h, 5)))
+    for ov in (2, 1, 0):
+        t.set_option("percell_overlap", ov)
+        tm("percell fused tv_sweep=%d overlap=%d" % (sweep, ov), lambda: t._ck(t.lib.lrf_train_percell_async(t.h, 5)), n=10)
+t.set_option("tv_sweep", 1); t.set_option("percell_overlap", 1)
+for bps in (0, 2, 3, 4, 5, 6):
+    t.set_option("tv_blocks_per_sm", bps)
+    tm("percell overlap, TV blocks/SM cap %d" % bps, lambda: t._ck(t.lib.lrf_train_percell_async(t.h, 5)), n=10)
+t.set_option("tv_blocks_per_sm", 0)
 t.fill_synthetic(20.0, 0)
 res = {}
 for sweep in (1, 0):
