@@ -15,7 +15,7 @@ interleaved over ranks): per-GPU work fixed => "scaling": "weak", no data-path c
   e2e       same metric through the public host API (RayMarcherExample.kernel2D_RayMarch == lrf_render):
             per view the camera goes host->device and the finished frame device->pinned host, inside the
             timed region.
-  roofline  dominant kernel render_image_kernel: algorithmic bytes per launch = 52 B x (distinct grid nodes
+  roofline  dominant kernel render_lean_kernel (lrf_lean.cuh): algorithmic bytes per launch = 52 B x (distinct grid nodes
             read by shaded samples of the view, counted on the device) + 4 B x rays, / mean launch time.
   cpu_baseline  the reference's kernel2D_RayMarch compiled from /root/reference (oracle/_ref/libref_O3.so,
             -O3 -fopenmp -ffp-contract=off) on the same grid + camera, bounded sample (a 96x96 frame of view 0).
@@ -123,7 +123,7 @@ def ncu_traffic():
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("render_image_kernel", {}).get("dram_bytes_per_launch")
+            return json.load(open(p)).get("render_lean_kernel", {}).get("dram_bytes_per_launch")
         except Exception:
             pass
     return None
@@ -392,7 +392,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                "kernel": "render_image_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "render_lean_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "n_touched_nodes_mean": n_touched, "n_touched_sampled_views": len(sel), "peak_source": peak_src,
                 "traffic_source": "from file: profiles/roofline_traffic.json (dram__bytes_read + dram__bytes_write of this kernel in a committed ncu --set full capture); not measured in this run"}
     if WORKLOAD != "render256":

@@ -97,6 +97,11 @@ int lrf_render_rows_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t width, uin
  * reference's `throughput < 0.1` break (ref example_tracer.cpp:131) — 0xffffffff where the pixel was handed to the exact
  * kernel (break too close to call on the approximate throughput, tie events, axis-aligned rays).  HOST arrays, may be NULL. */
 int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_host, uint32_t width, uint32_t height);
+/* Dense colour frames are rendered by the register-window march (lrf_lean.cuh; option "lean_render" = 0 selects the older gather
+ * kernel).  Its parity tap: the frame, per pixel the number of samples shaded before the reference's `throughput < 0.1` break
+ * (ref example_tracer.cpp:131; 0xffffffff where the pixel took the generic fallback) and the final transmittance (bits comparable
+ * with lrf_render_debug's).  HOST arrays, may be NULL.  Dense box sets only. */
+int lrf_render_lean_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_host, float *thr_host, uint32_t width, uint32_t height);
 /* counters since the last reset: [0] rays re-rendered by the exact kernel because the break was too close to call,
  * [1] other rays sent there, [2] pixel tiles whose footprint did not fit the staged box, [3] 1 if the last render was staged */
 int lrf_render_stats(lrf_ctx *h, uint32_t out4[4], int reset);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "lrf_render_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_rows_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_staged_debug": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
+    "lrf_render_lean_debug": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "lrf_render_stats": (C.c_int, [_vp, _vp, C.c_int]),
     "lrf_params_touched": (C.c_int, [_vp]),
     "lrf_render_debug": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, _c_u32p, _c_u32p, _c_fp, _c_i32p, C.c_uint32]),
@@ -368,6 +369,14 @@ class RayMarcherExample:
         ns = np.zeros(width * height, np.uint32)
         self._ck(self.lib.lrf_render_staged_debug(self.h, out.ctypes.data, ns.ctypes.data, width, height))
         return out, ns
+
+    def render_lean_debug(self, width, height):
+        """frame, per-pixel shaded-sample count (0xffffffff: generic fallback) and final transmittance of the register-window march"""
+        out = np.zeros(width * height, np.uint32)
+        ns = np.zeros(width * height, np.uint32)
+        thr = np.zeros(width * height, np.float32)
+        self._ck(self.lib.lrf_render_lean_debug(self.h, out.ctypes.data, ns.ctypes.data, thr.ctypes.data, width, height))
+        return out, ns, thr
 
     def render_stats(self, reset=False):
         """[ambiguous-break rays, other rays sent to the exact kernel, tiles that did not fit the staged box, last render staged?]"""

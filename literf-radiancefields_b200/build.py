@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "liblrf_b200.so")
 SOURCES = ["lrf_kernels.cu", "lrf_capi.cu"]
-HEADERS = ["lrf_device.cuh", "lrf_kernels.cuh", "lrf_fast.cuh", "lrf_wray.cuh", "lrf_staged.cuh", "lrf_tv.cuh", os.path.join("..", "..", "include", "lrf.h")]
+HEADERS = ["lrf_device.cuh", "lrf_kernels.cuh", "lrf_fast.cuh", "lrf_wray.cuh", "lrf_staged.cuh", "lrf_tv.cuh", "lrf_lean.cuh", os.path.join("..", "..", "include", "lrf.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -67,6 +67,7 @@ struct lrf_ctx
   float *dmax_dev = nullptr;          // largest |density| of the baked grid (device), and its host copy
   float dmax = 0.0f;
   uint32_t *st_stats = nullptr;       // 4 counters, see StagedArgs::stats
+  int lean = 1;                       // option "lean_render": dense colour frames by the register-window march (lrf_lean.cuh); 0 = FastMarch gather kernel
   int staged = 0;                     // option "staged_render": 1 = dense colour renders by the TMA-staged kernel (lrf_staged.cuh), 0 = by the gather kernel
   int tv_blocks_per_sm = 2;           // option "tv_blocks_per_sm": resident TV blocks per SM while it overlaps the colour Adam pass (0 = no cap)
   int percell_overlap = 1;            // option "percell_overlap": lrf_train_percell_async runs {TV -> Adam(density)} beside Adam(colour) on two streams
@@ -359,8 +360,8 @@ static int render_dispatch(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t h
     if (r == 1) return 1;
     if (r == 0) S.rec = h->rec;
   }
-  launch_render_image(S, out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream);
-  h->launches += 2;   // render_image_kernel + render_fallback_kernel
+  launch_render_image(S, out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream, 0, 0xffffffffu, h->lean);
+  h->launches += 2;   // render_lean_kernel / render_image_kernel + render_fallback_kernel
   return 0;
 }
 
@@ -645,7 +646,7 @@ int lrf_render_rows_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_
   if (w == 0 || hgt == 0 || y0 >= y1) return 0;
   if (y1 > hgt) return fail("row band exceeds the frame");
   if (ensure_fb(h, (size_t)w * hgt)) return 1;
-  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream, y0, y1);
+  launch_render_image(scene_of(h), out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream, y0, y1, h->lean);
   h->launches += 2;
   h->last_render_staged = 0;
   CK(cudaGetLastError());
@@ -669,6 +670,27 @@ int lrf_render_staged_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_h
   if (out_host) CKD(h, cudaMemcpyAsync(out_host, frame, bytes, cudaMemcpyDeviceToHost, h->stream));
   if (n_shaded_host) CKD(h, cudaMemcpyAsync(n_shaded_host, tap, bytes, cudaMemcpyDeviceToHost, h->stream));
   return sync_with_diag(h);
+}
+// parity tap of the register-window march (lrf_lean.cuh): frame + per-pixel shaded-sample count (0xffffffff where the pixel went to the
+// generic fallback) + final transmittance, host buffers.  Dense colour grids only.
+int lrf_render_lean_debug(lrf_ctx *h, uint32_t *out_host, uint32_t *n_shaded_host, float *thr_host, uint32_t w, uint32_t hgt)
+{
+  NEED_GRID(h);
+  if (w == 0 || hgt == 0) return 0;
+  if (!h->dense) return fail("lrf_render_lean_debug: dense box sets only");
+  const size_t bytes = (size_t)w * hgt * 4;
+  if (ensure_stage(h, 3 * bytes)) return 1;
+  if (ensure_fb(h, (size_t)w * hgt)) return 1;
+  uint32_t *frame = (uint32_t *)h->stage, *tap = frame + (size_t)w * hgt;
+  float *thr = (float *)(tap + (size_t)w * hgt);
+  launch_render_image(scene_of(h), frame, w, hgt, 0, h->fb, h->fb + kFbHeader, h->stream, 0, 0xffffffffu, 1, tap, thr);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  if (out_host) CK(cudaMemcpyAsync(out_host, frame, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (n_shaded_host) CK(cudaMemcpyAsync(n_shaded_host, tap, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (thr_host) CK(cudaMemcpyAsync(thr_host, thr, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 // counters of the staged render since the last reset: [0] rays re-rendered by the exact kernel because the throughput break was too close
 // to call, [1] other rays sent there, [2] tiles whose footprint did not fit the staged box, [3] 1 if the last render used the staged kernel
@@ -1368,6 +1390,7 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   if (s == "force_generic_march") h->force_generic = value ? 1 : 0;
   else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
   else if (s == "staged_render") h->staged = value ? 1 : 0;
+  else if (s == "lean_render") h->lean = value ? 1 : 0;
   else if (s == "baked_records") h->baked = value ? 1 : 0;
   else if (s == "tv_sweep") h->tv_sweep = value ? 1 : 0;
   else if (s == "percell_overlap") h->percell_overlap = value;

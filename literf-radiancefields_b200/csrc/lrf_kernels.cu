@@ -11,6 +11,7 @@
 #include <algorithm>
 #include "lrf_kernels.cuh"
 #include "lrf_fast.cuh"
+#include "lrf_lean.cuh"
 #include "lrf_wray.cuh"
 #include "lrf_staged.cuh"
 #include "lrf_tv.cuh"
@@ -358,6 +359,36 @@ __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(c
   const bool valid = tile_pixel(w, hb, px, py);
   py += y0;
   render_pixel<SPARSE, GREY, BAKED>(S, etab, ysm, csm, out, w, h, px, py, valid, fb_count, fb_list);
+}
+
+// Dense colour frames: the register-window march of lrf_lean.cuh (same decisions as FastMarch, bit for bit; fewer instructions and
+// L1 wavefronts per sample).  tap_n / tap_thr (TAPS): per-pixel shaded-sample count and final transmittance for the parity tests
+// (0xffffffff / NaN where the pixel went to the fallback list).
+template <bool TAPS>
+__global__ void __launch_bounds__(kBlock, LRF_LEAN_MINB) render_lean_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
+                                                                            uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb,
+                                                                            uint32_t *__restrict__ tap_n, float *__restrict__ tap_thr)
+{
+  __shared__ uint64_t etab[32];
+  load_exp_table(etab);
+  uint32_t px, py;
+  if (!tile_pixel(w, hb, px, py)) return;
+  py += y0;
+  float o[3], d[3];
+  gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
+  const size_t pixel = (size_t)py * w + px;
+  if (!fast_path_ok(d)) {
+    fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)pixel;
+    if (TAPS) { tap_n[pixel] = 0xffffffffu; tap_thr[pixel] = __int_as_float(0x7fc00000); }
+    return;
+  }
+  LeanMarch<TAPS> lm(S, etab);
+  lm.run(o, d);
+  uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
+  if (lm.any_hit)
+    pix = pack_color(lm_clamp(lm.col[0], 0.0f, 1.0f), lm_clamp(lm.col[1], 0.0f, 1.0f), lm_clamp(lm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
+  out[pixel] = pix;
+  if (TAPS) { tap_n[pixel] = lm.n_shaded; tap_thr[pixel] = lm.thr; }
 }
 
 __global__ void __launch_bounds__(kBlock) render_fallback_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h, int grey,
@@ -1463,14 +1494,17 @@ inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) 
 
 // ------------------------------------------------------------------------------------------------
 void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, uint32_t *fb_count, uint32_t *fb_list,
-                         cudaStream_t st, uint32_t y0, uint32_t y1)
+                         cudaStream_t st, uint32_t y0, uint32_t y1, int lean, uint32_t *tap_n, float *tap_thr)
 {
   cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
   if (y1 > h) y1 = h;
   if (y0 >= y1) return;
   const uint32_t hb = y1 - y0;
   const dim3 g(tile_grid(w, hb));
-  if (S.occ) {
+  if (lean && !S.occ && !grey && !S.rec) {
+    if (tap_n) render_lean_kernel<true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, tap_n, tap_thr);
+    else render_lean_kernel<false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, nullptr, nullptr);
+  } else if (S.occ) {
     if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
     else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
   } else {
