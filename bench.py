@@ -560,6 +560,62 @@ def other_configs(pkg, t0, local, rank, world, max_over_ranks, barrier):
     return out
 
 
+def exchange_check(pkg, t, grid, dist, torch, shard, one_nccl, one_peer_factory, n_it=4):
+    """the three exchange paths from the same state: replicas identical within a path (all-gathered checksum of the parameter bits),
+    and each fused path against the NCCL path (max |difference| over the parameter planes of this rank, max over ranks)"""
+    n = t.lib.lrf_param_count(t.h)
+
+    def params_tensor():
+        class _P:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (t.lib.lrf_param_device_ptr(t.h), False), "version": 2}
+        return torch.as_tensor(_P(), device="cuda")
+
+    def reset():
+        if FILL_MODE is None:
+            t.set_grid(grid)
+        else:
+            t.fill_synthetic(DENSITY_SCALE, FILL_MODE)
+        t.optimizerInit()
+        t.zeroGrad()
+        t.sync()
+
+    def checksum():
+        t.sync()
+        p = params_tensor()
+        bits = p.view(torch.int32).to(torch.int64)
+        cs = int((bits * (torch.arange(n, device="cuda", dtype=torch.int64) % 1000003 + 1)).sum().item())
+        alls = [None] * dist.get_world_size()
+        dist.all_gather_object(alls, cs)
+        return p, len(set(alls)) == 1
+
+    out = {}
+    reset()
+    for it in range(n_it):
+        one_nccl(it)
+    p, same = checksum()
+    ref = p.clone()
+    out["nccl_replicas_identical"] = same
+    for name, cls in (("peer", shard.PeerExchange), ("multicast", shard.McExchange)):
+        if name == "multicast" and not t.mc_supported():
+            continue
+        try:
+            reset()
+            e = cls(t, dist, torch)
+            step = one_peer_factory(e)
+            for it in range(n_it):
+                step(it)
+            p, same = checksum()
+            d = torch.tensor([float((p - ref).abs().max().item())], device="cuda")
+            dist.all_reduce(d, op=dist.ReduceOp.MAX)
+            out[name + "_replicas_identical"] = same
+            out[name + "_max_abs_diff_vs_nccl"] = float(d.item())
+            e.close()
+        except Exception as ex_:
+            out[name + "_error"] = "%s: %s" % (type(ex_).__name__, ex_)
+    out["note"] = "%d iterations from the same parameters through each path; the NCCL ring and the switch add in different orders than the rank-order sum (last-bit differences in the gradient sum)" % n_it
+    return out
+
+
 def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks, barrier, iters=20, batch=4096):
     """BASELINE.json configs[2]: grid optimisation on the 256^3 grid, 4096-ray batches per GPU against synthetic targets:
     one iteration = ray generation + backward(4096 rays) + per-cell pass ({TV -> Adam(density)} || Adam(colour), zeroing
@@ -585,9 +641,11 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
         import torch
         n = t.lib.lrf_param_count(t.h)
 
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (t.lib.lrf_grad_device_ptr(t.h), False), "version": 2}
-        grad_tensor = torch.as_tensor(_Arr(), device="cuda")
+        def grad_view():   # the planes move when a multicast group is joined or left: never keep the view across such a call
+            class _Arr:
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (t.lib.lrf_grad_device_ptr(t.h), False), "version": 2}
+            return torch.as_tensor(_Arr(), device="cuda")
+        grad_tensor = grad_view()
         ext = torch.cuda.ExternalStream(t.lib.lrf_stream(t.h))
 
     shard = sharding()
@@ -599,7 +657,7 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
         if grad_tensor is not None and exchange:
             import torch
             with torch.cuda.stream(ext):
-                shard.allreduce_gradient(grad_tensor, dist)
+                shard.allreduce_gradient(grad_view(), dist)
         t._ck(t.lib.lrf_train_percell_async(t.h, it))
 
     for it in range(3):
@@ -612,6 +670,7 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     barrier()
     ms_noex = None
     ms_peer = ms_peer_exchange = ms_barrier = None
+    ms_mc = ms_mc_exchange = mc_error = replica_check = None
     if grad_tensor is not None:   # same iterations without the exchange step: the all-reduce share of an iteration
         t.timer_start()
         for it in range(3, 3 + iters):
@@ -650,6 +709,34 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
         ms_barrier = max_over_ranks(t.timer_stop_ms()) / 5
         barrier()
         ex.close()
+        # the same exchange through the NVSwitch (NVLink multicast objects: multimem.ld_reduce / multimem.st, sharding.McExchange)
+        if t.mc_supported():
+            try:
+                exm = shard.McExchange(t, dist, torch)
+                ex = exm
+
+                for it in range(3):
+                    one_peer(it)
+                barrier()
+                t.timer_start()
+                for it in range(3, 3 + iters):
+                    one_peer(it)
+                ms_mc = max_over_ranks(t.timer_stop_ms())
+                barrier()
+                t.timer_start()
+                for it in range(5):
+                    exm.percell(300 + it, tv_done=True)
+                ms_mc_exchange = max_over_ranks(t.timer_stop_ms()) / 5
+                barrier()
+                exm.close()
+            except Exception as e:   # reported, not fatal: the point-to-point exchange above stands
+                mc_error = "%s: %s" % (type(e).__name__, e)
+        # replicas and paths agree: the same 4 iterations from the same state through each path; per path the parameter planes of all
+        # ranks are compared (bit pattern checksum all-gathered), and the paths against the NCCL one (max |difference|)
+        replica_check = exchange_check(pkg, t, grid, dist, torch, shard, one, one_peer_factory=lambda e: (lambda it: (
+            t._ck(t.lib.lrf_gen_rays_dev_async(t.h, batch, vi_dev.ptr, picks_dev.ptr + it * batch * 8, W, H, o_dev.ptr, d_dev.ptr)),
+            t._ck(t.lib.lrf_rays_grad_tv_dev_async(t.h, batch, o_dev.ptr, d_dev.ptr, ref_dev.ptr + it * batch * 16, 0)),
+            e.percell(it, tv_done=True))))
     # break-down: backward alone / per-cell alone
     t.timer_start()
     for it in range(5):
@@ -665,10 +752,18 @@ def train_bench(pkg, t, grid, views, proj_inv, rank, world, dist, max_over_ranks
     # node traffic (52 B read + 2 x 52 B gradient read-modify-write per touched node; counted as touched-node upper bound
     # rays x samples x 8 is NOT used — only the dense per-cell term, which dominates, enters the roofline figure)
     iter_bytes = 428.0 * N
-    best = min(ms, ms_peer) if ms_peer else ms
+    cands = [(ms, "NCCL all-reduce + replicated per-cell pass")]
+    if ms_peer:
+        cands.append((ms_peer, "peer-memory fused, point to point (lrf_train_percell_peer_async, adam_peer_kernel)"))
+    if ms_mc:
+        cands.append((ms_mc, "NVLink multicast fused: multimem.ld_reduce + multimem.st through the switch (lrf_mc_*, adam_mc_kernel)"))
+    best, best_name = min(cands)
     out = {"metric": "train_iters_per_s", "value": iters / (best * 1e-3), "ms_per_iter": best / iters, "rays_per_iter": batch * world, "n_gpus": world,
-           "exchange": ("peer-memory fused (lrf_train_percell_peer_async)" if ms_peer and ms_peer <= ms else "NCCL all-reduce + replicated per-cell pass") if world > 1 else "none (1 GPU)",
+           "exchange": best_name if world > 1 else "none (1 GPU)",
            "ms_per_iter_nccl_allreduce": ms / iters, "ms_per_iter_peer_fused": (ms_peer / iters) if ms_peer else None,
+           "ms_per_iter_multicast_fused": (ms_mc / iters) if ms_mc else None, "ms_multicast_exchange_alone": ms_mc_exchange, "multicast_error": mc_error,
+           "iter_frac_of_hbm_peak_multicast_fused": ((428.0 * GS ** 3 / (ms_mc / iters * 1e-3) / 1e9) / measured_peak()[0]) if ms_mc else None,
+           "replica_check": replica_check,
            "ms_peer_exchange_alone": ms_peer_exchange, "ms_stream_barrier": ms_barrier,
            "scaling": "weak (4096 rays per GPU per iteration)",
            "ms_backward_4096_rays": ms_bwd, "ms_percell_tv_adam_zero": ms_cell,

@@ -170,6 +170,26 @@ int lrf_peer_attach_flags_ipc(lrf_ctx *h, const void *flag_handles);
 int lrf_peer_barrier_async(lrf_ctx *h);
 int lrf_peer_barrier_timed_out(lrf_ctx *h);
 int lrf_tv_grad_slab_async(lrf_ctx *h);              /* kernel2D_TVGrad restricted to the own slab */
+/* The same exchange through the NVSwitch — NVLink multicast objects: multimem.ld_reduce returns the sum of every replica's gradient
+ * in one reduced response, multimem.st stores the new parameters into every replica with one store (half the NVLink volume of the
+ * point-to-point pass in each direction).  After the four steps below lrf_adam_peer_async / lrf_train_percell_peer_async take this
+ * path; lrf_peer_detach (or destroying the grid) leaves the group.  While attached the parameter and gradient planes live in
+ * cuMemCreate allocations (lrf_ipc_export of them is not available; the flag barrier is unchanged: lrf_ipc_export(h, 2, ..) +
+ * lrf_peer_attach_flags_ipc).  The switch sums in its own order: results can differ from the rank-order sum in the last bit, the
+ * replicas stay identical to each other.
+ *   1. every rank:  lrf_mc_prepare(h, world, rank)
+ *   2. one rank:    lrf_mc_create(h, &fd)  -> pass fd to the other processes (unix socket, SCM_RIGHTS);  others: lrf_mc_import(h, fd)
+ *   3. every rank:  lrf_mc_add_device(h);  group-wide barrier
+ *   4. every rank:  lrf_mc_bind(h);        group-wide barrier
+ * lrf_mc_attach_local does all of it for contexts of one process (and wires the barrier flags like lrf_peer_attach_local). */
+int lrf_mc_supported(int device);
+int lrf_mc_prepare(lrf_ctx *h, int world, int rank);
+int lrf_mc_create(lrf_ctx *h, int *fd_out);
+int lrf_mc_import(lrf_ctx *h, int fd);
+int lrf_mc_add_device(lrf_ctx *h);
+int lrf_mc_bind(lrf_ctx *h);
+int lrf_mc_attach_local(int world, lrf_ctx *const *ctxs);
+int lrf_mc_attached(lrf_ctx *h);
 int lrf_adam_peer_async(lrf_ctx *h, int iter);       /* optimizerStep(iter) on the own slab, gradient summed over the ranks */
 int lrf_train_percell_peer_async(lrf_ctx *h, int iter);   /* the two above */
 int lrf_zero_grad_async(lrf_ctx *h);                 /* zeroGrad without the stream sync */

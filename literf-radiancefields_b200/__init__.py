@@ -95,6 +95,14 @@ SIGNATURES = {
     "lrf_peer_detach": (C.c_int, [_vp]),
     "lrf_peer_attach_flags_ipc": (C.c_int, [_vp, _vp]),
     "lrf_peer_barrier_async": (C.c_int, [_vp]),
+    "lrf_mc_supported": (C.c_int, [C.c_int]),
+    "lrf_mc_prepare": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "lrf_mc_create": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "lrf_mc_import": (C.c_int, [_vp, C.c_int]),
+    "lrf_mc_add_device": (C.c_int, [_vp]),
+    "lrf_mc_bind": (C.c_int, [_vp]),
+    "lrf_mc_attach_local": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "lrf_mc_attached": (C.c_int, [_vp]),
     "lrf_peer_barrier_timed_out": (C.c_int, [_vp]),
     "lrf_tv_grad_slab_async": (C.c_int, [_vp]),
     "lrf_adam_peer_async": (C.c_int, [_vp, C.c_int]),
@@ -481,6 +489,36 @@ class RayMarcherExample:
     def peer_attach_flags_ipc(self, flag_handles):
         fb = b"".join(flag_handles)
         self._ck(self.lib.lrf_peer_attach_flags_ipc(self.h, fb))
+
+    # ---- the exchange through NVLink multicast objects (include/lrf.h: lrf_mc_*) ----
+    def mc_supported(self):
+        return bool(self.lib.lrf_mc_supported(self.device))
+
+    def mc_prepare(self, world, rank):
+        self._ck(self.lib.lrf_mc_prepare(self.h, world, rank))
+
+    def mc_create(self):
+        fd = C.c_int(-1)
+        self._ck(self.lib.lrf_mc_create(self.h, C.byref(fd)))
+        return fd.value
+
+    def mc_import(self, fd):
+        self._ck(self.lib.lrf_mc_import(self.h, fd))
+
+    def mc_add_device(self):
+        self._ck(self.lib.lrf_mc_add_device(self.h))
+
+    def mc_bind(self):
+        self._ck(self.lib.lrf_mc_bind(self.h))
+
+    def mc_attached(self):
+        return bool(self.lib.lrf_mc_attached(self.h))
+
+    @staticmethod
+    def mc_attach_local(tracers):
+        """contexts of ONE process (one per device) as a multicast group; rank = position in the list"""
+        arr = (_vp * len(tracers))(*[t.h for t in tracers])
+        tracers[0]._ck(tracers[0].lib.lrf_mc_attach_local(len(tracers), arr))
 
     def peer_barrier_async(self):
         self._ck(self.lib.lrf_peer_barrier_async(self.h))

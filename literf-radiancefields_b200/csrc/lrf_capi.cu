@@ -13,6 +13,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
+
+#include <cuda.h>   // driver API TYPES only (multicast objects, virtual memory management); entry points come from cudaGetDriverEntryPoint
 
 #include "lrf_kernels.cuh"
 
@@ -60,6 +63,15 @@ struct lrf_ctx
   uint32_t *flags = nullptr;          // own barrier flag array: [0..8) one slot per rank, [16] = time-out marker
   uint32_t *peer_flags[8] = {nullptr};
   uint32_t peer_epoch = 0;
+  // the exchange through NVLink multicast objects (lrf_mc_*): while attached, params / grad live in cuMemCreate allocations bound to
+  // the group's multicast object; mc_va maps it: [0, mc_bytes) parameters of every replica, [mc_bytes, 2 mc_bytes) gradients
+  bool mc = false;
+  CUmemGenericAllocationHandle mc_mem[2] = {0, 0};   // own physical allocations: params, grad
+  CUmemGenericAllocationHandle mc_obj = 0;           // the multicast object
+  bool mc_obj_owner = false;
+  CUdeviceptr mc_va = 0;
+  size_t mc_bytes = 0;                               // padded size of one plane set
+  int mc_state = 0;                                  // 0 none, 1 prepared (VMM), 2 object known, 3 device added, 4 bound + mapped
   // staged forward render (lrf_staged.cuh): baked 64-byte node records + what was learnt while baking
   float4 *rec = nullptr;              // N records
   size_t rec_N = 0;
@@ -365,15 +377,24 @@ static int render_dispatch(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t h
   return 0;
 }
 
+static void mc_teardown(lrf_ctx *h);
+static int peer_check(lrf_ctx *h, int world, int rank)
+{
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail("peer group: world must be 1..8 and 0 <= rank < world");
+  if (h->gs % (8 * world)) return fail("peer group: gridSize must be a multiple of 8 * world (z-slabs of whole 8^3 TV tiles)");
+  return 0;
+}
 static void peer_detach(lrf_ctx *h)
 {
   if (h->peer_ipc)
     for (int r = 0; r < h->peer_world; r++)
       if (r != h->peer_rank) {
-        cudaIpcCloseMemHandle(h->peer_param[r]); cudaIpcCloseMemHandle(h->peer_grad[r]);
+        if (h->peer_param[r]) cudaIpcCloseMemHandle(h->peer_param[r]);
+        if (h->peer_grad[r]) cudaIpcCloseMemHandle(h->peer_grad[r]);
         if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
       }
-  for (int r = 0; r < 8; r++) h->peer_flags[r] = nullptr;
+  mc_teardown(h);
+  for (int r = 0; r < 8; r++) { h->peer_flags[r] = nullptr; h->peer_param[r] = nullptr; h->peer_grad[r] = nullptr; }
   h->peer_world = 0;
   h->peer_ipc = false;
 }
@@ -415,6 +436,294 @@ static int alloc_grid(lrf_ctx *h, int gs)
   h->n_boxes = (size_t)(gs - 1) * (gs - 1) * (gs - 1);
   h->rec_dirty = true;
   return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// NVLink multicast ("NVLS") plumbing for the training exchange (adam_mc_kernel, lrf_kernels.cu).  No reference counterpart (the
+// reference is one process, #pragma omp parallel for at example_tracer.cpp:668).  Driver entry points are taken at run time.
+namespace {
+struct McDriver
+{
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+  CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MulticastCreate)(CUmemGenericAllocationHandle *, const CUmulticastObjectProp *) = nullptr;
+  CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+  CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
+  CUresult (*MulticastGetGranularity)(size_t *, const CUmulticastObjectProp *, CUmulticastGranularity_flags) = nullptr;
+  CUresult (*DeviceGet)(CUdevice *, int) = nullptr;
+  CUresult (*DeviceGetAttribute)(int *, CUdevice_attribute, CUdevice) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+  bool ok = false;
+};
+template <class F> bool mc_sym(const char *name, F &fn)
+{
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return false;
+  }
+  fn = reinterpret_cast<F>(p);
+  return true;
+}
+McDriver &mc_driver()
+{
+  static McDriver D;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    D.ok = mc_sym("cuMemCreate", D.MemCreate) && mc_sym("cuMemRelease", D.MemRelease) && mc_sym("cuMemAddressReserve", D.MemAddressReserve) &&
+           mc_sym("cuMemAddressFree", D.MemAddressFree) && mc_sym("cuMemMap", D.MemMap) && mc_sym("cuMemUnmap", D.MemUnmap) &&
+           mc_sym("cuMemSetAccess", D.MemSetAccess) && mc_sym("cuMemGetAllocationGranularity", D.MemGetAllocationGranularity) &&
+           mc_sym("cuMemExportToShareableHandle", D.MemExportToShareableHandle) &&
+           mc_sym("cuMemImportFromShareableHandle", D.MemImportFromShareableHandle) && mc_sym("cuMulticastCreate", D.MulticastCreate) &&
+           mc_sym("cuMulticastAddDevice", D.MulticastAddDevice) && mc_sym("cuMulticastBindMem", D.MulticastBindMem) &&
+           mc_sym("cuMulticastUnbind", D.MulticastUnbind) && mc_sym("cuMulticastGetGranularity", D.MulticastGetGranularity) &&
+           mc_sym("cuDeviceGet", D.DeviceGet) && mc_sym("cuDeviceGetAttribute", D.DeviceGetAttribute) && mc_sym("cuGetErrorString", D.GetErrorString);
+  }
+  return D;
+}
+int mc_fail(const char *what, CUresult r)
+{
+  const char *s = nullptr;
+  if (mc_driver().GetErrorString) mc_driver().GetErrorString(r, &s);
+  return fail(std::string(what) + ": CUresult " + std::to_string((int)r) + (s ? std::string(" (") + s + ")" : std::string()));
+}
+#define CKU(call)                                              \
+  do {                                                         \
+    CUresult r_ = (call);                                      \
+    if (r_ != CUDA_SUCCESS) return mc_fail(#call, r_);         \
+  } while (0)
+CUmemAllocationProp mc_alloc_prop(int device)
+{
+  CUmemAllocationProp prop{};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  return prop;
+}
+// a plane set (13 N floats) in a cuMemCreate allocation of `bytes`, mapped read-write on the context's device
+int mc_alloc_planes(lrf_ctx *h, size_t bytes, size_t gran, CUmemGenericAllocationHandle &mem, float *&ptr)
+{
+  McDriver &D = mc_driver();
+  const CUmemAllocationProp prop = mc_alloc_prop(h->device);
+  CKU(D.MemCreate(&mem, bytes, &prop, 0));
+  CUdeviceptr va = 0;
+  CKU(D.MemAddressReserve(&va, bytes, gran, 0, 0));
+  CKU(D.MemMap(va, bytes, 0, mem, 0));
+  CUmemAccessDesc acc{};
+  acc.location = prop.location;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  CKU(D.MemSetAccess(va, bytes, &acc, 1));
+  ptr = reinterpret_cast<float *>(va);
+  return 0;
+}
+void mc_free_planes(size_t bytes, CUmemGenericAllocationHandle mem, float *ptr)
+{
+  McDriver &D = mc_driver();
+  if (ptr) { D.MemUnmap((CUdeviceptr)ptr, bytes); D.MemAddressFree((CUdeviceptr)ptr, bytes); }
+  if (mem) D.MemRelease(mem);
+}
+}  // namespace
+
+// leaves the group: the multicast mapping goes away and the planes move back into cudaMalloc allocations (contents kept)
+static void mc_teardown(lrf_ctx *h)
+{
+  if (!h->mc) return;
+  McDriver &D = mc_driver();
+  cudaSetDevice(h->device);
+  const bool dbg = std::getenv("LRF_DEBUG") != nullptr;
+  auto step = [&](const char *what, long rc) {
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (dbg || e != cudaSuccess || rc != 0) std::fprintf(stderr, "[lrf] mc_teardown dev %d: %s -> rc %ld, device %s\n", h->device, what, rc, cudaGetErrorString(e));
+  };
+  step("entry", 0);
+  // 1. the contents move to ordinary allocations while everything is still mapped
+  const size_t bytes = h->N * kCell * sizeof(float);
+  float *np = nullptr, *ng = nullptr;
+  if (h->params) {
+    long rc = (long)cudaMalloc(&np, bytes);
+    if (!rc) rc = (long)cudaMalloc(&ng, bytes);
+    if (!rc) rc = (long)cudaMemcpy(np, h->params, bytes, cudaMemcpyDeviceToDevice);
+    if (!rc) rc = (long)cudaMemcpy(ng, h->grad, bytes, cudaMemcpyDeviceToDevice);
+    step("copy out", rc);
+  }
+  // 2. the multicast mapping, the bindings, the object
+  if (h->mc_va) {
+    long rc = (long)D.MemUnmap(h->mc_va, 2 * h->mc_bytes);
+    if (!rc) rc = (long)D.MemAddressFree(h->mc_va, 2 * h->mc_bytes);
+    step("unmap multicast range", rc);
+  }
+  if (h->mc_obj) {
+    if (h->mc_state >= 4) {
+      CUdevice dev;
+      long rc = (long)D.DeviceGet(&dev, h->device);
+      if (!rc) rc = (long)D.MulticastUnbind(h->mc_obj, dev, 0, h->mc_bytes);
+      if (!rc) rc = (long)D.MulticastUnbind(h->mc_obj, dev, h->mc_bytes, h->mc_bytes);
+      step("unbind", rc);
+    }
+    step("release object", (long)D.MemRelease(h->mc_obj));
+  }
+  // 3. the cuMemCreate planes
+  mc_free_planes(h->mc_bytes, h->mc_mem[0], h->params);
+  mc_free_planes(h->mc_bytes, h->mc_mem[1], h->grad);
+  step("free planes", 0);
+  h->params = np; h->grad = ng;
+  h->mc = false; h->mc_obj = 0; h->mc_va = 0; h->mc_mem[0] = h->mc_mem[1] = 0; h->mc_bytes = 0; h->mc_state = 0; h->mc_obj_owner = false;
+  params_changed(h);
+}
+
+extern "C" {
+int lrf_mc_supported(int device)
+{
+  McDriver &D = mc_driver();
+  if (!D.ok) return 0;
+  CUdevice dev;
+  int v = 0;
+  if (D.DeviceGet(&dev, device) != CUDA_SUCCESS) return 0;
+  if (D.DeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) != CUDA_SUCCESS) return 0;
+  return v;
+}
+// step 1 (every rank): the parameter and gradient planes move into shareable cuMemCreate allocations padded to the multicast granularity
+int lrf_mc_prepare(lrf_ctx *h, int world, int rank)
+{
+  NEED_GRID(h);
+  if (peer_check(h, world, rank)) return 1;
+  if (!lrf_mc_supported(h->device)) return fail("NVLink multicast objects are not supported on this device / driver");
+  peer_detach(h);
+  McDriver &D = mc_driver();
+  CUmulticastObjectProp mp{};
+  mp.numDevices = (unsigned)world;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  const size_t bytes = h->N * kCell * sizeof(float);
+  mp.size = bytes;
+  size_t gran = 0, agran = 0;
+  CKU(D.MulticastGetGranularity(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  const CUmemAllocationProp prop = mc_alloc_prop(h->device);
+  CKU(D.MemGetAllocationGranularity(&agran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  if (agran > gran) gran = agran;
+  const size_t padded = (bytes + gran - 1) / gran * gran;
+  CUmemGenericAllocationHandle m0 = 0, m1 = 0;
+  float *np = nullptr, *ng = nullptr;
+  if (mc_alloc_planes(h, padded, gran, m0, np)) return 1;
+  if (mc_alloc_planes(h, padded, gran, m1, ng)) { mc_free_planes(padded, m0, np); return 1; }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(np, h->params, bytes, cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(ng, h->grad, bytes, cudaMemcpyDeviceToDevice));
+  cudaFree(h->params); cudaFree(h->grad);
+  h->params = np; h->grad = ng;
+  h->mc_mem[0] = m0; h->mc_mem[1] = m1; h->mc_bytes = padded;
+  h->mc = true; h->mc_state = 1;
+  h->peer_world = world; h->peer_rank = rank; h->peer_ipc = true;   // the flag barrier maps its arrays with CUDA IPC
+  params_changed(h);
+  return 0;
+}
+// step 2, ONE rank: create the group's multicast object and export it as a POSIX file descriptor (to be passed to the other ranks'
+// processes, e.g. over a unix socket with SCM_RIGHTS); the caller closes the descriptor
+int lrf_mc_create(lrf_ctx *h, int *fd_out)
+{
+  NEED_GRID(h);
+  if (!h->mc || h->mc_state != 1) return fail("lrf_mc_create: call lrf_mc_prepare first");
+  McDriver &D = mc_driver();
+  CUmulticastObjectProp mp{};
+  mp.numDevices = (unsigned)h->peer_world;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  mp.size = 2 * h->mc_bytes;
+  CKU(D.MulticastCreate(&h->mc_obj, &mp));
+  h->mc_obj_owner = true;
+  h->mc_state = 2;
+  if (fd_out) {
+    int fd = -1;
+    CKU(D.MemExportToShareableHandle(&fd, h->mc_obj, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    *fd_out = fd;
+  }
+  return 0;
+}
+// step 2, the other ranks: import the object from the descriptor received
+int lrf_mc_import(lrf_ctx *h, int fd)
+{
+  NEED_GRID(h);
+  if (!h->mc || h->mc_state != 1) return fail("lrf_mc_import: call lrf_mc_prepare first");
+  McDriver &D = mc_driver();
+  CKU(D.MemImportFromShareableHandle(&h->mc_obj, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  h->mc_state = 2;
+  return 0;
+}
+// step 3 (every rank; all ranks must have done it before anyone binds): add the own device to the object
+int lrf_mc_add_device(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  if (!h->mc || h->mc_state != 2) return fail("lrf_mc_add_device: no multicast object yet (lrf_mc_create / lrf_mc_import)");
+  McDriver &D = mc_driver();
+  CUdevice dev;
+  CKU(D.DeviceGet(&dev, h->device));
+  CKU(D.MulticastAddDevice(h->mc_obj, dev));
+  h->mc_state = 3;
+  return 0;
+}
+// step 4 (every rank, after a group-wide barrier): bind the own planes and map the multicast range
+int lrf_mc_bind(lrf_ctx *h)
+{
+  NEED_GRID(h);
+  if (!h->mc || h->mc_state != 3) return fail("lrf_mc_bind: add the device first (lrf_mc_add_device)");
+  McDriver &D = mc_driver();
+  CKU(D.MulticastBindMem(h->mc_obj, 0, h->mc_mem[0], 0, h->mc_bytes, 0));
+  CKU(D.MulticastBindMem(h->mc_obj, h->mc_bytes, h->mc_mem[1], 0, h->mc_bytes, 0));
+  CUmulticastObjectProp mp{};
+  mp.numDevices = (unsigned)h->peer_world;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  mp.size = 2 * h->mc_bytes;
+  size_t gran = 0;
+  CKU(D.MulticastGetGranularity(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  CKU(D.MemAddressReserve(&h->mc_va, 2 * h->mc_bytes, gran, 0, 0));
+  CKU(D.MemMap(h->mc_va, 2 * h->mc_bytes, 0, h->mc_obj, 0));
+  CUmemAccessDesc acc{};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = h->device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  CKU(D.MemSetAccess(h->mc_va, 2 * h->mc_bytes, &acc, 1));
+  h->mc_state = 4;
+  return 0;
+}
+// all four steps for a group whose contexts live in ONE process (tests, single-process multi-GPU hosts); flags as lrf_peer_attach_local
+int lrf_mc_attach_local(int world, lrf_ctx *const *ctxs)
+{
+  if (world < 1 || world > 8 || !ctxs) return fail("lrf_mc_attach_local: world must be 1..8");
+  for (int r = 0; r < world; r++) {
+    if (!ctxs[r]) return fail("null context");
+    if (lrf_mc_prepare(ctxs[r], world, r)) return 1;
+    ctxs[r]->peer_ipc = false;
+  }
+  if (lrf_mc_create(ctxs[0], nullptr)) return 1;
+  for (int r = 1; r < world; r++) {
+    // one process: the handle itself is valid for every device; every context keeps (and later releases) its own reference
+    int fd = -1;
+    McDriver &D = mc_driver();
+    CKU(D.MemExportToShareableHandle(&fd, ctxs[0]->mc_obj, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    const int rc = lrf_mc_import(ctxs[r], fd);
+    close(fd);
+    if (rc) return 1;
+  }
+  for (int r = 0; r < world; r++)
+    if (lrf_mc_add_device(ctxs[r])) return 1;
+  for (int r = 0; r < world; r++)
+    if (lrf_mc_bind(ctxs[r])) return 1;
+  for (int r = 0; r < world; r++)
+    for (int q = 0; q < world; q++) ctxs[r]->peer_flags[q] = ctxs[q]->flags;
+  return 0;
+}
+int lrf_mc_attached(lrf_ctx *h) { return h && h->mc && h->mc_state == 4 ? 1 : 0; }
 }
 
 extern "C" {
@@ -1132,12 +1441,6 @@ int lrf_adam_zero_async(lrf_ctx *h, int iter)
 }
 
 // ---- multi-GPU exchange over peer memory ----
-static int peer_check(lrf_ctx *h, int world, int rank)
-{
-  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail("peer group: world must be 1..8 and 0 <= rank < world");
-  if (h->gs % (8 * world)) return fail("peer group: gridSize must be a multiple of 8 * world (z-slabs of whole 8^3 TV tiles)");
-  return 0;
-}
 int lrf_ipc_export(lrf_ctx *h, int which, void *handle64)
 {
   NEED_GRID(h);
@@ -1192,7 +1495,7 @@ int lrf_peer_detach(lrf_ctx *h) { NEED(h); peer_detach(h); return 0; }
 int lrf_peer_attach_flags_ipc(lrf_ctx *h, const void *flag_handles)
 {
   NEED(h);
-  if (h->peer_world < 1 || !h->peer_ipc) return fail("attach the group with lrf_peer_attach_ipc first");
+  if (h->peer_world < 1 || !h->peer_ipc) return fail("attach the group with lrf_peer_attach_ipc or lrf_mc_prepare first");
   for (int r = 0; r < h->peer_world; r++) {
     if (r == h->peer_rank) { h->peer_flags[r] = h->flags; continue; }
     cudaIpcMemHandle_t hf;
@@ -1239,6 +1542,15 @@ int lrf_adam_peer_async(lrf_ctx *h, int iter)
   const size_t n = (size_t)h->peer_world, r = (size_t)h->peer_rank;
   // own slab of the density plane and of the colour plane (contiguous z-slabs of both)
   params_changed(h);   // every rank runs this pass and every replica is rewritten by it
+  if (h->mc) {
+    if (h->mc_state != 4) return fail("multicast group not bound yet (lrf_mc_bind)");
+    float *mcp = reinterpret_cast<float *>(h->mc_va), *mcg = reinterpret_cast<float *>(h->mc_va + h->mc_bytes);
+    launch_adam_mc(mcg, mcp, h->params, h->V, h->S, h->N / n * r, h->N / n, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, h->stream);
+    launch_adam_mc(mcg, mcp, h->params, h->V, h->S, h->N + h->N * 12 / n * r, h->N * 12 / n, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, h->stream);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+  }
   launch_adam_peer(h->peer_world, h->peer_rank, h->peer_grad, h->peer_param, h->V, h->S, h->N / n * r, h->N / n, h->lr, h->beta1, h->beta2, h->eps,
                    1 - b1, 1 - b2, h->stream);
   launch_adam_peer(h->peer_world, h->peer_rank, h->peer_grad, h->peer_param, h->V, h->S, h->N + h->N * 12 / n * r, h->N * 12 / n, h->lr, h->beta1,

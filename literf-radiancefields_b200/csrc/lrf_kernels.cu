@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kBlock, LRF_LEAN_MINB) render_lean_kernel(cons
   LeanMarch<TAPS> lm(S, etab);
   lm.run(o, d);
   uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
-  if (lm.any_hit)
+  if (lm.any_hit())
     pix = pack_color(lm_clamp(lm.col[0], 0.0f, 1.0f), lm_clamp(lm.col[1], 0.0f, 1.0f), lm_clamp(lm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
   out[pixel] = pix;
   if (TAPS) { tap_n[pixel] = lm.n_shaded; tap_thr[pixel] = lm.thr; }
@@ -1264,6 +1264,51 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(const PeerSet P, float *
   }
 }
 
+// The same exchange through the NVSwitch (NVLink multicast objects, "NVLS"): the gradient planes of all ranks are bound to ONE
+// multicast address range and so are the parameter planes.  multimem.ld_reduce asks the switch for the SUM of every replica's value
+// at an address (one reduced 16-byte response comes back instead of world - 1 peer loads), multimem.st stores one value into every
+// replica (one store goes out instead of world - 1 peer stores): per rank and direction the NVLink volume falls from
+// 2 (n-1)/n to (n-1)/n + 1/n of a plane set.  The switch adds in an order of its own, so the sum may differ from the rank-order sum
+// of adam_peer_kernel in the last bit; every element is reduced once (by its owner) and broadcast, so the replicas stay identical.
+__device__ __forceinline__ float4 mc_ld_reduce(const float *mc)
+{
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(float *mc, const float4 &v)
+{
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// count is a multiple of 4 (slabs of whole z planes of a grid whose size is a multiple of 8); kMcUnroll float4 per thread, all
+// reductions requested before the first one is consumed (a switch round trip is microseconds)
+constexpr int kMcUnroll = 4;
+__global__ void __launch_bounds__(256) adam_mc_kernel(const float *__restrict__ mc_grad, float *__restrict__ mc_param, const float *__restrict__ param,
+                                                      float *__restrict__ V, float *__restrict__ Sq, size_t off, size_t count, const AdamConst C)
+{
+  const size_t base = ((size_t)blockIdx.x * blockDim.x * kMcUnroll + threadIdx.x) * 4;
+  float4 g[kMcUnroll];
+#pragma unroll
+  for (int u = 0; u < kMcUnroll; u++) {
+    const size_t i4 = base + (size_t)u * blockDim.x * 4;
+    if (i4 < count) g[u] = mc_ld_reduce(mc_grad + off + i4);
+  }
+#pragma unroll
+  for (int u = 0; u < kMcUnroll; u++) {
+    const size_t i4 = base + (size_t)u * blockDim.x * 4;
+    if (i4 >= count) continue;
+    const size_t at = off + i4;
+    float4 pv = *reinterpret_cast<const float4 *>(param + at);
+    float4 vv = *reinterpret_cast<float4 *>(V + at), sv = *reinterpret_cast<float4 *>(Sq + at);
+    const float4 gv = g[u];
+    adam_update(pv.x, gv.x, vv.x, sv.x, C); adam_update(pv.y, gv.y, vv.y, sv.y, C);
+    adam_update(pv.z, gv.z, vv.z, sv.z, C); adam_update(pv.w, gv.w, vv.w, sv.w, C);
+    *reinterpret_cast<float4 *>(V + at) = vv;
+    *reinterpret_cast<float4 *>(Sq + at) = sv;
+    mc_st(mc_param + at, pv);
+  }
+}
+
 // Inter-GPU barrier over peer memory for the exchange above: rank r stores the epoch into slot r of EVERY rank's flag array
 // (release, system scope) and waits until every slot of its own array has reached the epoch (acquire, system scope).  Stream
 // order makes the kernels queued before it complete first, so "all ranks passed the barrier" implies "all ranks finished what
@@ -1653,6 +1698,16 @@ void launch_adam_peer(int world, int rank, float *const *grads, float *const *pa
   P.world = world; P.rank = rank;
   for (int r = 0; r < world; r++) { P.grad[r] = grads[r]; P.param[r] = params[r]; }
   adam_peer_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(P, V, S, off, count, C);
+}
+void launch_adam_mc(const float *mc_grad, float *mc_param, const float *param, float *V, float *S, size_t off, size_t count, float lr, float beta1,
+                    float beta2, float eps, double om_b1, double om_b2, cudaStream_t st)
+{
+  if (count == 0) return;
+  AdamConst C;
+  C.lr = lr; C.beta1 = beta1; C.beta2 = beta2; C.eps = eps;
+  C.omb1f = 1 - beta1; C.omb2f = 1 - beta2;
+  C.om_b1 = om_b1; C.om_b2 = om_b2; C.inv_om_b1 = 1.0 / om_b1; C.inv_om_b2 = 1.0 / om_b2;
+  adam_mc_kernel<<<blocks_for((count + 3) / 4, 256 * kMcUnroll), 256, 0, st>>>(mc_grad, mc_param, param, V, S, off, count, C);
 }
 void launch_peer_barrier(int world, int rank, uint32_t *const *flags, uint32_t epoch, uint32_t *timed_out, cudaStream_t st)
 {

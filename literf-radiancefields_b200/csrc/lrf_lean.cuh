@@ -63,7 +63,7 @@ static __device__ __noinline__ int lean_exact_cross(float p0, float p1, float p2
 
 template <bool TAPS> struct LeanMarch
 {
-  static constexpr uint32_t kFull = 1u, kResync = 2u, kLeaving = 4u, kSeeded = 8u, kQueue = 0xff00u;
+  static constexpr uint32_t kFull = 1u, kResync = 2u, kLeaving = 4u, kSeeded = 8u, kHit = 16u, kQueue = 0xff00u;
 
   const SceneDev &S;
   const uint64_t *etab;
@@ -84,7 +84,7 @@ template <bool TAPS> struct LeanMarch
   float thr = 1.0f, tPrev = -1.0f;
   float col[3] = {0.0f, 0.0f, 0.0f};
   uint32_t n_shaded = 0;
-  bool any_hit = false;
+  __device__ __forceinline__ bool any_hit() const { return (cold & kHit) != 0; }   // set with the first cell (on a dense lattice the first event always holds at least one cell)
 
   __device__ LeanMarch(const SceneDev &s, const uint64_t *t) : S(s), etab(t) {}
   __device__ __forceinline__ uint32_t slot_node(int s) const { return nx[s & 1] + ny[(s >> 1) & 1] + nz[s >> 2]; }
@@ -235,7 +235,7 @@ template <bool TAPS> struct LeanMarch
       col[2] = fmaf(wgt, __saturatef(Bc * s), col[2]);
     }
     thr *= tr;                                                 // :189
-    n_shaded++;
+    if (TAPS) n_shaded++;
     return !(thr < 0.1f);                                      // :131
   }
   __device__ void run(const float *of, const float *df)
@@ -335,7 +335,10 @@ template <bool TAPS> struct LeanMarch
           }
           if (reseed) set_cell(x, y, z);
           cold |= kSeeded;
-          if (from_queue) return true;
+          if (from_queue) {
+            cold |= kHit;
+            return true;
+          }
         }
         // ---- which face does the ray leave through?  fp32 filter, exact fp64 when close (lrf_fast.cuh) ----
         const float m = fminf(fminf(tf[0], tf[1]), tf[2]);
@@ -399,7 +402,6 @@ template <bool TAPS> struct LeanMarch
     for (;;) {
       // One sample: (1) request the stale half of the window for the current cell, (2) the cell's geometry and the whole traversal
       // step to the next cell while the loads fly, (3) contract, shade, composite.
-      any_hit = true;
       if (cold & kFull) load_all();
       Pending P;
       P.stale = stale;

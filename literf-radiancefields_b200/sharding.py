@@ -105,6 +105,66 @@ class PeerExchange:
     def close(self):
         self.t.sync()
         self.dist.barrier()                  # nobody unmaps while a peer's kernel may still store into the arrays
-        if self.t.peer_barrier_timed_out():
-            raise RuntimeError("a peer-memory barrier timed out: a rank did not arrive within 2 s")
+        timed_out = self.t.peer_barrier_timed_out()
         self.t.peer_detach()
+        self.torch.cuda.synchronize()
+        self.dist.barrier()                  # every rank has unmapped its peers before anyone frees or re-allocates its planes
+        if timed_out:
+            raise RuntimeError("a peer-memory barrier timed out: a rank did not arrive within 2 s")
+
+
+class McExchange(PeerExchange):
+    """the per-iteration exchange through NVLink multicast objects (include/lrf.h lrf_mc_*; adam_mc_kernel): multimem.ld_reduce sums
+    the gradient replicas in the switch, multimem.st writes the new parameters into every replica.  Same call sequence as
+    PeerExchange (barrier, own-slab pass, barrier, zero); the barrier is the same peer-memory flag barrier.  The multicast object is
+    created by rank 0 and reaches the other processes as a POSIX file descriptor over a unix socket (SCM_RIGHTS)."""
+
+    def __init__(self, tracer, dist, torch):
+        import os
+        import socket
+        self.t, self.dist, self.torch = tracer, dist, torch
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if not tracer.mc_supported():
+            raise RuntimeError("NVLink multicast objects are not supported on this device / driver")
+        tracer.sync()
+        torch.cuda.synchronize()
+        dist.barrier()                       # nothing of an earlier group is in flight anywhere: the planes are about to move
+        tracer.mc_prepare(self.world, self.rank)
+        path = [None]
+        srv = None
+        if self.rank == 0:
+            path[0] = "/tmp/lrf_mc_%d_%s.sock" % (os.getpid(), os.environ.get("MASTER_PORT", "0"))
+            if os.path.exists(path[0]):
+                os.unlink(path[0])
+            srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            srv.bind(path[0])
+            srv.listen(self.world)
+        dist.broadcast_object_list(path, src=0)
+        if self.rank == 0:
+            fd = tracer.mc_create()
+            for _ in range(self.world - 1):
+                conn, _ = srv.accept()
+                socket.send_fds(conn, [b"mc"], [fd])
+                conn.recv(1)                  # the peer has imported the object
+                conn.close()
+            os.close(fd)
+            srv.close()
+            os.unlink(path[0])
+        else:
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(path[0])
+            _, fds, _, _ = socket.recv_fds(c, 16, 1)
+            tracer.mc_import(fds[0])
+            os.close(fds[0])
+            c.send(b"k")
+            c.close()
+        tracer.mc_add_device()
+        dist.barrier()                       # every device is part of the object before anyone binds memory to it
+        tracer.mc_bind()
+        flags = [None] * self.world
+        dist.all_gather_object(flags, tracer.ipc_export(2))
+        tracer.peer_attach_flags_ipc(flags)
+        self.stream = torch.cuda.ExternalStream(tracer.lib.lrf_stream(tracer.h))
+        self.flag = torch.zeros(1, device="cuda")
+        self.use_nccl_barrier = False
+        dist.barrier()                       # every rank has bound its planes and mapped every flag array

@@ -130,6 +130,80 @@ def test_peer_flag_barrier_two_contexts(pkg):
     ta.close(); tb.close()
 
 
+@pytest.mark.parametrize("gs", [16, 32])
+def test_multicast_fused_percell(pkg, gs):
+    """the exchange through NVLink multicast objects (lrf_mc_*, adam_mc_kernel: multimem.ld_reduce / multimem.st) with one context per
+    visible device (at most 2; on a 1-GPU box the group has one member and the switch reduction degenerates to a read): replicas
+    identical, parameters and moments equal the oracle's Adam fed with the summed gradient bit for bit (a two-term fp32 sum does not
+    depend on the order), and the planes survive joining and leaving the group"""
+    import torch
+    world = min(2, torch.cuda.device_count())
+    grid = libs.lcg_grid(gs, 20.0)
+    S = OracleScene(gs, grid)
+    vi, pi = cameras(None, 2, 7)
+    S.set_cam(vi, pi)
+    o, d = S.gen_rays(24, 24)
+    n = o.shape[0]
+    ts = []
+    for r in range(world):
+        t = pkg.RayMarcherExample(r)
+        t.InitGrid(gs)
+        t.set_grid(grid)
+        t.optimizerInit()
+        t.zeroGrad()
+        ts.append(t)
+    if not ts[0].mc_supported():
+        pytest.skip("no NVLink multicast support on this device / driver")
+    try:
+        pkg.RayMarcherExample.mc_attach_local(ts)
+    except pkg.LrfError as e:
+        pytest.skip("multicast group could not be formed here: %s" % e)
+    assert all(t.mc_attached() for t in ts)
+    assert np.array_equal(ts[0].get_grid().view(np.uint32), np.asarray(grid, np.float32).reshape(-1, 13).view(np.uint32)), "planes changed while joining the group"
+    S.O.orc_adam_init(S.h)
+    for it in range(3):
+        ref = np.random.default_rng(70 + it).random((n, 4)).astype(np.float32)
+        cut = [n * r // world for r in range(world + 1)]
+        for r, t in enumerate(ts):
+            t.rays_grad(o[cut[r]:cut[r + 1]], d[cut[r]:cut[r + 1]], ref[cut[r]:cut[r + 1]])
+            t.tv_grad_slab_async()
+        for t in ts:
+            t.sync()
+        gsum = ts[0].get_grad()
+        for t in ts[1:]:
+            gsum = gsum + t.get_grad()
+        for t in ts:
+            t.adam_peer_async(it)
+        for t in ts:
+            t.sync()
+        ps = [t.get_grid() for t in ts]
+        for p in ps[1:]:
+            assert np.array_equal(ps[0].view(np.uint32), p.view(np.uint32)), "replicas diverged"
+        S.grad[:] = gsum
+        S.O.orc_adam_step(S.h, it, 0)
+        assert np.array_equal(ps[0].view(np.uint32), S.grid.view(np.uint32)), "multicast Adam differs from the oracle's Adam on the summed gradient"
+        zs = gs ** 3 // world
+        for r, t in enumerate(ts):
+            Vr, Sr = t.get_adam_state()
+            assert np.array_equal(Vr[zs * r:zs * (r + 1)], S.adam_v[zs * r:zs * (r + 1)])
+            assert np.array_equal(Sr[zs * r:zs * (r + 1)], S.adam_s[zs * r:zs * (r + 1)])
+        for t in ts:
+            t.zero_grad_async()
+        for t in ts:
+            t.sync()
+    last = ts[0].get_grid()
+    for t in ts:
+        t.peer_detach()
+        assert not t.mc_attached()
+        assert np.array_equal(t.get_grid().view(np.uint32), last.view(np.uint32)), "planes changed while leaving the group"
+    # and the context keeps working on ordinary allocations
+    ts[0].rays_grad(o, d, ref)
+    ts[0].optimizerStep(3)
+    for t in ts:
+        t.close()
+    S.close()
+
+
 def test_peer_exchange_ipc_two_processes():
     """the CUDA-IPC path of the exchange under torchrun (2 ranks, one GPU each) against the NCCL all-reduce path; needs 2 GPUs"""
     import os
