@@ -29,7 +29,8 @@ struct lrf_ctx
   float *params = nullptr, *grad = nullptr, *V = nullptr, *S = nullptr;
   float *tv_tmp = nullptr;            // 2*N floats
   int32_t *boxes = nullptr;           // device, n_boxes*3 (null while dense)
-  uint32_t *occ = nullptr, *vox2id = nullptr, *occ8 = nullptr;   // occ8: one bit per 8^3-voxel brick
+  uint32_t *occ = nullptr, *vox2id = nullptr, *occ8 = nullptr;   // occ8: one bit per 8^3-voxel brick, followed by the brick distance field
+  uint32_t occ8_words = 0;
   size_t n_boxes = 0;
   bool dense = true;
   float bb_min[3] = {0, 0, 0}, bb_max[3] = {1, 1, 1};
@@ -134,6 +135,7 @@ static SceneDev scene_of(const lrf_ctx *h)
   S.occ = h->dense ? nullptr : h->occ;
   S.vox2id = h->dense ? nullptr : h->vox2id;
   S.occ8 = h->dense ? nullptr : h->occ8;
+  S.occ8_words = h->occ8_words;
   S.nb8 = (h->gs - 1 + 7) / 8;
   S.gs_f = (float)h->gs;
   S.inv_gs_f = 1.0f / (float)h->gs;
@@ -889,10 +891,13 @@ static int install_boxes_dev(lrf_ctx *h, int32_t *xyz_dev, size_t n)  // takes o
   CK(cudaMemsetAsync(h->vox2id, 0, (nv + 1) * 4, h->stream));
   const int nb8 = (h->gs - 1 + 7) / 8;
   const size_t words8 = ((size_t)nb8 * nb8 * nb8 + 31) / 32 + 1;
-  CK(cudaMalloc(&h->occ8, words8 * 4));
+  const size_t nb3 = (size_t)nb8 * nb8 * nb8;
+  CK(cudaMalloc(&h->occ8, words8 * 4 + 2 * nb3 + 16));      // coarse bitmap + the brick distance field (one byte per brick) + its ping-pong copy
   CK(cudaMemsetAsync(h->occ8, 0, words8 * 4, h->stream));
+  h->occ8_words = (uint32_t)words8;
   launch_build_box_maps(h->gs - 1, h->boxes, n, h->occ, h->vox2id, h->occ8, nb8, h->stream);
-  h->launches++;
+  launch_brick_dist(nb8, h->occ8, reinterpret_cast<uint8_t *>(h->occ8 + words8), reinterpret_cast<uint8_t *>(h->occ8 + words8) + nb3, h->stream);
+  h->launches += 2;
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

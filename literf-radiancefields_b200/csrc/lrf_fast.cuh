@@ -100,6 +100,9 @@ template <int MODE, bool SPARSE, bool GREY, bool BAKED = false> struct FastMarch
   // empty space a traversal step then costs no memory access at all
   uint32_t brick_id = 0xffffffffu;   // index of the cached coarse word
   uint32_t brick_word = 0;
+  uint32_t brick_b = 0xffffffffu;    // linear index of the brick whose distance byte is cached
+  uint32_t far_dist = 0;             // Chebyshev distance (bricks) from the current cell's brick to the nearest occupied one; >= 2: the ray may jump (try_jump)
+  bool far_empty = false;
   uint32_t odd;      // parity bits of the cell coordinates
   // compositing
   float thr = 1.0f, tPrev = -1.0f, cauchy = 0.0f;
@@ -148,10 +151,15 @@ template <int MODE, bool SPARSE, bool GREY, bool BAKED = false> struct FastMarch
     // both as PREDICATED loads, so that the lanes of a warp stay in lock-step through empty space
     const uint32_t b = (uint32_t)(cell[0] >> 3) + (uint32_t)(cell[1] >> 3) * S.nb8 + (uint32_t)(cell[2] >> 3) * S.nb8 * S.nb8;
     const uint32_t wi = b >> 5;
-    uint32_t w = brick_word;
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p ld.global.nc.u32 %0, [%3];\n\t}" : "+r"(w) : "r"(wi), "r"(brick_id), "l"(S.occ8 + wi));
+    uint32_t w = brick_word, fd = far_dist;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, %3;\n\t@p ld.global.nc.u32 %0, [%4];\n\tsetp.ne.u32 p, %5, %6;\n\t@p ld.global.nc.u8 %1, [%7];\n\t}"
+                 : "+r"(w), "+r"(fd)
+                 : "r"(wi), "r"(brick_id), "l"(S.occ8 + wi), "r"(b), "r"(brick_b), "l"(reinterpret_cast<const uint8_t *>(S.occ8 + S.occ8_words) + b));
     brick_word = w;
     brick_id = wi;
+    brick_b = b;
+    far_dist = fd;
+    far_empty = fd >= 2u;
     const uint32_t on = (w >> (b & 31)) & 1u;
     const uint32_t lin = (uint32_t)cell[0] + (uint32_t)cell[1] * S.n + (uint32_t)cell[2] * S.n * S.n;
     uint32_t fw = 0;
@@ -610,6 +618,45 @@ template <int MODE, bool SPARSE, bool GREY, bool BAKED = false> struct FastMarch
     return !(thr < 0.1f);                                      // :131
   }
 
+  // Empty-space jump for sparse sets.  Every 8^3-voxel brick carries its Chebyshev distance k (in bricks) to the nearest occupied
+  // brick.  k >= 2: the cube of bricks within k - 2 of the current one AND its one-brick rim are empty, so nothing the ray can touch
+  // before it has left that cube — face crossings, or the 3 / 7 cells of an edge / corner event on the cube's boundary — is present.
+  // So the traversal is re-seeded in the cell that holds the ray point just behind the cube's exit plane, PROVIDED that cell is
+  // certainly on the exact path: its fp32 slab interval
+  // [max tn, min tf] must be open by more than the rounding bound (then the exact fp64 interval is non-empty and the ray passes
+  // through the cell's interior; the per-cell state is a function of the cell alone, so the march continues bit for bit as if it
+  // had stepped there).  Otherwise nothing is changed and the march steps on voxel by voxel.
+  // Returns -1: the ray leaves the lattice (nothing present is left on it), 0: no jump, 1: jumped.
+  __device__ __forceinline__ int try_jump()
+  {
+    float tb = __int_as_float(0x7f800000);
+    const int r8 = ((int)far_dist - 2) * 8;                    // the bricks within far_dist - 2 of this one form the box to leave; its rim is empty too
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int lo = cell[a] & ~7;
+      const float pb = (float)(sgn[a] > 0 ? lo + 8 + r8 : lo - r8) * S.inv_gs_f;
+      tb = fminf(tb, idir(a) * (pb - o(a)));
+    }
+    const float tj = tb + fmaf(fabsf(tb), 0x1p-17f, 0x1p-40f);
+    int c[3];
+    bool outside = false;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      c[a] = (int)floorf((o(a) + tj * d(a)) * S.gs_f);
+      outside = outside || (unsigned)c[a] >= (unsigned)S.n;
+    }
+    if (outside) return -1;
+    if (c[0] == cell[0] && c[1] == cell[1] && c[2] == cell[2]) return 0;
+    const int old[3] = {cell[0], cell[1], cell[2]};
+    const uint32_t old_dirty = dirty;
+    set_cell(c[0], c[1], c[2]);
+    const float tmin = fmaxf(fmaxf(tn[0], tn[1]), tn[2]), tmax = fminf(fminf(tf[0], tf[1]), tf[2]);
+    if (tmax - tmin > fmaf(fabsf(tmax), 0x1p-19f, 0x1p-100f)) return 1;
+    set_cell(old[0], old[1], old[2]);                          // too close to call: back to the cell we stood on (same state, bit for bit)
+    dirty = old_dirty | dirty;
+    return 0;
+  }
+
   // fp32 filter on the three exit times: the axis whose plane comes first, or -1 when two of them are within the
   // rounding bound of each other (then the exact fp64 quotients decide)
   __device__ __forceinline__ int decide_fast() const
@@ -697,12 +744,19 @@ template <int MODE, bool SPARSE, bool GREY, bool BAKED = false> struct FastMarch
         int x, y, z;
         unpack_cell(queue[--nq], x, y, z);
         set_cell(x, y, z);
+        far_empty = false;                                     // describes another cell's brick
         return 1;
       }
       if (resync) {
         if (leaving_after) return -1;
         if (cell[0] != cur[0] || cell[1] != cur[1] || cell[2] != cur[2]) set_cell(cur[0], cur[1], cur[2]);
         resync = false;
+        far_empty = false;
+      }
+      if (SPARSE && far_empty) {                               // empty space: to the exit of the brick in one go
+        const int j = try_jump();
+        if (j < 0) return -1;
+        if (j > 0) return present_here() ? 1 : 0;
       }
       // ---- which face does the ray leave through?  fp32 filter, exact fp64 when close ----
       int ax = decide_fast();

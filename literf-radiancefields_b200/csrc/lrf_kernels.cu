@@ -1470,6 +1470,30 @@ __global__ void build_box_maps_kernel(int nv, const int32_t *__restrict__ xyz, s
   if (!((occ8[b >> 5] >> (b & 31)) & 1u)) atomicOr(occ8 + (b >> 5), 1u << (b & 31));
   vox2id[lin] = (uint32_t)t;
 }
+// brick distance field for the empty-space jump (FastMarch::try_jump): dist[b] = Chebyshev distance in bricks to the nearest occupied
+// brick, capped at kBrickDistCap.  One init pass + kBrickDistCap relaxation passes over the nb8^3 bricks (ping-pong).
+constexpr int kBrickDistCap = 40;
+__global__ void brick_dist_init_kernel(int nb8, const uint32_t *__restrict__ occ8, uint8_t *__restrict__ dist)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= (uint32_t)nb8 * nb8 * nb8) return;
+  dist[b] = ((occ8[b >> 5] >> (b & 31)) & 1u) ? 0 : kBrickDistCap;
+}
+__global__ void brick_dist_relax_kernel(int nb8, const uint8_t *__restrict__ in, uint8_t *__restrict__ out)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= (uint32_t)nb8 * nb8 * nb8) return;
+  const int bx = b % nb8, by = (b / nb8) % nb8, bz = b / (nb8 * nb8);
+  int m = in[b];
+  for (int dz = -1; dz <= 1; dz++)
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++) {
+        const int x = bx + dx, y = by + dy, z = bz + dz;
+        if ((unsigned)x >= (unsigned)nb8 || (unsigned)y >= (unsigned)nb8 || (unsigned)z >= (unsigned)nb8) continue;   // nothing exists outside the lattice
+        m = min(m, (int)in[(uint32_t)x + (uint32_t)y * nb8 + (uint32_t)z * nb8 * nb8] + 1);
+      }
+  out[b] = (uint8_t)m;
+}
 __global__ void count_nonzero_kernel(const uint8_t *__restrict__ marks, size_t n, unsigned long long *out)
 {
   unsigned long long local = 0;
@@ -1759,6 +1783,17 @@ void launch_build_box_maps(int nv, const int32_t *xyz, size_t n, uint32_t *occ, 
 {
   if (n == 0) return;
   build_box_maps_kernel<<<blocks_for(n, 256), 256, 0, st>>>(nv, xyz, n, occ, vox2id, occ8, nb8);
+}
+void launch_brick_dist(int nb8, const uint32_t *occ8, uint8_t *dist, uint8_t *tmp, cudaStream_t st)
+{
+  const unsigned g = blocks_for((size_t)nb8 * nb8 * nb8, 256);
+  brick_dist_init_kernel<<<g, 256, 0, st>>>(nb8, occ8, dist);
+  uint8_t *a = dist, *b = tmp;
+  for (int it = 0; it < kBrickDistCap; it++) {   // an even number of passes: the result ends in `dist`
+    brick_dist_relax_kernel<<<g, 256, 0, st>>>(nb8, a, b);
+    uint8_t *t = a; a = b; b = t;
+  }
+  static_assert(kBrickDistCap % 2 == 0, "ping-pong parity");
 }
 void launch_count_nonzero(const uint8_t *marks, size_t n, unsigned long long *out, cudaStream_t st)
 {

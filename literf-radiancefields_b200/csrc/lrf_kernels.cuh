@@ -98,6 +98,8 @@ void launch_box_compact_children(const int32_t *old_xyz, size_t n_old, const uin
                                  cudaStream_t st);
 void launch_box_compact(const int32_t *xyz, size_t n, const uint32_t *flags, const uint32_t *offsets, int32_t *new_xyz, cudaStream_t st);
 void launch_build_box_maps(int n_vox_axis, const int32_t *xyz, size_t n, uint32_t *occ, uint32_t *vox2id, uint32_t *occ8, int nb8, cudaStream_t st);
+// dist / tmp: nb8^3 bytes each; dist[b] = Chebyshev distance (bricks, capped) from brick b to the nearest occupied brick
+void launch_brick_dist(int nb8, const uint32_t *occ8, uint8_t *dist, uint8_t *tmp, cudaStream_t st);
 void launch_count_nonzero(const uint8_t *marks, size_t n, unsigned long long *out, cudaStream_t st);
 // exclusive prefix sum of uint32 flags (single-pass decoupled look-back is overkill here; two-level scan)
 void launch_exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *block_tmp, cudaStream_t st);
