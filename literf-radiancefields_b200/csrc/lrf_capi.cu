@@ -7,6 +7,7 @@
 //   occ, vox2id (sparse sets only)  : bitmap and id table over the (gs-1)^3 voxel lattice
 #include "../../include/lrf.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1708,6 +1709,32 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
   else if (s == "staged_render") h->staged = value ? 1 : 0;
   else if (s == "lean_render") h->lean = value ? 1 : 0;
+  else if (s == "l2_persist_density") {
+    // experiment (north_star: "L2-persisting windows"): value = percent of the density plane (0 = off) marked persisting in L2 for the
+    // kernels of this context's stream; the plane is 4 N bytes (67 MB at 256^3, the L2 is 126 MB).  Measured: DESIGN.md 4-K1c.
+    NEED_GRID(h);
+    cudaStreamAttrValue av{};
+    if (value > 0) {
+      int max_persist = 0, max_win = 0;
+      CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device));
+      CK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, h->device));
+      size_t bytes = h->N * sizeof(float);
+      if (bytes > (size_t)max_win) bytes = (size_t)max_win;
+      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+      av.accessPolicyWindow.base_ptr = h->params;
+      av.accessPolicyWindow.num_bytes = bytes;
+      av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)value / 100.0f * (float)max_persist / (float)bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      if (std::getenv("LRF_DEBUG")) std::fprintf(stderr, "[lrf] L2 window: %zu bytes, hit ratio %.2f (persisting L2 max %d MB, window max %d MB)\n", bytes, av.accessPolicyWindow.hitRatio, max_persist >> 20, max_win >> 20);
+    } else {
+      av.accessPolicyWindow.num_bytes = 0;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    if (value <= 0) CK(cudaCtxResetPersistingL2Cache());
+  }
   else if (s == "baked_records") h->baked = value ? 1 : 0;
   else if (s == "tv_sweep") h->tv_sweep = value ? 1 : 0;
   else if (s == "percell_overlap") h->percell_overlap = value;
