@@ -74,13 +74,6 @@ int lrf_get_boxes(lrf_ctx *h, int32_t *xyz);
 /* ref: SetWorldViewMatrix / SetWorldViewMProjatrix, example_tracer.h:214-215 (members m_worldViewInv, m_worldViewProjInv) */
 int lrf_set_view_inv(lrf_ctx *h, const float m16[16]);
 int lrf_set_proj_inv(lrf_ctx *h, const float m16[16]);
-/* caller-side helpers, bit-identical restatements of the LiteMath routines main.cpp uses
- * (main.cpp:78,99-102; LiteMath.h:1494-1499,1521-1529,1556-1569,1571-1653,1770-1815) for hosts
- * that do not have LiteMath (the Python harness): */
-void lrf_cam_perspective(float fovy, float aspect, float zn, float zf, float out16[16]);
-void lrf_cam_orbit_view(int k, int n_views, float out16[16]);
-void lrf_mat4_inverse(const float in16[16], float out16[16]);
-void lrf_mat4_mul(const float a16[16], const float b16[16], float out16[16]);
 
 /* ---- forward --------------------------------------------------------------------------------- */
 /* ref: kernel2D_RayMarch(uint32_t*,uint32_t,uint32_t,bool), example_tracer.cpp:627-663.

@@ -43,10 +43,6 @@ SIGNATURES = {
     "lrf_get_boxes": (C.c_int, [_vp, _c_i32p]),
     "lrf_set_view_inv": (C.c_int, [_vp, _c_fp]),
     "lrf_set_proj_inv": (C.c_int, [_vp, _c_fp]),
-    "lrf_cam_perspective": (None, [C.c_float, C.c_float, C.c_float, C.c_float, _c_fp]),
-    "lrf_cam_orbit_view": (None, [C.c_int, C.c_int, _c_fp]),
-    "lrf_mat4_inverse": (None, [_c_fp, _c_fp]),
-    "lrf_mat4_mul": (None, [_c_fp, _c_fp, _c_fp]),
     "lrf_render": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_rows_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
@@ -153,30 +149,50 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-# ---- caller-side camera helpers (main.cpp:78,99-102), bit-identical to LiteMath ----
+# ---- caller-side camera helpers (main.cpp:78,99-102), bit-identical to LiteMath: a small host-only helper library of the harness
+# (host/harness/lrf_camera.cpp -> _build/liblrf_camera.so), not part of the product library ----
+_cam = None
+
+
+def _camera_lib():
+    global _cam
+    if _cam is None:
+        path = os.path.join(os.path.dirname(LIB_PATH), "liblrf_camera.so")
+        if not os.path.exists(path):
+            raise LrfError("liblrf_camera.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+        _cam = C.CDLL(path)
+        _cam.lrf_cam_perspective.argtypes = [C.c_float] * 4 + [_c_fp]
+        _cam.lrf_cam_orbit_view.argtypes = [C.c_int, C.c_int, _c_fp]
+        _cam.lrf_mat4_inverse.argtypes = [_c_fp, _c_fp]
+        _cam.lrf_mat4_mul.argtypes = [_c_fp, _c_fp, _c_fp]
+        for f in (_cam.lrf_cam_perspective, _cam.lrf_cam_orbit_view, _cam.lrf_mat4_inverse, _cam.lrf_mat4_mul):
+            f.restype = None
+    return _cam
+
+
 def perspective(fovy, aspect, zn, zf):
     m = np.zeros(16, np.float32)
-    load_library().lrf_cam_perspective(fovy, aspect, zn, zf, _fp(m))
+    _camera_lib().lrf_cam_perspective(fovy, aspect, zn, zf, _fp(m))
     return m
 
 
 def orbit_view(k, n_views):
     m = np.zeros(16, np.float32)
-    load_library().lrf_cam_orbit_view(k, n_views, _fp(m))
+    _camera_lib().lrf_cam_orbit_view(k, n_views, _fp(m))
     return m
 
 
 def inverse4x4(m):
     m = _f32(m).ravel()
     out = np.zeros(16, np.float32)
-    load_library().lrf_mat4_inverse(_fp(m), _fp(out))
+    _camera_lib().lrf_mat4_inverse(_fp(m), _fp(out))
     return out
 
 
 def mat4_mul(a, b):
     a, b = _f32(a).ravel(), _f32(b).ravel()
     out = np.zeros(16, np.float32)
-    load_library().lrf_mat4_mul(_fp(a), _fp(b), _fp(out))
+    _camera_lib().lrf_mat4_mul(_fp(a), _fp(b), _fp(out))
     return out
 
 

@@ -41,7 +41,21 @@ def build_variant(name, defines):
     return lib
 
 
+CAMERA_SRC = os.path.join(HERE, "host", "harness", "lrf_camera.cpp")
+CAMERA_LIB = os.path.join(OUT_DIR, "liblrf_camera.so")
+
+
+def build_camera():
+    """the harness's host-only camera helpers (LiteMath restatements; not part of the product library)"""
+    if os.path.exists(CAMERA_LIB) and os.path.getmtime(CAMERA_LIB) >= os.path.getmtime(CAMERA_SRC):
+        return CAMERA_LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", CAMERA_LIB, CAMERA_SRC])
+    return CAMERA_LIB
+
+
 def build(force=False, verbose=False):
+    build_camera()
     if not force and not stale():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)

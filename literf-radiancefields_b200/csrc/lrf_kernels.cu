@@ -364,6 +364,9 @@ __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(c
 // Dense colour frames: the register-window march of lrf_lean.cuh (same decisions as FastMarch, bit for bit; fewer instructions and
 // L1 wavefronts per sample).  tap_n / tap_thr (TAPS): per-pixel shaded-sample count and final transmittance for the parity tests
 // (0xffffffff / NaN where the pixel went to the fallback list).
+#ifndef LRF_LEAN_TILE2D
+#define LRF_LEAN_TILE2D 0
+#endif
 template <bool TAPS>
 __global__ void __launch_bounds__(kBlock, LRF_LEAN_MINB) render_lean_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
                                                                             uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb,
@@ -372,7 +375,19 @@ __global__ void __launch_bounds__(kBlock, LRF_LEAN_MINB) render_lean_kernel(cons
   __shared__ uint64_t etab[32];
   load_exp_table(etab);
   uint32_t px, py;
+#if LRF_LEAN_TILE2D
+  {
+    // a block covers 16 x 8 pixels (2 x 2 warp tiles of 8 x 4) instead of a 32 x 4 strip: its four warps share more nodes in L1
+    const uint32_t bx_n = (w + 15) / 16;
+    const uint32_t bx = blockIdx.x % bx_n, by = blockIdx.x / bx_n, wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q = lane >> 3, sub = lane & 7;
+    px = bx * 16 + (wq & 1) * 8 + (q & 1) * 4 + (sub & 3);
+    py = by * 8 + (wq >> 1) * 4 + (q >> 1) * 2 + (sub >> 2);
+    if (px >= w || py >= hb) return;
+  }
+#else
   if (!tile_pixel(w, hb, px, py)) return;
+#endif
   py += y0;
   float o[3], d[3];
   gen_ray(S.view_inv, S.proj_inv, px, py, w, h, o, d);
@@ -1571,8 +1586,9 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
   const uint32_t hb = y1 - y0;
   const dim3 g(tile_grid(w, hb));
   if (lean && !S.occ && !grey && !S.rec) {
-    if (tap_n) render_lean_kernel<true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, tap_n, tap_thr);
-    else render_lean_kernel<false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, nullptr, nullptr);
+    const dim3 gl(LRF_LEAN_TILE2D ? ((w + 15) / 16) * ((hb + 7) / 8) : g.x);
+    if (tap_n) render_lean_kernel<true><<<gl, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, tap_n, tap_thr);
+    else render_lean_kernel<false><<<gl, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, nullptr, nullptr);
   } else if (S.occ) {
     if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
     else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);
