@@ -31,9 +31,10 @@ for scheme in ("peer", "allreduce"):
     ex = shard.PeerExchange(t, dist, torch) if scheme == "peer" else None
     n = t.lib.lrf_param_count(t.h)
 
-    class _Arr:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (t.lib.lrf_grad_device_ptr(t.h), False), "version": 2}
-    gten = torch.as_tensor(_Arr(), device="cuda")
+    def gview():   # the gradient pointer is not stable across lrf_train_percell_async (gradient ping-pong)
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (t.lib.lrf_grad_device_ptr(t.h), False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
     stream = torch.cuda.ExternalStream(t.lib.lrf_stream(t.h))
     for it in range(3):
         t.set_view_inv(pkg.inverse4x4(pkg.orbit_view(3 * it + rank, 16)))
@@ -43,7 +44,7 @@ for scheme in ("peer", "allreduce"):
             ex.percell(it)
         else:
             with torch.cuda.stream(stream):
-                shard.allreduce_gradient(gten, dist)
+                shard.allreduce_gradient(gview(), dist)
             t._ck(t.lib.lrf_train_percell_async(t.h, it))
         t.sync()
         if it == 0:
