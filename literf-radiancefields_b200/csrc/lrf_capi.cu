@@ -74,6 +74,7 @@ struct lrf_ctx
   CUdeviceptr mc_va = 0;
   size_t mc_bytes = 0;                               // padded size of one plane set
   int mc_state = 0;                                  // 0 none, 1 prepared (VMM), 2 object known, 3 device added, 4 bound + mapped
+  int mc_unroll = 4, mc_blocks_per_sm = 0;           // options "mc_unroll" (2 / 4 / 8 float4 in flight per thread), "mc_blocks_per_sm" (0 = one block per chunk, else a persistent grid)
   // staged forward render (lrf_staged.cuh): baked 64-byte node records + what was learnt while baking
   float4 *rec = nullptr;              // N records
   size_t rec_N = 0;
@@ -1551,8 +1552,8 @@ int lrf_adam_peer_async(lrf_ctx *h, int iter)
   if (h->mc) {
     if (h->mc_state != 4) return fail("multicast group not bound yet (lrf_mc_bind)");
     float *mcp = reinterpret_cast<float *>(h->mc_va), *mcg = reinterpret_cast<float *>(h->mc_va + h->mc_bytes);
-    launch_adam_mc(mcg, mcp, h->params, h->V, h->S, h->N / n * r, h->N / n, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, h->stream);
-    launch_adam_mc(mcg, mcp, h->params, h->V, h->S, h->N + h->N * 12 / n * r, h->N * 12 / n, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, h->stream);
+    launch_adam_mc(mcg, mcp, h->params, h->V, h->S, h->N / n * r, h->N / n, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, h->stream, h->mc_unroll, h->mc_blocks_per_sm);
+    launch_adam_mc(mcg, mcp, h->params, h->V, h->S, h->N + h->N * 12 / n * r, h->N * 12 / n, h->lr, h->beta1, h->beta2, h->eps, 1 - b1, 1 - b2, h->stream, h->mc_unroll, h->mc_blocks_per_sm);
     h->launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -1709,6 +1710,8 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
   else if (s == "staged_render") h->staged = value ? 1 : 0;
   else if (s == "lean_render") h->lean = value ? 1 : 0;
+  else if (s == "mc_unroll") h->mc_unroll = value;
+  else if (s == "mc_blocks_per_sm") h->mc_blocks_per_sm = value;
   else if (s == "l2_persist_density") {
     // experiment (north_star: "L2-persisting windows"): value = percent of the density plane (0 = off) marked persisting in L2 for the
     // kernels of this context's stream; the plane is 4 N bytes (67 MB at 256^3, the L2 is 126 MB).  Measured: DESIGN.md 4-K1c.

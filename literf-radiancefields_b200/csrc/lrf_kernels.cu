@@ -1295,32 +1295,35 @@ __device__ __forceinline__ void mc_st(float *mc, const float4 &v)
 {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-// count is a multiple of 4 (slabs of whole z planes of a grid whose size is a multiple of 8); kMcUnroll float4 per thread, all
+// count is a multiple of 4 (slabs of whole z planes of a grid whose size is a multiple of 8); UNROLL float4 per thread, all
 // reductions requested before the first one is consumed (a switch round trip is microseconds)
-constexpr int kMcUnroll = 4;
+template <int UNROLL>
 __global__ void __launch_bounds__(256) adam_mc_kernel(const float *__restrict__ mc_grad, float *__restrict__ mc_param, const float *__restrict__ param,
                                                       float *__restrict__ V, float *__restrict__ Sq, size_t off, size_t count, const AdamConst C)
 {
-  const size_t base = ((size_t)blockIdx.x * blockDim.x * kMcUnroll + threadIdx.x) * 4;
-  float4 g[kMcUnroll];
+  // grid-stride over chunks of 256 * UNROLL float4: a persistent grid (launch_adam_mc caps it) keeps every SM's request queues full
+  for (size_t chunk = blockIdx.x; chunk * (256 * UNROLL * 4) < count; chunk += gridDim.x) {
+    const size_t base = (chunk * 256 * UNROLL + threadIdx.x) * 4;
+    float4 g[UNROLL];
 #pragma unroll
-  for (int u = 0; u < kMcUnroll; u++) {
-    const size_t i4 = base + (size_t)u * blockDim.x * 4;
-    if (i4 < count) g[u] = mc_ld_reduce(mc_grad + off + i4);
-  }
+    for (int u = 0; u < UNROLL; u++) {
+      const size_t i4 = base + (size_t)u * 256 * 4;
+      if (i4 < count) g[u] = mc_ld_reduce(mc_grad + off + i4);
+    }
 #pragma unroll
-  for (int u = 0; u < kMcUnroll; u++) {
-    const size_t i4 = base + (size_t)u * blockDim.x * 4;
-    if (i4 >= count) continue;
-    const size_t at = off + i4;
-    float4 pv = *reinterpret_cast<const float4 *>(param + at);
-    float4 vv = *reinterpret_cast<float4 *>(V + at), sv = *reinterpret_cast<float4 *>(Sq + at);
-    const float4 gv = g[u];
-    adam_update(pv.x, gv.x, vv.x, sv.x, C); adam_update(pv.y, gv.y, vv.y, sv.y, C);
-    adam_update(pv.z, gv.z, vv.z, sv.z, C); adam_update(pv.w, gv.w, vv.w, sv.w, C);
-    *reinterpret_cast<float4 *>(V + at) = vv;
-    *reinterpret_cast<float4 *>(Sq + at) = sv;
-    mc_st(mc_param + at, pv);
+    for (int u = 0; u < UNROLL; u++) {
+      const size_t i4 = base + (size_t)u * 256 * 4;
+      if (i4 >= count) continue;
+      const size_t at = off + i4;
+      float4 pv = *reinterpret_cast<const float4 *>(param + at);
+      float4 vv = *reinterpret_cast<float4 *>(V + at), sv = *reinterpret_cast<float4 *>(Sq + at);
+      const float4 gv = g[u];
+      adam_update(pv.x, gv.x, vv.x, sv.x, C); adam_update(pv.y, gv.y, vv.y, sv.y, C);
+      adam_update(pv.z, gv.z, vv.z, sv.z, C); adam_update(pv.w, gv.w, vv.w, sv.w, C);
+      *reinterpret_cast<float4 *>(V + at) = vv;
+      *reinterpret_cast<float4 *>(Sq + at) = sv;
+      mc_st(mc_param + at, pv);
+    }
   }
 }
 
@@ -1740,14 +1743,19 @@ void launch_adam_peer(int world, int rank, float *const *grads, float *const *pa
   adam_peer_kernel<<<blocks_for((count + 3) / 4, 256), 256, 0, st>>>(P, V, S, off, count, C);
 }
 void launch_adam_mc(const float *mc_grad, float *mc_param, const float *param, float *V, float *S, size_t off, size_t count, float lr, float beta1,
-                    float beta2, float eps, double om_b1, double om_b2, cudaStream_t st)
+                    float beta2, float eps, double om_b1, double om_b2, cudaStream_t st, int unroll, int blocks_per_sm)
 {
   if (count == 0) return;
   AdamConst C;
   C.lr = lr; C.beta1 = beta1; C.beta2 = beta2; C.eps = eps;
   C.omb1f = 1 - beta1; C.omb2f = 1 - beta2;
   C.om_b1 = om_b1; C.om_b2 = om_b2; C.inv_om_b1 = 1.0 / om_b1; C.inv_om_b2 = 1.0 / om_b2;
-  adam_mc_kernel<<<blocks_for((count + 3) / 4, 256 * kMcUnroll), 256, 0, st>>>(mc_grad, mc_param, param, V, S, off, count, C);
+  if (unroll != 2 && unroll != 8) unroll = 4;
+  unsigned grid = blocks_for((count + 3) / 4, 256 * unroll);
+  if (blocks_per_sm > 0 && grid > 148u * blocks_per_sm) grid = 148u * blocks_per_sm;
+  if (unroll == 2) adam_mc_kernel<2><<<grid, 256, 0, st>>>(mc_grad, mc_param, param, V, S, off, count, C);
+  else if (unroll == 8) adam_mc_kernel<8><<<grid, 256, 0, st>>>(mc_grad, mc_param, param, V, S, off, count, C);
+  else adam_mc_kernel<4><<<grid, 256, 0, st>>>(mc_grad, mc_param, param, V, S, off, count, C);
 }
 void launch_peer_barrier(int world, int rank, uint32_t *const *flags, uint32_t epoch, uint32_t *timed_out, cudaStream_t st)
 {

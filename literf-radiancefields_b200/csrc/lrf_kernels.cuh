@@ -73,7 +73,7 @@ void launch_fill(float *p, size_t count, float v, cudaStream_t st);
 // the exchange through NVLink multicast objects: mc_grad / mc_param = multicast addresses of the gradient / parameter planes of the
 // group (multimem.ld_reduce / multimem.st), param = this rank's own (unicast) parameter planes; count a multiple of 4
 void launch_adam_mc(const float *mc_grad, float *mc_param, const float *param, float *V, float *S, size_t off, size_t count, float lr, float beta1,
-                    float beta2, float eps, double om_b1, double om_b2, cudaStream_t st);
+                    float beta2, float eps, double om_b1, double om_b2, cudaStream_t st, int unroll = 4, int blocks_per_sm = 0);
 void launch_peer_barrier(int world, int rank, uint32_t *const *flags, uint32_t epoch, uint32_t *timed_out, cudaStream_t st);
 // multi-GPU: TV gradient of the nodes in z-planes [z_begin, z_end) (multiples of 8), and the Adam pass over the element range
 // [off, off+count) that sums the gradient of all ranks through peer memory and writes the parameters to every replica

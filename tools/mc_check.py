@@ -64,6 +64,21 @@ for k in range(3):
     stage("unsynchronised iterations x10 (%d)" % k, lambda: [(t._ck(t.lib.lrf_rays_grad_tv_dev_async(t.h, n, od.ptr, dd.ptr, rf.ptr, 0)), ex.percell(3 + i, tv_done=True)) for i in range(10)])
 for k in range(3):
     stage("exchange alone x5 (%d)" % k, lambda: [ex.percell(40 + i, tv_done=True) for i in range(5)])
+if mode == "mc":
+    for unroll, bps in ((4, 0), (2, 0), (8, 0), (4, 8), (8, 4), (8, 8), (4, 16), (4, 0)):
+        t.set_option("mc_unroll", unroll)
+        t.set_option("mc_blocks_per_sm", bps)
+        for i in range(3):
+            ex.percell(100 + i, tv_done=True)
+        t.sync(); dist.barrier()
+        t.timer_start()
+        for i in range(10):
+            ex.percell(110 + i, tv_done=True)
+        ms = torch.tensor([t.timer_stop_ms() / 10], device="cuda")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print("exchange alone (barrier, multicast Adam pass, barrier, zero): unroll %d, blocks/SM cap %2d: %.3f ms" % (unroll, bps, float(ms.item())), flush=True)
+    t.set_option("mc_unroll", 4); t.set_option("mc_blocks_per_sm", 0)
 t.sync()
 p = t.get_grid()
 cs = float(np.abs(p.astype(np.float64)).sum())
