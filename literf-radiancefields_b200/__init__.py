@@ -157,7 +157,7 @@ _cam = None
 def _camera_lib():
     global _cam
     if _cam is None:
-        path = os.path.join(os.path.dirname(LIB_PATH), "liblrf_camera.so")
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liblrf_camera.so")
         if not os.path.exists(path):
             raise LrfError("liblrf_camera.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
         _cam = C.CDLL(path)

@@ -82,6 +82,7 @@ struct lrf_ctx
   float *dmax_dev = nullptr;          // largest |density| of the baked grid (device), and its host copy
   float dmax = 0.0f;
   uint32_t *st_stats = nullptr;       // 4 counters, see StagedArgs::stats
+  int wray_parallel = 1;              // option "wray_parallel": packed-batch backward enumerates the hits of a group on all lanes at once (lrf_wray.cuh); 0 = lock-step walk
   int lean = 1;                       // option "lean_render": dense colour frames by the register-window march (lrf_lean.cuh); 0 = FastMarch gather kernel
   int staged = 0;                     // option "staged_render": 1 = dense colour renders by the TMA-staged kernel (lrf_staged.cuh), 0 = by the gather kernel
   int tv_blocks_per_sm = 2;           // option "tv_blocks_per_sm": resident TV blocks per SM while it overlaps the colour Adam pass (0 = no cap)
@@ -1150,7 +1151,7 @@ int lrf_rays_grad_dev_async(lrf_ctx *h, size_t n, const float *o, const float *d
     }
     hits = h->hit_scratch;
   }
-  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->fb, h->fb + kFbHeader, hits, h->stream);
+  launch_grad_rays(scene_of(h), n, o, d, ref, grey, h->fb, h->fb + kFbHeader, hits, h->stream, h->wray_parallel);
   h->launches += 2;   // grad_rays_warp_kernel + the generic fallback over its queue
   CK(cudaGetLastError());
   return 0;
@@ -1710,6 +1711,7 @@ int lrf_set_option(lrf_ctx *h, const char *name, int value)
   else if (s == "generic_image_grad") h->generic_image_grad = value ? 1 : 0;
   else if (s == "staged_render") h->staged = value ? 1 : 0;
   else if (s == "lean_render") h->lean = value ? 1 : 0;
+  else if (s == "wray_parallel") h->wray_parallel = value ? 1 : 0;
   else if (s == "mc_unroll") h->mc_unroll = value;
   else if (s == "mc_blocks_per_sm") h->mc_blocks_per_sm = value;
   else if (s == "l2_persist_density") {

@@ -857,9 +857,10 @@ template <bool SPARSE, bool GREY>
 __global__ void __launch_bounds__(kWrayBlock, LRF_WRAY_MINB) grad_rays_warp_kernel(const __grid_constant__ SceneDev S, size_t n_rays, const float *__restrict__ ro,
                                                                 const float *__restrict__ rd, const float *__restrict__ ref_rgba,
                                                                 uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list,
-                                                                HitRec *__restrict__ hitbuf, uint32_t hitcap)
+                                                                HitRec *__restrict__ hitbuf, uint32_t hitcap, int parallel_gather)
 {
   __shared__ uint64_t etab[32];
+  __shared__ uint32_t wslots[kWrayBlock / 32][36];             // per warp: the rank -> crossing-count table of WarpRay::gather_parallel
   load_exp_table(etab);
   const size_t ray = ((size_t)blockIdx.x * kWrayBlock + threadIdx.x) >> 5;
   if (ray >= n_rays) return;
@@ -876,7 +877,7 @@ __global__ void __launch_bounds__(kWrayBlock, LRF_WRAY_MINB) grad_rays_warp_kern
     const float gsc = 0.11f * rp.z + 0.59f * rp.y + 0.3f * rp.x;
     ref[0] = ref[1] = ref[2] = gsc;
   }
-  warp_ray_backward<SPARSE, GREY>(S, etab, o, d, ref, hitbuf ? hitbuf + ray * hitcap : nullptr, hitcap);
+  warp_ray_backward<SPARSE, GREY>(S, etab, o, d, ref, hitbuf ? hitbuf + ray * hitcap : nullptr, hitcap, parallel_gather ? wslots[threadIdx.x >> 5] : nullptr);
 }
 
 // device-side ray generation for (view, pixel) picks — ref :635-639
@@ -1664,7 +1665,7 @@ size_t grad_rays_hit_bytes(size_t n, int gs, uint32_t *cap_out)
   return n * cap * sizeof(HitRec);
 }
 void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, uint32_t *fb_count,
-                      uint32_t *fb_list, void *hit_scratch, cudaStream_t st)
+                      uint32_t *fb_list, void *hit_scratch, cudaStream_t st, int parallel_gather)
 {
   if (n == 0) return;
   cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
@@ -1673,11 +1674,11 @@ void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *
   grad_rays_hit_bytes(n, S.gs, &cap);
   HitRec *hb = (HitRec *)hit_scratch;
   if (S.occ) {
-    if (grey) grad_rays_warp_kernel<true, true><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
-    else grad_rays_warp_kernel<true, false><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
+    if (grey) grad_rays_warp_kernel<true, true><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap, parallel_gather);
+    else grad_rays_warp_kernel<true, false><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap, parallel_gather);
   } else {
-    if (grey) grad_rays_warp_kernel<false, true><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
-    else grad_rays_warp_kernel<false, false><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap);
+    if (grey) grad_rays_warp_kernel<false, true><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap, parallel_gather);
+    else grad_rays_warp_kernel<false, false><<<g, kWrayBlock, 0, st>>>(S, n, o, d, ref_rgba, fb_count, fb_list, hb, cap, parallel_gather);
   }
   // rays the warp kernel cannot take (axis-aligned): the generic thread-per-ray march, usually an empty launch
   grad_kernel<false><<<blocks_for(n, kBlock), kBlock, 0, st>>>(S, 0, 0, n, o, d, ref_rgba, grey, fb_list, fb_count);

@@ -57,7 +57,7 @@ void launch_grad_image(const SceneDev &S, uint32_t w, uint32_t h, const float *r
 // hit_scratch: grad_rays_hit_bytes(n, gs) bytes where pass A leaves each ray's hit list for pass B, or nullptr (pass B walks again)
 size_t grad_rays_hit_bytes(size_t n, int gs, uint32_t *cap_out);
 void launch_grad_rays(const SceneDev &S, size_t n, const float *o, const float *d, const float *ref_rgba, int grey, uint32_t *fb_count,
-                      uint32_t *fb_list, void *hit_scratch, cudaStream_t st);
+                      uint32_t *fb_list, void *hit_scratch, cudaStream_t st, int parallel_gather = 1);
 void launch_gen_rays(const float *proj_inv_host16, size_t n, const float *view_inv_dev, const uint32_t *picks, uint32_t w, uint32_t h,
                      float *o, float *d, cudaStream_t st);
 // per-cell

@@ -22,6 +22,13 @@
 #pragma once
 #include "lrf_fast.cuh"
 
+#ifndef LRF_WRAY_PARALLEL
+#define LRF_WRAY_PARALLEL 1   // dense sets: hits of a group computed by all lanes at once (gather_parallel); 0 = always the lock-step walk
+#endif
+#ifndef LRF_WRAY_CHECK
+#define LRF_WRAY_CHECK 0      // debug build: run both and print mismatches
+#endif
+
 namespace lrf {
 
 // Exact hit enumeration without any node window: the traversal half of FastMarch.
@@ -36,6 +43,28 @@ template <bool SPARSE> struct RayWalker
   bool leaving_after = false, resync = true;
 
   __device__ RayWalker(const SceneDev &s) : S(s) {}
+  // the mutable part of the walker (debug builds compare the lane-parallel enumeration with the lock-step walk)
+  struct State
+  {
+    int cell[3], cur[3], nq;
+    float pa[3], tn[3], tf[3];
+    uint32_t queue[8];
+    bool leaving_after, resync;
+  };
+  __device__ __forceinline__ State save() const
+  {
+    State t;
+    for (int a = 0; a < 3; a++) { t.cell[a] = cell[a]; t.cur[a] = cur[a]; t.pa[a] = pa[a]; t.tn[a] = tn[a]; t.tf[a] = tf[a]; }
+    for (int i = 0; i < 8; i++) t.queue[i] = queue[i];
+    t.nq = nq; t.leaving_after = leaving_after; t.resync = resync;
+    return t;
+  }
+  __device__ __forceinline__ void restore(const State &t)
+  {
+    for (int a = 0; a < 3; a++) { cell[a] = t.cell[a]; cur[a] = t.cur[a]; pa[a] = t.pa[a]; tn[a] = t.tn[a]; tf[a] = t.tf[a]; }
+    for (int i = 0; i < 8; i++) queue[i] = t.queue[i];
+    nq = t.nq; leaving_after = t.leaving_after; resync = t.resync;
+  }
 
   __device__ __forceinline__ void set_cell(int x, int y, int z)
   {
@@ -241,7 +270,9 @@ template <bool SPARSE, bool GREY> struct WarpRay
   float Y[9];
   bool more = false;     // the walker currently stands on an unconsumed hit
 
-  __device__ WarpRay(const SceneDev &s, const uint64_t *t) : S(s), etab(t), lane(threadIdx.x & 31), W(s) {}
+  uint32_t *slot = nullptr;   // this warp's 36 words of shared memory for gather_parallel (nullptr: always walk serially)
+
+  __device__ WarpRay(const SceneDev &s, const uint64_t *t, uint32_t *sl = nullptr) : S(s), etab(t), lane(threadIdx.x & 31), W(s), slot(sl) {}
 
   __device__ __forceinline__ bool begin(const float *o, const float *d)
   {
@@ -249,9 +280,132 @@ template <bool SPARSE, bool GREY> struct WarpRay
     more = W.next();
     return more;
   }
+  // Dense sets: the next `want` hits by all lanes AT ONCE instead of 32 lock-step traversal steps (which were ~3/4 of this kernel's
+  // instructions).  On a dense lattice the hit sequence is the merge of three monotone sequences: the j-th crossing of axis a happens
+  // at  t_a(j) = idir_a * (plane_a(j) / gs - o_a)  — the very fp32 value the serial walk carries as tf[a] — and the r-th crossing
+  // overall leads to hit r.  Lane l takes crossing j = l + 1 of every axis, COUNTS the crossings of the other two axes that come
+  // before it (an estimate from the pitch, corrected against the exact fp32 times), and so knows its rank r = j + count_b + count_c
+  // and the cell it leads to: c0 + sgn * (n_x, n_y, n_z).  It leaves the triple in slot[r]; lane r picks it up and forms the hit's
+  // slab times from t_a(n_a) / t_a(n_a + 1).  Whenever two crossing times of the first 33 are within the rounding bound of each
+  // other (the serial walk would consult the exact fp64 quotients, and a true tie expands into 3 / 7 boxes) the group is walked
+  // serially instead: returns -1 with nothing changed.  Otherwise the fp32 order IS the exact order (lrf_fast.cuh) and the result is
+  // the serial walk's, bit for bit.
+  __device__ __forceinline__ int gather_parallel(LaneSample &L, int want)
+  {
+    if (SPARSE || slot == nullptr || !more || W.nq != 0 || W.leaving_after) return -1;
+    if (W.resync && (W.cell[0] != W.cur[0] || W.cell[1] != W.cur[1] || W.cell[2] != W.cur[2])) return -1;
+    const int n = S.n;
+    const int c0[3] = {W.cell[0], W.cell[1], W.cell[2]};
+    const int E[3] = {c0[0] + (W.sgn[0] > 0 ? 1 : 0), c0[1] + (W.sgn[1] > 0 ? 1 : 0), c0[2] + (W.sgn[2] > 0 ? 1 : 0)};
+    auto tcross = [&](int a, int j) { return W.idir[a] * ((float)(E[a] + (j - 1) * W.sgn[a]) * S.inv_gs_f - W.o[a]); };   // exact plane coordinate: gs = 2^k
+    const float INF = __int_as_float(0x7f800000);
+    __syncwarp();                                              // the previous group's slots have been read
+    const int j = lane + 1;
+    bool amb = false;
+    uint32_t my_exit = 99u;
+    if (lane == 0) slot[0] = 0u;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float T = tcross(a, j);
+      const float gate = fmaf(fabsf(T), 0x1p-19f, 0x1p-90f);
+      int cnt[3];
+      bool amb_a = false;
+      cnt[a] = j;
+#pragma unroll
+      for (int q = 1; q <= 2; q++) {
+        const int b = (a + q) % 3;
+        // crossings of axis b strictly before T: t_b(k) < T <= t_b(k + 1)
+        // (the estimate from the pitch is off by at most one; one correction step, then the bracket is CHECKED — a miss walks serially)
+        int k = 1 + (int)floorf((T - W.tf[b]) * (fabsf(W.d[b]) * S.gs_f));
+        k = max(0, min(k, 40));
+        float lo = k >= 1 ? tcross(b, k) : -INF, hi = tcross(b, k + 1);
+        if (!(lo < T)) { k--; hi = lo; lo = k >= 1 ? tcross(b, k) : -INF; }
+        else if (hi < T) { k++; lo = hi; hi = tcross(b, k + 1); }
+        if (k < 0 || !(lo < T) || hi < T || T - lo <= gate || hi - T <= gate) amb_a = true;
+        cnt[b] = max(k, 0);
+      }
+      const int rank = cnt[0] + cnt[1] + cnt[2];
+      if (rank <= 32) {
+        const bool exits = (unsigned)(c0[a] + j * W.sgn[a]) >= (unsigned)n;
+        slot[rank] = (uint32_t)cnt[0] | ((uint32_t)cnt[1] << 8) | ((uint32_t)cnt[2] << 16);
+        if (exits) my_exit = min(my_exit, (uint32_t)rank);
+        amb = amb || amb_a;
+      }
+    }
+    if (__any_sync(0xffffffffu, amb)) return -1;
+    const int r_exit = (int)__reduce_min_sync(0xffffffffu, my_exit);   // the crossing of this rank leaves the lattice: hits are ranks 0 .. r_exit - 1
+    const int m = min(want, r_exit);
+    __syncwarp();
+    auto times = [&](uint32_t packed, int *nn, float *tn_, float *tf_) {
+      nn[0] = (int)(packed & 255u); nn[1] = (int)((packed >> 8) & 255u); nn[2] = (int)((packed >> 16) & 255u);
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        tn_[a] = nn[a] >= 1 ? tcross(a, nn[a]) : W.tn[a];
+        tf_[a] = tcross(a, nn[a] + 1);
+      }
+    };
+    if (lane < m) {
+      int nn[3];
+      float tn_[3], tf_[3];
+      times(slot[lane], nn, tn_, tf_);
+      L.x = c0[0] + nn[0] * W.sgn[0]; L.y = c0[1] + nn[1] * W.sgn[1]; L.z = c0[2] + nn[2] * W.sgn[2];
+      L.tmin = fmaxf(fmaxf(tn_[0], tn_[1]), tn_[2]);
+      L.tmax = fminf(fminf(tf_[0], tf_[1]), tf_[2]);
+    }
+    W.resync = false;
+    if (m < r_exit) {                                          // the walker moves on to the first hit that was not latched
+      int nn[3];
+      float tn_[3], tf_[3];
+      times(slot[m], nn, tn_, tf_);
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        W.cell[a] = c0[a] + nn[a] * W.sgn[a];
+        W.pa[a] = (float)(E[a] + nn[a] * W.sgn[a]) * S.inv_gs_f;
+        W.tn[a] = tn_[a];
+        W.tf[a] = tf_[a];
+      }
+      more = true;
+    } else more = false;                                       // the ray left the lattice behind the last hit latched
+    return m;
+  }
   // latch up to `want` (<= 32) hits, lane k taking the k-th; returns the number latched
   __device__ __forceinline__ int gather(LaneSample &L, int want)
   {
+#if LRF_WRAY_PARALLEL
+    {
+#if LRF_WRAY_CHECK
+      const typename RayWalker<SPARSE>::State W0 = W.save();
+      const bool more0 = more;
+      LaneSample Lp = L;
+      const int mp = gather_parallel(Lp, want);
+      if (mp >= 0) {
+        const typename RayWalker<SPARSE>::State W1 = W.save();
+        const bool more1 = more;
+        W.restore(W0); more = more0;
+        int ms = 0;
+        while (ms < want && more) {
+          if (lane == ms) {
+            L.x = W.cell[0]; L.y = W.cell[1]; L.z = W.cell[2];
+            L.tmin = fmaxf(fmaxf(W.tn[0], W.tn[1]), W.tn[2]);
+            L.tmax = fminf(fminf(W.tf[0], W.tf[1]), W.tf[2]);
+          }
+          ms++;
+          more = W.next();
+        }
+        bool bad = ms != mp || more != more1;
+        if (lane < ms && (L.x != Lp.x || L.y != Lp.y || L.z != Lp.z || __float_as_uint(L.tmin) != __float_as_uint(Lp.tmin) || __float_as_uint(L.tmax) != __float_as_uint(Lp.tmax))) bad = true;
+        if (more && (W.cell[0] != W1.cell[0] || W.cell[1] != W1.cell[1] || W.cell[2] != W1.cell[2] || W.tf[0] != W1.tf[0] || W.tf[1] != W1.tf[1] || W.tf[2] != W1.tf[2] ||
+                     fmaxf(fmaxf(W.tn[0], W.tn[1]), W.tn[2]) != fmaxf(fmaxf(W1.tn[0], W1.tn[1]), W1.tn[2]) || W.pa[0] != W1.pa[0] || W.pa[1] != W1.pa[1] || W.pa[2] != W1.pa[2])) bad = true;
+        if (bad) printf("WRAY MISMATCH lane %d: serial m %d more %d cell %d %d %d t %a %a | parallel m %d more %d cell %d %d %d t %a %a\n", lane, ms, (int)more, L.x, L.y, L.z,
+                        L.tmin, L.tmax, mp, (int)more1, Lp.x, Lp.y, Lp.z, Lp.tmin, Lp.tmax);
+        return ms;
+      }
+#else
+      const int mp = gather_parallel(L, want);
+      if (mp >= 0) return mp;
+#endif
+    }
+#endif
     int m = 0;
     while (m < want && more) {
       if (lane == m) {
@@ -356,10 +510,10 @@ template <bool SPARSE, bool GREY> struct WarpRay
 // the closed form of the reverse sweep  aT <- tr aT + (1 - tr)(c . aC);  suffix_k = total - prefix_k.
 template <bool SPARSE, bool GREY>
 __device__ void warp_ray_backward(const SceneDev &S, const uint64_t *etab, const float *o, const float *d, const float *ref, HitRec *buf,
-                                  uint32_t cap)
+                                  uint32_t cap, uint32_t *slots = nullptr)
 {
   const int lane = threadIdx.x & 31;
-  WarpRay<SPARSE, GREY> R(S, etab);
+  WarpRay<SPARSE, GREY> R(S, etab, slots);
   if (!GREY) sh_eval_2(d, R.Y);
   double ctot[3] = {0.0, 0.0, 0.0};
   float aC[3] = {0.0f, 0.0f, 0.0f}, Tn = 0.0f, aTn = 0.0f;

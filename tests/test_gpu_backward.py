@@ -258,6 +258,52 @@ def test_packed_rays_backward_with_axis_aligned_and_tie_rays(pkg):
             S.close()
 
 
+@pytest.mark.parametrize("gs", [32, 128])
+def test_packed_backward_parallel_hits_equal_lockstep_walk(pkg, gs):
+    """the warp-per-ray backward enumerates the hits of a 32-hit group on all lanes at once (WarpRay::gather_parallel: rank of every
+    plane crossing from counts of the other axes' crossings) where the fp32 order is certainly the exact order, and walks in lock-step
+    otherwise.  Both must give the same hit list, so the two gradients may differ only by the order of the fp32 atomics (~1e-7
+    relative); ONE wrong or missing hit among ~100 per ray would show at >= 1e-5.  Rays: orbit-camera pixels (long, oblique), a
+    symmetric camera whose diagonal rays cross two planes at exactly the same time at every step, and lattice-rational rays."""
+    S, t = make_pair(pkg, gs, 20.0)
+    rays_o, rays_d = [], []
+    for k in (0, 3):
+        vi, pi = cameras(pkg, k, 7)
+        S.set_cam(vi, pi)
+        o_all, d_all = S.gen_rays(96, 96)
+        rays_o.append(o_all[::3]); rays_d.append(d_all[::3])
+    vi = np.zeros(16, np.float32)
+    vi[0] = 1.0; vi[5] = 1.0; vi[10] = -1.0; vi[15] = 1.0
+    vi[12], vi[13], vi[14] = 0.5, 0.5, -1.5
+    S.set_cam(vi, pi)
+    o_all, d_all = S.gen_rays(64, 64)
+    ok = (d_all != 0).all(axis=1)
+    rays_o.append(o_all[ok]); rays_d.append(d_all[ok])
+    rng = np.random.default_rng(5)
+    g = 1.0 / gs
+    oo = rng.integers(-8, 24, (200, 3)) * g * 0.5
+    dd = rng.integers(1, 5, (200, 3)).astype(np.float64) * rng.choice([-1.0, 1.0], (200, 3))
+    rays_o.append(oo.astype(np.float32)); rays_d.append((dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32))
+    o, d = np.concatenate(rays_o).astype(np.float32), np.concatenate(rays_d).astype(np.float32)
+    ref = rng.random((o.shape[0], 4)).astype(np.float32)
+    grads = {}
+    for mode in (1, 0):
+        t.set_option("wray_parallel", mode)
+        t.zeroGrad()
+        t.rays_grad(o, d, ref)
+        grads[mode] = t.get_grad().astype(np.float64)
+    t.set_option("wray_parallel", 1)
+    n0 = np.linalg.norm(grads[0])
+    assert n0 > 0
+    assert np.linalg.norm(grads[1] - grads[0]) <= 2e-6 * n0
+    # and against the oracle (the bar of the other backward tests)
+    S.O.orc_zero_grad(S.h)
+    S.O.orc_rays_grad(S.h, o.shape[0], fp(o), fp(d), fp(ref), 0)
+    assert_grad_close(S.grad.copy(), t.get_grad(), "parallel hit enumeration")
+    t.close()
+    S.close()
+
+
 @pytest.mark.parametrize("gs,wh,grey,sparse", [(32, 48, False, False), (32, 40, True, False), (64, 40, False, True)])
 def test_image_backward_fast_equals_generic(pkg, gs, wh, grey, sparse):
     """the whole-image backward on the forward's incremental window (lrf_fast.cuh MODE 2/3) against the older generic
