@@ -25,6 +25,9 @@
 #ifndef LRF_WRAY_PARALLEL
 #define LRF_WRAY_PARALLEL 1   // dense sets: hits of a group computed by all lanes at once (gather_parallel); 0 = always the lock-step walk
 #endif
+#ifndef LRF_WRAY_PREFETCH
+#define LRF_WRAY_PREFETCH 0   // colour lines of a group's corners requested while its density is being shaded
+#endif
 #ifndef LRF_WRAY_CHECK
 #define LRF_WRAY_CHECK 0      // debug build: run both and print mismatches
 #endif
@@ -451,6 +454,19 @@ template <bool SPARSE, bool GREY> struct WarpRay
     const float xy00 = lm_lerp(d000, d100, L.lf[0]), xy10 = lm_lerp(d010, d110, L.lf[0]);
     const float xy01 = lm_lerp(d001, d101, L.lf[0]), xy11 = lm_lerp(d011, d111, L.lf[0]);
     const float xyz0 = lm_lerp(xy00, xy10, L.lf[1]), xyz1 = lm_lerp(xy01, xy11, L.lf[1]);
+#if LRF_WRAY_PREFETCH
+    if (!GREY) {
+      // the colour of the 8 corners is wanted a few hundred cycles from now (behind the density lerps, expf and the 32-step throughput
+      // product): ask for its lines now — the kernel is bound by DRAM latency (71 % of the stall samples on the load scoreboard, issue
+      // slots 19 % busy), the gathers of a lane cannot all be in flight at once at 128 registers
+#pragma unroll
+      for (int cn = 0; cn < 8; cn++) {
+        const float4 *q = S.col + (size_t)(L.base + (cn & 1) + ((cn >> 1) & 1) * sy + ((cn >> 2) & 1) * sz) * kColF4;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 2));
+      }
+    }
+#endif
     L.dens_raw = lm_lerp(xyz0, xyz1, L.lf[2]);                 // :155-167, bit-exact
     L.sigma = L.dens_raw < 0.0f ? 0.0f : L.dens_raw;           // :170-171
     L.tr = expf_libm(-L.sigma * delta, etab);                  // :175
