@@ -29,6 +29,15 @@ namespace lrf {
 #ifndef LRF_LEAN_MINB
 #define LRF_LEAN_MINB 3      // resident blocks of 128 threads per SM the register allocation is sized for (168 registers)
 #endif
+#ifndef LRF_LEAN_NOBRANCH
+#define LRF_LEAN_NOBRANCH 1  // 1 = shade the colour of zero-weight samples too instead of branching around it
+#endif
+#ifndef LRF_LEAN_EXPF_NB
+#define LRF_LEAN_EXPF_NB 1   // branch-free libm-exact expf (range cases selected afterwards): +2.9 %
+#endif
+#ifndef LRF_LEAN_QPACK
+#define LRF_LEAN_QPACK 0
+#endif
 #ifndef LRF_LEAN_TWOPHASE
 #define LRF_LEAN_TWOPHASE 0  // 1 = the SH chunks of pairs 2, 3 are requested after the traversal step (16 fewer registers in flight across it)
 #endif
@@ -50,6 +59,34 @@ __device__ __forceinline__ void add_sel(bool p, float &a, float &b, float x, flo
 {
   asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.rn.f32 %0, %3, %4;\n\t@!q add.rn.f32 %1, %3, %4;\n\t}" : "+f"(a), "+f"(b) : "r"((uint32_t)p), "f"(x), "f"(y));
 }
+// expf_libm (lrf_device.cuh) without its range branch: the table path runs for every argument and the out-of-range results
+// (|x| >= 88: overflow / underflow / inf / nan, lrf_device.cuh:59-64) are selected over it afterwards — same values, no divergent branch
+__device__ __forceinline__ float expf_libm_nb(float x, const uint64_t *tab)
+{
+  const uint32_t ix = __float_as_uint(x);
+  const uint32_t abstop = (ix >> 20) & 0x7ff;
+  const double InvLn2N = 0x1.71547652b82fep+5, SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
+  const double z = InvLn2N * (double)x;
+  double kd = z + SHIFT;
+  const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+  kd = kd - SHIFT;
+  const double r = z - kd;
+  const uint64_t t = tab[ki & 31] + (ki << 47);
+  const double s = __longlong_as_double((long long)t);
+  const double zz = fma(C0, r, C1);
+  const double r2 = r * r;
+  double y = fma(C2, r, 1.0);
+  y = fma(zz, r2, y);
+  y = y * s;
+  float res = __double2float_rn(y);
+  // every special case implies |x| >= 88 (abstop >= 0x42b), so the selects need no outer test
+  res = x < -0x1.9fe368p6f ? 0.0f : res;
+  res = x > 0x1.62e42ep6f ? __int_as_float(0x7f800000) : res;
+  res = abstop >= 0x7f8 ? x + x : res;
+  res = ix == 0xff800000u ? 0.0f : res;
+  return res;
+}
 // packed lerp, tolerance path: a + t * (b - a) as two fma.rn.f32x2
 __device__ __forceinline__ u64 lerp2(u64 a, u64 b, u64 t, u64 neg1) { return fma2(t, fma2(a, neg1, b), a); }
 
@@ -61,7 +98,8 @@ static __device__ __noinline__ int lean_exact_cross(float p0, float p1, float p2
   return (t0 == em ? 1 : 0) | (t1 == em ? 2 : 0) | (t2 == em ? 4 : 0);
 }
 
-template <bool TAPS> struct LeanMarch
+// GATE = false compiles the step-length rule of ref :145-146 out (experiment only, see launch_render_image: it is NOT safe behind tie events)
+template <bool TAPS, bool GATE = true> struct LeanMarch
 {
   static constexpr uint32_t kFull = 1u, kResync = 2u, kLeaving = 4u, kSeeded = 8u, kHit = 16u, kQueue = 0xff00u;
 
@@ -171,13 +209,13 @@ template <bool TAPS> struct LeanMarch
     add_sel((st & (1u << J)) != 0, qr[J], qr[7 - J], ql, qh);
   }
   // geometry of the sample in the current cell, ref RayGridIntersection example_tracer.cpp:134-153 (bit-exact)
-  __device__ __forceinline__ void geometry(Geom &g)
+  template <bool G> __device__ __forceinline__ void geometry(Geom &g)
   {
     const float tmax = fminf(fminf(tf[0], tf[1]), tf[2]);      // all finite: == the std::min chain of :18-43
     if (tPrev < 0.0f) tPrev = tin;                             // :139
     const float t = (tin + tmax) * 0.5f;                       // :142
     float delta = t - tPrev;                                   // :144
-    if (delta > S.step_gate_f)                                 // :145-146
+    if (G && delta > S.step_gate_f)                            // :145-146
       delta = (float)((double)delta - (double)((int)((double)delta / S.step) - 1) * S.step);
     tPrev = t;                                                 // :190
     g.delta = delta;
@@ -208,23 +246,39 @@ template <bool TAPS> struct LeanMarch
     }
     float sigma = (od2 ? B[1] : B[0]) + s2 * (B[1] - B[0]);
     if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
+#if LRF_LEAN_EXPF_NB
+    const float tr = expf_libm_nb(-sigma * g.delta, etab);     // :175
+#else
     const float tr = expf_libm(-sigma * g.delta, etab);        // :175
+#endif
     const float wgt = thr * (1.0f - tr);                       // :187
+#if LRF_LEAN_NOBRANCH
+    {   // colour always (a zero weight adds exactly nothing): no divergent branch, no reconvergence barrier
+#else
     if (wgt != 0.0f) {
+#endif
       // ---- colour: 1e-4-tolerance path, packed nested lerps in slot order ----
       const float tx = od0 ? 1.0f - g.lf[0] : g.lf[0], ty = od1 ? 1.0f - g.lf[1] : g.lf[1], tz = od2 ? 1.0f - g.lf[2] : g.lf[2];
       const u64 TX = pk2(tx, tx), TY = pk2(ty, ty), TZ = pk2(tz, tz), N1 = pk2(-1.0f, -1.0f);
       u64 rg[4], bs[4];
-      float qa[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         rg[j] = lerp2(pk2(cw[2 * j].x, cw[2 * j].y), pk2(cw[2 * j + 1].x, cw[2 * j + 1].y), TX, N1);
         bs[j] = lerp2(pk2(cw[2 * j].z, cw[2 * j].w), pk2(cw[2 * j + 1].z, cw[2 * j + 1].w), TX, N1);
-        qa[j] = fmaf(tx, qr[2 * j + 1] - qr[2 * j], qr[2 * j]);
       }
       const u64 rg0 = lerp2(rg[0], rg[1], TY, N1), rg1 = lerp2(rg[2], rg[3], TY, N1);
       const u64 bs0 = lerp2(bs[0], bs[1], TY, N1), bs1 = lerp2(bs[2], bs[3], TY, N1);
+#if LRF_LEAN_QPACK
+      // q' lerps packed over z: (slot s, slot s + 4) pairs go through the x and y lerps together, the z lerp joins the halves
+      const u64 qx0 = lerp2(pk2(qr[0], qr[4]), pk2(qr[1], qr[5]), TX, N1), qx1 = lerp2(pk2(qr[2], qr[6]), pk2(qr[3], qr[7]), TX, N1);
+      float qb0, qb1;
+      upk2(lerp2(qx0, qx1, TY, N1), qb0, qb1);
+#else
+      float qa[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) qa[j] = fmaf(tx, qr[2 * j + 1] - qr[2 * j], qr[2 * j]);
       const float qb0 = fmaf(ty, qa[1] - qa[0], qa[0]), qb1 = fmaf(ty, qa[3] - qa[2], qa[2]);
+#endif
       float R, G, Bc, S0;
       upk2(lerp2(rg0, rg1, TZ, N1), R, G);
       upk2(lerp2(bs0, bs1, TZ, N1), Bc, S0);
@@ -412,7 +466,7 @@ template <bool TAPS> struct LeanMarch
       P.b[2] = __ldg(c2 + 1); P.e[2] = __ldg(c2 + 2);
       P.b[3] = __ldg(c3 + 1); P.e[3] = __ldg(c3 + 2);
 #endif
-      geometry(P.g);
+      geometry<GATE>(P.g);
       const bool more = next_cell();
 #if LRF_LEAN_TWOPHASE
       P.b[2] = __ldg(c2 + 1); P.e[2] = __ldg(c2 + 2);

@@ -25,12 +25,12 @@ def build(specs):
         for f in cf.as_completed(futs):
             lib = f.result()
             log = open(lib + ".log").read()
-            info = [l for l in log.splitlines() if "render_lean_kernelILb0" in l]
+            info = [l for l in log.splitlines() if "render_lean_kernelILb0ELb1" in l]
             # the ptxas line after "Compiling entry function ... render_image_kernel<0,0>" holds registers / spills
             lines = log.splitlines()
             used = ""
             for i, l in enumerate(lines):
-                if "Compiling entry function" in l and "render_lean_kernelILb0" in l:
+                if "Compiling entry function" in l and "render_lean_kernelILb0ELb1" in l:
                     used = " | ".join(x.strip() for x in lines[i + 1:i + 4])
                     break
             print(futs[f], "->", used)
