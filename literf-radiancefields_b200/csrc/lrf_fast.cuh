@@ -573,7 +573,7 @@ template <int MODE, bool SPARSE, bool GREY, bool BAKED = false> struct FastMarch
     const bool od[3] = {(g.odd & 1u) != 0, (g.odd & 2u) != 0, (g.odd & 4u) != 0};
     const float *lf = g.lf;
     const float tr = sg.tr, wgt = sg.wgt;
-    if (wgt != 0.0f) {
+    if (wgt != 0.0f) {                                         // (shading zero-weight samples too instead of branching pays in the register-window kernel, not here: 2.33 -> 2.47 ms)
       if (GREY) {
         col[0] = col[0] + wgt; col[1] = col[1] + wgt; col[2] = col[2] + wgt;
         if (MODE == 2) { csum[0] += (double)wgt; csum[1] += (double)wgt; csum[2] += (double)wgt; }

@@ -32,9 +32,6 @@ namespace lrf {
 #ifndef LRF_LEAN_NOBRANCH
 #define LRF_LEAN_NOBRANCH 1  // 1 = shade the colour of zero-weight samples too instead of branching around it
 #endif
-#ifndef LRF_LEAN_EXPF_NB
-#define LRF_LEAN_EXPF_NB 1   // branch-free libm-exact expf (range cases selected afterwards): +2.9 %
-#endif
 #ifndef LRF_LEAN_QPACK
 #define LRF_LEAN_QPACK 0
 #endif
@@ -58,34 +55,6 @@ __device__ __forceinline__ void ldg_pair_head(bool p, const float *dA, const flo
 __device__ __forceinline__ void add_sel(bool p, float &a, float &b, float x, float y)
 {
   asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.rn.f32 %0, %3, %4;\n\t@!q add.rn.f32 %1, %3, %4;\n\t}" : "+f"(a), "+f"(b) : "r"((uint32_t)p), "f"(x), "f"(y));
-}
-// expf_libm (lrf_device.cuh) without its range branch: the table path runs for every argument and the out-of-range results
-// (|x| >= 88: overflow / underflow / inf / nan, lrf_device.cuh:59-64) are selected over it afterwards — same values, no divergent branch
-__device__ __forceinline__ float expf_libm_nb(float x, const uint64_t *tab)
-{
-  const uint32_t ix = __float_as_uint(x);
-  const uint32_t abstop = (ix >> 20) & 0x7ff;
-  const double InvLn2N = 0x1.71547652b82fep+5, SHIFT = 0x1.8p+52;
-  const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
-  const double z = InvLn2N * (double)x;
-  double kd = z + SHIFT;
-  const uint64_t ki = (uint64_t)__double_as_longlong(kd);
-  kd = kd - SHIFT;
-  const double r = z - kd;
-  const uint64_t t = tab[ki & 31] + (ki << 47);
-  const double s = __longlong_as_double((long long)t);
-  const double zz = fma(C0, r, C1);
-  const double r2 = r * r;
-  double y = fma(C2, r, 1.0);
-  y = fma(zz, r2, y);
-  y = y * s;
-  float res = __double2float_rn(y);
-  // every special case implies |x| >= 88 (abstop >= 0x42b), so the selects need no outer test
-  res = x < -0x1.9fe368p6f ? 0.0f : res;
-  res = x > 0x1.62e42ep6f ? __int_as_float(0x7f800000) : res;
-  res = abstop >= 0x7f8 ? x + x : res;
-  res = ix == 0xff800000u ? 0.0f : res;
-  return res;
 }
 // packed lerp, tolerance path: a + t * (b - a) as two fma.rn.f32x2
 __device__ __forceinline__ u64 lerp2(u64 a, u64 b, u64 t, u64 neg1) { return fma2(t, fma2(a, neg1, b), a); }
@@ -246,11 +215,7 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
     }
     float sigma = (od2 ? B[1] : B[0]) + s2 * (B[1] - B[0]);
     if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
-#if LRF_LEAN_EXPF_NB
-    const float tr = expf_libm_nb(-sigma * g.delta, etab);     // :175
-#else
-    const float tr = expf_libm(-sigma * g.delta, etab);        // :175
-#endif
+    const float tr = expf_libm(-sigma * g.delta, etab);        // :175 (branch-free, lrf_device.cuh)
     const float wgt = thr * (1.0f - tr);                       // :187
 #if LRF_LEAN_NOBRANCH
     {   // colour always (a zero weight adds exactly nothing): no divergent branch, no reconvergence barrier
