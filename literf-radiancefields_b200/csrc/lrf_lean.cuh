@@ -81,7 +81,7 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
   uint32_t odd, negmask;         // parity bits of the cell coordinates; axes the ray travels down
   uint32_t stale = 0;            // bit J (J = 0..3): slot J is the stale member of pair (J, 7 - J), else slot 7 - J (or none)
   uint32_t cold = 0;             // rare-path flags, one register tested on the hot path: kFull | kResync | kLeaving | kSeeded, queue length << 8
-  float sd[3], hs[3];            // per axis: signed cell pitch of the exit plane (+-1/gs); offset from the exit plane back to the cell's lower plane (1/gs or 0)
+  float hs[3];                   // per axis: offset from the exit plane back to the cell's lower plane (1/gs or 0)
   uint32_t dn2[3];               // per axis: signed node-index step of two nodes
   float dn[8];
   float4 cw[8];                  // {R, G, B, sh0} as loaded
@@ -266,7 +266,6 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
       d_[a] = df[a];
       idir_[a] = 1.0f / df[a];                                 // ref example_tracer.cpp:20-22
       negmask |= df[a] > 0.0f ? 0u : (1u << a);
-      sd[a] = df[a] > 0.0f ? S.inv_gs_f : -S.inv_gs_f;
       hs[a] = df[a] > 0.0f ? S.inv_gs_f : 0.0f;
     }
     {
@@ -401,7 +400,9 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
 #pragma unroll
         for (int a = 0; a < 3; a++) {
           const bool on = (cm & (1u << a)) != 0;
-          const float pan = pa[a] + sd[a];                     // exact: multiples of 2^-k
+          // signed cell pitch copysign(1/gs, d): one LOP3 on the spot (as a per-ray register it was spilled and re-read every iteration)
+          const float sda = __uint_as_float(__float_as_uint(S.inv_gs_f) | (__float_as_uint(d_[a]) & 0x80000000u));
+          const float pan = pa[a] + sda;                       // exact: multiples of 2^-k
           const float tfn = idir_[a] * (pan - o_[a]);
           pa[a] = on ? pan : pa[a];
           tf[a] = on ? tfn : tf[a];
