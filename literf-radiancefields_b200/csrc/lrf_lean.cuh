@@ -1,26 +1,32 @@
 // lrf_lean.cuh — the dense colour forward march with the whole 2x2x2 node window in REGISTERS (round 2).
 //
 // Same results as FastMarch<0> of lrf_fast.cuh (bit-exact hit set, order, shaded-sample count and transmittance: every
-// decision-critical operation is the same IEEE operation on the same operands; RGB on the 1e-4 tolerance path), a third fewer
-// instructions and a third fewer L1 wavefronts per sample.  ncu on FastMarch (profiles/r1t_render_ncu_summary.txt) showed the
-// L1 data pipe 88 % busy and 415 warp instructions per sample-iteration; 57 of its 154 wavefronts per iteration were the
-// shared-memory colour window and the SH basis, 16 % of its instructions the selects of the parity-slot permutation and of a
-// traversal step that computed all three axes.  What is different here:
+// decision-critical operation is the same IEEE operation on the same operands; RGB on the 1e-4 tolerance path), 9 % fewer
+// instructions, a quarter fewer L1 wavefronts and three fewer divergent branches per sample.  ncu on FastMarch
+// (profiles/r1t_render_ncu_summary.txt) showed the L1 data pipe 88 % busy and 415 warp instructions per sample-iteration; 57 of its
+// 154 wavefronts per iteration were the shared-memory colour window and the SH basis, 16 % of its instructions the selects of the
+// parity-slot permutation and of a traversal step that computed all three axes.  What is different here:
 //
-//  * the colour window {R, G, B, q = sh . Y(d)} x 8 and the SH basis live in registers.  A face step replaces one member of each
-//    antipodal slot pair (J, 7 - J); the member is chosen by PREDICATED loads that write straight into the slot's registers
-//    (@p ld -> slot J, @!p ld -> slot 7 - J: two issue slots, no selects, no shared-memory round trip), and the SH contraction's
-//    last FMA is predicated the same way.  The density window is filled the same way.
+//  * the colour window {R, G, B, sh0} x 8, q' = sum_{j>=1} sh_j Y_j(d) x 8 and the SH basis live in registers.  A face step replaces
+//    one member of each antipodal slot pair (J, 7 - J); the member is chosen by PREDICATED loads that write straight into the slot's
+//    registers (@p ld [A] -> slot J, @!p ld [B] -> slot 7 - J: two issue slots, no selects, no shared-memory round trip), and the
+//    SH contraction's last add is predicated the same way.  Nothing reads a loaded register before the shading (a move of .w right
+//    behind the load made the warp wait for the gather there and then: 3.2 ms instead of 2.2).
 //  * the slab entry time is ONE running maximum: the reference's tmin = max_a tn[a] (RayBoxIntersection, ref
 //    example_tracer.cpp:18-43) where tn[a] is the exit time the ray had when it last crossed axis a; the exit-time sequence of an
 //    axis is monotone (fp32 subtraction and multiplication are monotone), so max_a tn[a] == max(tin, tf[crossed axis]) carried
 //    from cell to cell — three registers and the per-axis entry-time selects go away, bit for bit the same value.
-//  * the traversal step is predicated per axis (only the crossed axis's three operations execute), the cell coordinates are not
-//    carried at all (the exit-plane coordinates pa[] determine them; the lattice is left when pa leaves [0, n/gs]).
+//  * the traversal step works on a one-hot crossed-axis mask: the three axes' candidates are formed and the crossed one is kept
+//    by selects (an if / else per axis compiled to three divergent 25-instruction paths); the cell coordinates are not carried at
+//    all (the exit-plane coordinates pa[] determine them; the lattice is left when pa leaves [0, n/gs]); rare-path state is one
+//    flag register.
 //  * density lerps: the parity permutation costs one select per lerp instead of two: lerp(p1, p0, t) == p1 + (-t) * (p1 - p0)
 //    bit for bit (IEEE negation commutes with rounding), so the difference is formed once and the sign rides on t.
-//  * colour: packed nested lerps (fma.rn.f32x2) in slot order with t' = odd ? 1 - t : t (tolerance path), no weights.
+//  * colour: packed nested lerps (fma.rn.f32x2) in slot order with t' = odd ? 1 - t : t (tolerance path), no weights; shaded for
+//    zero-weight samples too (a zero weight adds exactly nothing) — no divergent branch, no reconvergence barrier; expf_libm
+//    (lrf_device.cuh) is branch-free for the same reason.
 // Tie events (edge / corner grazing, exact fp64 compare) re-seed the traversal from scratch like in FastMarch: cold code.
+// Measurements and the variants that did not pay: DESIGN.md 4-K1c.
 #pragma once
 #include "lrf_fast.cuh"
 
@@ -33,7 +39,7 @@ namespace lrf {
 #define LRF_LEAN_NOBRANCH 1  // 1 = shade the colour of zero-weight samples too instead of branching around it
 #endif
 #ifndef LRF_LEAN_QPACK
-#define LRF_LEAN_QPACK 0
+#define LRF_LEAN_QPACK 0     // 1 = the q' lerps packed over z (measured +0.3 %: noise)
 #endif
 #ifndef LRF_LEAN_TWOPHASE
 #define LRF_LEAN_TWOPHASE 0  // 1 = the SH chunks of pairs 2, 3 are requested after the traversal step (16 fewer registers in flight across it)
