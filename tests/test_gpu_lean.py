@@ -43,7 +43,7 @@ def _check(t, S, w, h):
     return int((ns_g == FALLBACK).sum()), int(ns_o.sum())
 
 
-@pytest.mark.parametrize("gs,D,wh", [(16, 20.0, 64), (32, 2.0, 96), (64, 20.0, 128), (128, 20.0, 160)])
+@pytest.mark.parametrize("gs,D,wh", [(4, 6.0, 48), (8, 20.0, 48), (16, 20.0, 64), (32, 2.0, 96), (64, 20.0, 128), (128, 20.0, 160)])
 def test_lean_orbit_views(pkg, gs, D, wh):
     grid = libs.lcg_grid(gs, D)
     S = OracleScene(gs, grid)
