@@ -42,7 +42,8 @@ namespace lrf {
 #define LRF_LEAN_QPACK 0     // 1 = the q' lerps packed over z (measured +0.3 %: noise)
 #endif
 #ifndef LRF_LEAN_TWOPHASE
-#define LRF_LEAN_TWOPHASE 0  // 1 = the SH chunks of pairs 2, 3 are requested after the traversal step (16 fewer registers in flight across it)
+#define LRF_LEAN_TWOPHASE 1  // SH chunks requested AFTER the traversal step: 0 = none, 1 = pairs 2, 3 (16 fewer registers in flight across it: no spills,
+                             // 2.02 -> 1.975 ms), 2 = pairs 1, 2, 3, 3 = all
 #endif
 
 // Predicated gathers of one antipodal slot pair: @p loads come from node A and land in slot J's registers, @!p loads from node B
@@ -432,18 +433,21 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
       Pending P;
       P.stale = stale;
       const float4 *c0 = issue_pair<0>(P.stale), *c1 = issue_pair<1>(P.stale), *c2 = issue_pair<2>(P.stale), *c3 = issue_pair<3>(P.stale);
-      P.b[0] = __ldg(c0 + 1); P.e[0] = __ldg(c0 + 2);
-      P.b[1] = __ldg(c1 + 1); P.e[1] = __ldg(c1 + 2);
-#if !LRF_LEAN_TWOPHASE
-      P.b[2] = __ldg(c2 + 1); P.e[2] = __ldg(c2 + 2);
-      P.b[3] = __ldg(c3 + 1); P.e[3] = __ldg(c3 + 2);
-#endif
+      // the SH chunks of the first (4 - LRF_LEAN_TWOPHASE * 2 ...) pairs fly across the traversal step, the rest are requested behind it
+      if (LRF_LEAN_TWOPHASE < 3) { P.b[0] = __ldg(c0 + 1); P.e[0] = __ldg(c0 + 2); }
+      if (LRF_LEAN_TWOPHASE < 2) { P.b[1] = __ldg(c1 + 1); P.e[1] = __ldg(c1 + 2); }
+      if (LRF_LEAN_TWOPHASE < 1) {
+        P.b[2] = __ldg(c2 + 1); P.e[2] = __ldg(c2 + 2);
+        P.b[3] = __ldg(c3 + 1); P.e[3] = __ldg(c3 + 2);
+      }
       geometry<GATE>(P.g);
       const bool more = next_cell();
-#if LRF_LEAN_TWOPHASE
-      P.b[2] = __ldg(c2 + 1); P.e[2] = __ldg(c2 + 2);
-      P.b[3] = __ldg(c3 + 1); P.e[3] = __ldg(c3 + 2);
-#endif
+      if (LRF_LEAN_TWOPHASE >= 3) { P.b[0] = __ldg(c0 + 1); P.e[0] = __ldg(c0 + 2); }
+      if (LRF_LEAN_TWOPHASE >= 2) { P.b[1] = __ldg(c1 + 1); P.e[1] = __ldg(c1 + 2); }
+      if (LRF_LEAN_TWOPHASE >= 1) {
+        P.b[2] = __ldg(c2 + 1); P.e[2] = __ldg(c2 + 2);
+        P.b[3] = __ldg(c3 + 1); P.e[3] = __ldg(c3 + 2);
+      }
       commit_pair<0>(P.stale, P.b[0], P.e[0]); commit_pair<1>(P.stale, P.b[1], P.e[1]);
       commit_pair<2>(P.stale, P.b[2], P.e[2]); commit_pair<3>(P.stale, P.b[3], P.e[3]);
       if (!shade(P.g)) return;
