@@ -367,8 +367,12 @@ __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(c
 #ifndef LRF_LEAN_TILE2D
 #define LRF_LEAN_TILE2D 1   // blocks of 16 x 8 pixels (2 x 2 warp tiles); 0 = 32 x 4 strips (measured: +0.5 % with 1)
 #endif
+#ifndef LRF_LEAN_BLOCK
+#define LRF_LEAN_BLOCK 128   // threads per block: 128 = 16 x 8 pixels, 64 = 16 x 4, 32 = 8 x 4 (one warp tile; same warps per SM, finer tail)
+#endif
+constexpr uint32_t kLeanBW = LRF_LEAN_BLOCK >= 64 ? 16 : 8, kLeanBH = LRF_LEAN_BLOCK >= 128 ? 8 : 4;
 template <bool TAPS, bool GATE>
-__global__ void __launch_bounds__(kBlock, LRF_LEAN_MINB) render_lean_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
+__global__ void __launch_bounds__(LRF_LEAN_BLOCK, LRF_LEAN_MINB * 128 / LRF_LEAN_BLOCK) render_lean_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
                                                                             uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb,
                                                                             uint32_t *__restrict__ tap_n, float *__restrict__ tap_thr)
 {
@@ -378,11 +382,11 @@ __global__ void __launch_bounds__(kBlock, LRF_LEAN_MINB) render_lean_kernel(cons
 #if LRF_LEAN_TILE2D
   {
     // a block covers 16 x 8 pixels (2 x 2 warp tiles of 8 x 4) instead of a 32 x 4 strip: its four warps share more nodes in L1
-    const uint32_t bx_n = (w + 15) / 16;
+    const uint32_t bx_n = (w + kLeanBW - 1) / kLeanBW;
     const uint32_t bx = blockIdx.x % bx_n, by = blockIdx.x / bx_n, wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t q = lane >> 3, sub = lane & 7;
-    px = bx * 16 + (wq & 1) * 8 + (q & 1) * 4 + (sub & 3);
-    py = by * 8 + (wq >> 1) * 4 + (q >> 1) * 2 + (sub >> 2);
+    px = bx * kLeanBW + (wq & 1) * 8 + (q & 1) * 4 + (sub & 3);
+    py = by * kLeanBH + (wq >> 1) * 4 + (q >> 1) * 2 + (sub >> 2);
     if (px >= w || py >= hb) return;
   }
 #else
@@ -1590,7 +1594,7 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
   const uint32_t hb = y1 - y0;
   const dim3 g(tile_grid(w, hb));
   if (lean && !S.occ && !grey && !S.rec) {
-    const dim3 gl(LRF_LEAN_TILE2D ? ((w + 15) / 16) * ((hb + 7) / 8) : g.x);
+    const dim3 gl(LRF_LEAN_TILE2D ? ((w + kLeanBW - 1) / kLeanBW) * ((hb + kLeanBH - 1) / kLeanBH) : g.x);
     // The step-length rule (ref :145-146: a sample step longer than sqrt(3) * step is shortened) cannot fire between CONSECUTIVE face-adjacent
     // cells of a dense lattice (the step is at most half the diagonal of a 2 x 1 x 1 box = 1.2247 / gs < 1.7320 / gs), and compiling it out
     // of the loop is worth 2 % (2.05 -> 2.01 ms per view).  But behind a tie event tPrev can be the ENTRY point of a cell (a grazing box
@@ -1598,11 +1602,11 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
     // iteration keeps it exact but costs more registers than the branch: 2.13 ms.)
     const bool gate = true;
     if (tap_n) {
-      if (gate) render_lean_kernel<true, true><<<gl, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, tap_n, tap_thr);
-      else render_lean_kernel<true, false><<<gl, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, tap_n, tap_thr);
+      if (gate) render_lean_kernel<true, true><<<gl, LRF_LEAN_BLOCK, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, tap_n, tap_thr);
+      else render_lean_kernel<true, false><<<gl, LRF_LEAN_BLOCK, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, tap_n, tap_thr);
     } else {
-      if (gate) render_lean_kernel<false, true><<<gl, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, nullptr, nullptr);
-      else render_lean_kernel<false, false><<<gl, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, nullptr, nullptr);
+      if (gate) render_lean_kernel<false, true><<<gl, LRF_LEAN_BLOCK, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, nullptr, nullptr);
+      else render_lean_kernel<false, false><<<gl, LRF_LEAN_BLOCK, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb, nullptr, nullptr);
     }
   } else if (S.occ) {
     if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, y0, hb);

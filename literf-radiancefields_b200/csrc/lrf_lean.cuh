@@ -41,6 +41,18 @@ namespace lrf {
 #ifndef LRF_LEAN_QPACK
 #define LRF_LEAN_QPACK 0     // 1 = the q' lerps packed over z (measured +0.3 %: noise)
 #endif
+#ifndef LRF_LEAN_PREDADD
+#define LRF_LEAN_PREDADD 1   // 1 = node-index updates of the traversal step as predicated adds (12 fewer instructions per sample)
+#endif
+#ifndef LRF_LEAN_DPACK
+#define LRF_LEAN_DPACK 1     // 1 = the x and y density lerps two at a time (add / mul / fma .f32x2: the same IEEE operations)
+#endif
+#ifndef LRF_LEAN_PREDASM
+#define LRF_LEAN_PREDASM 1   // 1 = the pair predicates are formed from the stale mask inside the asm blocks that use them
+#endif
+#ifndef LRF_LEAN_MERGE
+#define LRF_LEAN_MERGE 0     // rare-event regions per sample: 1 = step-length rule and first-cell / tie state share one, 2 = the full window load joins them (spills)
+#endif
 #ifndef LRF_LEAN_TWOPHASE
 #define LRF_LEAN_TWOPHASE 1  // SH chunks requested AFTER the traversal step: 0 = none, 1 = pairs 2, 3 (16 fewer registers in flight across it: no spills,
                              // 2.02 -> 1.975 ms), 2 = pairs 1, 2, 3, 3 = all
@@ -58,10 +70,35 @@ __device__ __forceinline__ void ldg_pair_head(bool p, const float *dA, const flo
       : "+f"(da), "+f"(db), "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w)
       : "r"((uint32_t)p), "l"(dA), "l"(dB), "l"(cA), "l"(cB));
 }
+// The same with the predicate formed from the stale mask inside the block (one LOP3 instead of a bool materialised and tested again) and the node
+// the SH chunks come from selected on the same predicate.
+template <uint32_t BIT>
+__device__ __forceinline__ uint32_t ldg_pair_head_m(uint32_t st, uint32_t nA, uint32_t nB, const float *dA, const float *dB, const float4 *cA, const float4 *cB,
+                                                    float &da, float &db, float4 &a, float4 &b)
+{
+  uint32_t nsel;
+  asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %11, %12;\n\tsetp.ne.u32 q, t, 0;\n\t"
+      "@q ld.global.nc.f32 %0, [%13];\n\t@!q ld.global.nc.f32 %1, [%14];\n\t"
+      "@q ld.global.nc.v4.f32 {%2, %3, %4, %5}, [%15];\n\t@!q ld.global.nc.v4.f32 {%6, %7, %8, %9}, [%16];\n\t"
+      "selp.u32 %10, %17, %18, q;\n\t}"
+      : "+f"(da), "+f"(db), "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w), "=r"(nsel)
+      : "r"(st), "n"(BIT), "l"(dA), "l"(dB), "l"(cA), "l"(cB), "r"(nA), "r"(nB));
+  return nsel;
+}
+template <uint32_t BIT> __device__ __forceinline__ void add_sel_m(uint32_t st, float &a, float &b, float x, float y)
+{
+  asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\t@q add.rn.f32 %0, %4, %5;\n\t@!q add.rn.f32 %1, %4, %5;\n\t}"
+      : "+f"(a), "+f"(b) : "r"(st), "n"(BIT), "f"(x), "f"(y));
+}
 // @p a = x + y, @!p b = x + y
 __device__ __forceinline__ void add_sel(bool p, float &a, float &b, float x, float y)
 {
   asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.rn.f32 %0, %3, %4;\n\t@!q add.rn.f32 %1, %3, %4;\n\t}" : "+f"(a), "+f"(b) : "r"((uint32_t)p), "f"(x), "f"(y));
+}
+// x += v if (m & BIT): one predicate-producing LOP3 and one predicated add (the ?: form compiled to shift / sign-extend / and / add)
+template <uint32_t BIT> __device__ __forceinline__ void add_if(uint32_t &x, uint32_t m, uint32_t v)
+{
+  asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 q, t, 0;\n\t@q add.u32 %0, %0, %3;\n\t}" : "+r"(x) : "r"(m), "n"(BIT), "r"(v));
 }
 // packed lerp, tolerance path: a + t * (b - a) as two fma.rn.f32x2
 __device__ __forceinline__ u64 lerp2(u64 a, u64 b, u64 t, u64 neg1) { return fma2(t, fma2(a, neg1, b), a); }
@@ -169,10 +206,16 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
   };
   template <int J> __device__ __forceinline__ const float4 *issue_pair(uint32_t st)
   {
-    const bool p = (st & (1u << J)) != 0;
     const uint32_t nA = slot_node(J), nB = slot_node(7 - J);
+#if LRF_LEAN_PREDASM
+    const uint32_t ns = ldg_pair_head_m<(1u << J)>(st, nA, nB, S.dens + nA, S.dens + nB, S.col + (size_t)nA * kColF4, S.col + (size_t)nB * kColF4, dn[J], dn[7 - J],
+                                                   cw[J], cw[7 - J]);
+    return S.col + (size_t)ns * kColF4;
+#else
+    const bool p = (st & (1u << J)) != 0;
     ldg_pair_head(p, S.dens + nA, S.dens + nB, S.col + (size_t)nA * kColF4, S.col + (size_t)nB * kColF4, dn[J], dn[7 - J], cw[J], cw[7 - J]);
     return S.col + (size_t)(p ? nA : nB) * kColF4;             // the SH chunks come from ONE address: an unsplit load costs fewer L1 wavefronts
+#endif
   }
   template <int J> __device__ __forceinline__ void commit_pair(uint32_t st, const float4 &b, const float4 &e)
   {
@@ -182,7 +225,11 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
     q2 = fma2(pk2(e.z, e.w), Y78, q2);
     float ql, qh;
     upk2(q2, ql, qh);
+#if LRF_LEAN_PREDASM
+    add_sel_m<(1u << J)>(st, qr[J], qr[7 - J], ql, qh);
+#else
     add_sel((st & (1u << J)) != 0, qr[J], qr[7 - J], ql, qh);
+#endif
   }
   // geometry of the sample in the current cell, ref RayGridIntersection example_tracer.cpp:134-153 (bit-exact)
   template <bool G> __device__ __forceinline__ void geometry(Geom &g)
@@ -191,8 +238,10 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
     if (tPrev < 0.0f) tPrev = tin;                             // :139
     const float t = (tin + tmax) * 0.5f;                       // :142
     float delta = t - tPrev;                                   // :144
+#if !LRF_LEAN_MERGE
     if (G && delta > S.step_gate_f)                            // :145-146
       delta = (float)((double)delta - (double)((int)((double)delta / S.step) - 1) * S.step);
+#endif
     tPrev = t;                                                 // :190
     g.delta = delta;
 #pragma unroll
@@ -209,7 +258,23 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
     const bool od0 = (g.odd & 1u) != 0, od1 = (g.odd & 2u) != 0, od2 = (g.odd & 4u) != 0;
     // ---- density: the reference's nested lerps (:155-167 via lerpCell :72-80), bit-exact ----
     const float s0 = od0 ? -g.lf[0] : g.lf[0], s1 = od1 ? -g.lf[1] : g.lf[1], s2 = od2 ? -g.lf[2] : g.lf[2];
-    float A[4], B[2];
+    float B[2];
+#if LRF_LEAN_DPACK
+    {   // the same IEEE operations, the subtraction and the addition two at a time: p1 - p0 as fma(p0, -1, p1) and base + m as fma(m, 1, base)
+        // (exact products).  The multiplication stays scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 — and even mul.rn.f32x2 +
+        // fma.rn.f32x2(m, 1, c) — into one FFMA2, which rounds once where the reference rounds twice.
+      const u64 N1 = pk2(-1.0f, -1.0f), P1 = pk2(1.0f, 1.0f);
+      auto lerp_pair = [&](u64 p0, u64 p1, float sg, bool od) {
+        float dl, dh;
+        upk2(fma2(p0, N1, p1), dl, dh);
+        return fma2(pk2(sg * dl, sg * dh), P1, od ? p1 : p0);
+      };
+      const u64 Aa = lerp_pair(pk2(dn[0], dn[4]), pk2(dn[1], dn[5]), s0, od0);   // {A[0], A[2]}
+      const u64 Ab = lerp_pair(pk2(dn[2], dn[6]), pk2(dn[3], dn[7]), s0, od0);   // {A[1], A[3]}
+      upk2(lerp_pair(Aa, Ab, s1, od1), B[0], B[1]);
+    }
+#else
+    float A[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const float p0 = dn[2 * j], p1 = dn[2 * j + 1];
@@ -220,6 +285,7 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
       const float p0 = A[2 * j], p1 = A[2 * j + 1];
       B[j] = (od1 ? p1 : p0) + s1 * (p1 - p0);
     }
+#endif
     float sigma = (od2 ? B[1] : B[0]) + s2 * (B[1] - B[0]);
     if (sigma < 0.0f) sigma = 0.0f;                            // :170-171
     const float tr = expf_libm(-sigma * g.delta, etab);        // :175 (branch-free, lrf_device.cuh)
@@ -342,29 +408,51 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
     const float pmax = (float)n * S.inv_gs_f;                  // exact
     cold = kResync | (leaving_after ? kLeaving : 0u) | ((uint32_t)nq << 8);
 
+    Pending P;
+    // cold: first cell, tie events.  0 = go on to the face selection, 1 = the next cell is set, 2 = the ray is done
+    auto cold_part = [&]() -> int {
+      int x, y, z;
+      const bool from_queue = (cold & kQueue) != 0;
+      bool reseed = true;
+      if (from_queue) {
+        cold -= 0x100u;
+        unpack_cell(queue[cold >> 8], x, y, z);
+      } else {
+        if (cold & kLeaving) return 2;
+        x = cur[0]; y = cur[1]; z = cur[2];
+        reseed = !(cold & kSeeded) || cell_of(0) != x || cell_of(1) != y || cell_of(2) != z;
+        cold &= ~kResync;
+      }
+      if (reseed) set_cell(x, y, z);
+      cold |= kSeeded;
+      if (from_queue) {
+        cold |= kHit;
+        return 1;
+      }
+      return 0;
+    };
     // moves the traversal to the next cell to be shaded; false = the ray is done
     auto next_cell = [&]() -> bool {
-      for (;;) {
-        if (cold & (kQueue | kResync)) {                       // cold: first cell, tie events
-          int x, y, z;
-          const bool from_queue = (cold & kQueue) != 0;
-          bool reseed = true;
-          if (from_queue) {
-            cold -= 0x100u;
-            unpack_cell(queue[cold >> 8], x, y, z);
-          } else {
-            if (cold & kLeaving) return false;
-            x = cur[0]; y = cur[1]; z = cur[2];
-            reseed = !(cold & kSeeded) || cell_of(0) != x || cell_of(1) != y || cell_of(2) != z;
-            cold &= ~kResync;
-          }
-          if (reseed) set_cell(x, y, z);
-          cold |= kSeeded;
-          if (from_queue) {
-            cold |= kHit;
-            return true;
-          }
+#if LRF_LEAN_MERGE
+      // ONE rare region per sample in front of the face selection: the full window load a re-seed asked for (the stale-pair requests issued
+      // just before it reload slots from their own nodes: harmless), the step-length rule (ref :145-146), and the first-cell / tie-event state
+      if ((cold & ((LRF_LEAN_MERGE > 1 ? kFull : 0u) | kQueue | kResync)) | (uint32_t)(GATE && P.g.delta > S.step_gate_f)) {
+        if (LRF_LEAN_MERGE > 1 && (cold & kFull)) load_all();
+        if (GATE && P.g.delta > S.step_gate_f)
+          P.g.delta = (float)((double)P.g.delta - (double)((int)((double)P.g.delta / S.step) - 1) * S.step);
+        if (cold & (kQueue | kResync)) {
+          const int r = cold_part();
+          if (r) return r == 1;
         }
+      }
+#endif
+      for (;;) {
+#if !LRF_LEAN_MERGE
+        if (cold & (kQueue | kResync)) {
+          const int r = cold_part();
+          if (r) return r == 1;
+        }
+#endif
         // ---- which face does the ray leave through?  fp32 filter, exact fp64 when close (lrf_fast.cuh) ----
         const float m = fminf(fminf(tf[0], tf[1]), tf[2]);
         const float gate = fmaf(fabsf(m), 0x1p-20f, 0x1p-100f);
@@ -393,6 +481,12 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
             const int mm = build_event_cells(S, lo[0], lo[1], lo[2], cross, cross, pos_mask, cells);
             for (int j = 0; j < mm; j++) queue[j] = cells[mm - 1 - j];
             cold = (cold & ~kQueue) | ((uint32_t)mm << 8) | kResync;
+#if LRF_LEAN_MERGE
+            {
+              const int r = cold_part();
+              if (r) return r == 1;
+            }
+#endif
             continue;
           }
           cm = (uint32_t)cross;
@@ -415,9 +509,15 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
           tf[a] = on ? tfn : tf[a];
         }
         const float pnew = x0 ? pa[0] : (x1 ? pa[1] : pa[2]);
+#if LRF_LEAN_PREDADD
+        add_if<1>(nx[0], up0, dn2[0]); add_if<1>(nx[1], up1, dn2[0]);
+        add_if<2>(ny[0], up0, dn2[1]); add_if<2>(ny[1], up1, dn2[1]);
+        add_if<4>(nz[0], up0, dn2[2]); add_if<4>(nz[1], up1, dn2[2]);
+#else
         nx[0] += (up0 & 1u) ? dn2[0] : 0u; nx[1] += (up1 & 1u) ? dn2[0] : 0u;
         ny[0] += (up0 & 2u) ? dn2[1] : 0u; ny[1] += (up1 & 2u) ? dn2[1] : 0u;
         nz[0] += (up0 & 4u) ? dn2[2] : 0u; nz[1] += (up1 & 4u) ? dn2[2] : 0u;
+#endif
         // stale low members: the slots J < 4 whose bit along the crossed axis equals the leaving parity (x: 5 / a, y: 3 / c, z: f / 0)
         stale = ((0xf35u >> ((cm >> 1) * 4u)) & 0xfu) ^ (up1 ? 0xfu : 0u);
         if (pnew > pmax || pnew < 0.0f) return false;          // left the lattice
@@ -425,12 +525,14 @@ template <bool TAPS, bool GATE = true> struct LeanMarch
       }
     };
 
+    P.g.delta = 0.0f;
     if (!next_cell()) return;
     for (;;) {
       // One sample: (1) request the stale half of the window for the current cell, (2) the cell's geometry and the whole traversal
       // step to the next cell while the loads fly, (3) contract, shade, composite.
+#if LRF_LEAN_MERGE < 2
       if (cold & kFull) load_all();
-      Pending P;
+#endif
       P.stale = stale;
       const float4 *c0 = issue_pair<0>(P.stale), *c1 = issue_pair<1>(P.stale), *c2 = issue_pair<2>(P.stale), *c3 = issue_pair<3>(P.stale);
       // the SH chunks of the first (4 - LRF_LEAN_TWOPHASE * 2 ...) pairs fly across the traversal step, the rest are requested behind it
