@@ -43,9 +43,16 @@ def time_one(n_views):
     import __graft_entry__ as ge
     import bench
     pkg = ge.package()
+    if os.environ.get("LRF_VARIANTS_WORKLOAD"):     # e.g. sparse512, hires512_1080p (bench.py's workload table)
+        bench.select_workload(os.environ["LRF_VARIANTS_WORKLOAD"])
     t = pkg.RayMarcherExample(0)
     t.InitGrid(bench.GS)
-    t.set_grid(bench.lcg_grid(bench.GS, bench.DENSITY_SCALE))
+    if bench.FILL_MODE is None:
+        t.set_grid(bench.lcg_grid(bench.GS, bench.DENSITY_SCALE))
+    else:
+        t.fill_synthetic(bench.DENSITY_SCALE, bench.FILL_MODE)
+    if bench.SPARSE:
+        t.RebuildOctree()
     proj_inv, views = bench.cameras(pkg, 0, 1)
     t.set_proj_inv(proj_inv)
     frame = pkg.DeviceBuffer(t, bench.W * bench.H * 4)
