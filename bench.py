@@ -11,12 +11,13 @@ With N GPUs each rank holds a grid replica and renders its own 100 views of a 10
 interleaved over ranks): per-GPU work fixed => "scaling": "weak", no data-path collective.
 
   value     Mrays/s with everything resident in HBM (grid, output frames), CUDA events on the launching
-            stream, max over ranks.
-  e2e       same metric through the public host API (RayMarcherExample.kernel2D_RayMarch == lrf_render):
-            per view the camera goes host->device and the finished frame device->pinned host, inside the
-            timed region.
-  roofline  dominant kernel render_lean_kernel (lrf_lean.cuh): algorithmic bytes per launch = 52 B x (distinct grid nodes
-            read by shaded samples of the view, counted on the device) + 4 B x rays, / mean launch time.
+            stream, max over ranks.  A step is ONE call of lrf_render_views_dev_async: the step's views in one launch
+            of the forward kernel (no idle SMs between views), frame v of a views x frame device buffer.
+  e2e       same metric through the public host API (RayMarcherExample.render_views == lrf_render_views): the view
+            matrices go host->device and every finished frame device->pinned host inside the timed region,
+            synchronous like kernel2D_RayMarch; three of the frames are compared with kernel2D_RayMarch's afterwards.
+  roofline  dominant kernel render_lean_kernel (lrf_lean.cuh): algorithmic bytes per launch = sum over the launch's views of
+            52 B x (distinct grid nodes read by shaded samples of the view, counted on the device) + 4 B x rays, / mean launch time.
   cpu_baseline  the reference's kernel2D_RayMarch compiled from /root/reference (oracle/_ref/libref_O3.so,
             -O3 -fopenmp -ffp-contract=off) on the same grid + camera, bounded sample (a 96x96 frame of view 0).
 """
@@ -118,15 +119,22 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, or None"""
+def ncu_traffic(views_per_launch):
+    """(dram bytes per launch of the dominant kernel, provenance) from the committed ncu --set full summaries, or (None, why)"""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    src = "from file: profiles/roofline_traffic.json (dram__bytes_read + dram__bytes_write of this kernel in a committed ncu --set full capture); not measured in this run"
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("render_lean_kernel", {}).get("dram_bytes_per_launch")
+            d = json.load(open(p))
+            b = d.get("render_lean_kernel_batch", {})
+            if b.get("views_per_launch") == views_per_launch:
+                return b.get("dram_bytes_per_launch"), src + "; capture of one %d-view launch" % views_per_launch
+            v = d.get("render_lean_kernel", {}).get("dram_bytes_per_launch")
+            if v is not None:
+                return v * views_per_launch, src + "; capture of a one-view launch x %d views" % views_per_launch
         except Exception:
             pass
-    return None
+    return None, "no committed capture"
 
 
 def sharding():
@@ -337,10 +345,12 @@ def main():
         return float(v.item())
 
     # ---- value: device-resident ----
+    # one step = the VIEWS views of this GPU's shard through lrf_render_views_dev_async: one launch of the forward kernel over all views
+    # (frame v of `frames`), the view matrices travel inside the call
+    frames = pkg.DeviceBuffer(t, len(views) * W * H * 4)
+
     def step_resident():
-        for vi in views:
-            t.set_view_inv(vi)
-            t.render_dev_async(frame.ptr, W, H)
+        t.render_views_dev_async(views, frames.ptr, W, H)
 
     for _ in range(warmup):
         step_resident()
@@ -362,13 +372,13 @@ def main():
     value = rays_per_step * steps / (ms * 1e-3) / 1e6
 
     # ---- e2e: host API, camera h2d + frame d2h per view inside the timed region ----
-    pinned = pkg.PinnedBuffer(W * H, np.uint32)
+    pinned = pkg.PinnedBuffer(len(views) * W * H, np.uint32)
     e2e_steps = max(1, min(steps, 2))
 
     def step_host():
-        for vi in views:
-            t.set_view_inv(vi)                       # host matrices travel as kernel arguments
-            t.kernel2D_RayMarch(pinned.array, W, H)  # kernel + D2H of the frame into pinned host memory, synchronous
+        # host matrices in, every finished frame out into pinned host memory, synchronous (lrf_render_views: batches of views, a finished
+        # batch is copied out while the next one renders)
+        t.render_views(views, pinned.array, W, H)
 
     step_host()
     barrier()
@@ -377,8 +387,15 @@ def main():
         step_host()
     t.sync()
     e2e_s = max_over_ranks(time.perf_counter() - te0)
-    checksum = int(pinned.array.astype(np.uint64).sum())
+    checksum = int(pinned.array[-W * H:].astype(np.uint64).sum())      # the last view's frame, as before the batch call existed
     e2e_value = rays_per_step * e2e_steps / e2e_s / 1e6
+    # the batch frames are the frames the per-view call (kernel2D_RayMarch == lrf_render) delivers: checked on three views, outside the timed regions
+    one = np.zeros(W * H, np.uint32)
+    batch_ok = True
+    for k in sorted({0, len(views) // 2, len(views) - 1}):
+        t.set_view_inv(views[k])
+        t.kernel2D_RayMarch(one, W, H)
+        batch_ok = batch_ok and bool(np.array_equal(one, pinned.array[k * W * H:(k + 1) * W * H]))
 
     # ---- roofline of the dominant kernel ----
     sel = list(range(0, VIEWS, 10 if VIEWS >= 20 else 2))
@@ -387,18 +404,21 @@ def main():
         t.set_view_inv(views[k])
         touched.append(t.count_touched_nodes(W, H))
     n_touched = float(np.mean(touched))
-    alg_bytes = 52.0 * n_touched + 4.0 * W * H
-    kernel_ms = ms / (steps * VIEWS)               # launches are back to back on one stream: mean launch duration
+    alg_bytes_view = 52.0 * n_touched + 4.0 * W * H
+    alg_bytes = alg_bytes_view * len(views)        # ONE launch renders the step's views
+    kernel_ms = ms / steps                         # the step is that launch (plus the 3 us fallback kernel): mean launch duration
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                "kernel": "render_lean_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+    traffic, traffic_src = ncu_traffic(len(views))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "render_lean_kernel", "kernel_ms": kernel_ms, "views_per_launch": len(views), "kernel_ms_per_view": kernel_ms / len(views),
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_view": alg_bytes_view,
                 "n_touched_nodes_mean": n_touched, "n_touched_sampled_views": len(sel), "peak_source": peak_src,
-                "traffic_source": "from file: profiles/roofline_traffic.json (dram__bytes_read + dram__bytes_write of this kernel in a committed ncu --set full capture); not measured in this run"}
+                "traffic_source": traffic_src}
     if WORKLOAD != "render256":
         roofline["traffic"] = None     # the committed ncu capture is of the default workload
 
-    extra = {"e2e_checksum": checksum}
+    extra = {"e2e_checksum": checksum, "batch_frames_equal_per_view_frames": batch_ok}
     if SPARSE:
         extra["boxes"] = int(t.box_count())
         extra["occupancy"] = t.box_count() / float((GS - 1) ** 3)

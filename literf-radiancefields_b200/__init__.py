@@ -45,6 +45,8 @@ SIGNATURES = {
     "lrf_set_proj_inv": (C.c_int, [_vp, _c_fp]),
     "lrf_render": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
+    "lrf_render_views_dev_async": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
+    "lrf_render_views": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_rows_dev_async": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "lrf_render_staged_debug": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32]),
     "lrf_render_lean_debug": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32]),
@@ -382,6 +384,18 @@ class RayMarcherExample:
 
     def render_dev_async(self, out_dev_ptr, width, height, greyscale=False):
         self._ck(self.lib.lrf_render_dev_async(self.h, out_dev_ptr, width, height, int(greyscale)))
+
+    def render_views_dev_async(self, view_invs, out_dev_ptr, width, height, greyscale=False):
+        """len(view_invs) frames (width*height pixels apart in the device buffer) in one call; view_invs: inverse view matrices, 16 floats each"""
+        m = np.ascontiguousarray(np.asarray(view_invs, dtype=np.float32).reshape(-1, 16))
+        self._ck(self.lib.lrf_render_views_dev_async(self.h, m.shape[0], m.ctypes.data_as(_vp), out_dev_ptr, width, height, int(greyscale)))
+
+    def render_views(self, view_invs, out_color, width, height, greyscale=False):
+        """len(view_invs) frames into the host array out_color (uint32, frame v at v*width*height; PinnedBuffer.array for overlapped copies), synchronous"""
+        m = np.ascontiguousarray(np.asarray(view_invs, dtype=np.float32).reshape(-1, 16))
+        assert out_color.dtype == np.uint32 and out_color.size >= m.shape[0] * width * height and out_color.flags.c_contiguous
+        self._ck(self.lib.lrf_render_views(self.h, m.shape[0], m.ctypes.data_as(_vp), out_color.ctypes.data, width, height, int(greyscale)))
+        return out_color
 
     def render_rows_dev_async(self, out_dev_ptr, width, height, y0, y1, greyscale=False):
         """rows [y0, y1) of the frame into the full-frame device buffer (latency mode: row bands over GPUs)"""

@@ -50,6 +50,8 @@ struct lrf_ctx
   // fallback queue of the forward render (rays that need the generic march): [0] = count, [1..] = pixel indices
   uint32_t *fb = nullptr;
   size_t fb_cap = 0;
+  float *views_dev = nullptr;         // view matrices of a batch render (lrf_render_views_dev_async), n x 16 floats
+  size_t views_cap = 0;
   void *hit_scratch = nullptr;        // per-ray hit lists of the packed-batch backward
   size_t hit_bytes = 0;
   int generic_image_grad = 0;   // 1: whole-image backward by the generic thread-per-ray kernel (tests compare the two)
@@ -785,6 +787,7 @@ int lrf_destroy(lrf_ctx *h)
   free_grid(h);
   cudaFree(h->stage);
   cudaFree(h->fb);
+  cudaFree(h->views_dev);
   cudaFree(h->hit_scratch);
   cudaFree(h->targets);
   cudaFree(h->gamma_lut);
@@ -955,6 +958,47 @@ int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt
   CK(cudaGetLastError());
   return 0;
 }
+// n_views frames in one call: frame v (w * hgt pixels) of out_dev is the render with view matrix view_inv_host[16 v .. 16 v + 15] (the
+// projection matrix, grid and options are the context's; the context's own view matrix is left as it was).  Dense colour frames go to ONE
+// launch of the register-window march over all views (no idle SMs between views); every other configuration is rendered view by view.
+// The matrices are copied before the call returns; the frames are complete when the stream reaches this point.
+int lrf_render_views_dev_async(lrf_ctx *h, uint32_t n_views, const float *view_inv_host, uint32_t *out_dev, uint32_t w, uint32_t hgt, int grey)
+{
+  NEED_GRID(h);
+  if (n_views == 0 || w == 0 || hgt == 0) return 0;
+  if (!view_inv_host || !out_dev) return fail("null view matrices / frame buffer");
+  const size_t frame = (size_t)w * hgt;
+  const bool one_launch = h->lean && h->dense && !grey && !h->staged && !h->baked && frame * n_views < (1ull << 32) &&
+                          (uint64_t)n_views * (((w + 15) / 16) * (uint64_t)((hgt + 3) / 4)) < (1ull << 31);
+  if (!one_launch) {
+    float keep[16];
+    std::memcpy(keep, h->view_inv, 64);
+    if (ensure_fb(h, frame)) return 1;
+    int rc = 0;
+    for (uint32_t v = 0; v < n_views && !rc; v++) {
+      std::memcpy(h->view_inv, view_inv_host + 16 * (size_t)v, 64);
+      rc = render_dispatch(h, out_dev + frame * v, w, hgt, grey, nullptr);
+    }
+    std::memcpy(h->view_inv, keep, 64);
+    if (rc) return 1;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  if (h->views_cap < n_views) {
+    cudaFree(h->views_dev);
+    h->views_dev = nullptr; h->views_cap = 0;
+    CK(cudaMalloc(&h->views_dev, (size_t)n_views * 64));
+    h->views_cap = n_views;
+  }
+  if (ensure_fb(h, frame * n_views)) return 1;
+  // pageable host memory: the copy is staged before cudaMemcpyAsync returns, so the caller may reuse the matrices right away
+  CK(cudaMemcpyAsync(h->views_dev, view_inv_host, (size_t)n_views * 64, cudaMemcpyHostToDevice, h->stream));
+  launch_render_views(scene_of(h), h->views_dev, n_views, out_dev, w, hgt, h->fb, h->fb + kFbHeader, h->stream);
+  h->launches += 2;   // render_lean_kernel (all views) + render_fallback_kernel
+  h->last_render_staged = 0;
+  CK(cudaGetLastError());
+  return 0;
+}
 // rows [y0, y1) of the frame into the full-frame buffer out_dev (latency mode: one frame split over several GPUs in row bands, the
 // way the reference splits the rows of a frame over its OpenMP threads, ref example_tracer.cpp:630); gather kernel
 int lrf_render_rows_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt, uint32_t y0, uint32_t y1, int grey)
@@ -1024,6 +1068,40 @@ int lrf_render_stats(lrf_ctx *h, uint32_t out[4], int reset)
 }
 // for callers that write the parameters through lrf_param_device_ptr / peer memory: derived copies (the render records) are stale now
 int lrf_params_touched(lrf_ctx *h) { NEED(h); params_changed(h); return 0; }
+// n_views frames into HOST memory (frame v at out_host + v * w * hgt), synchronous: the views are rendered in up to four batches and the
+// finished batch travels to the host on the second stream while the next one is rendered (pinned out_host: the copies overlap the
+// kernels; pageable: correct, not overlapped).
+int lrf_render_views(lrf_ctx *h, uint32_t n_views, const float *view_inv_host, uint32_t *out_host, uint32_t w, uint32_t hgt, int grey)
+{
+  NEED_GRID(h);
+  if (n_views == 0 || w == 0 || hgt == 0) return 0;
+  if (!view_inv_host || !out_host) return fail("null view matrices / frame buffer");
+  const size_t frame = (size_t)w * hgt;
+  if (ensure_stage(h, frame * n_views * 4)) return 1;
+  const uint32_t chunk = (n_views + 3) / 4;
+  cudaEvent_t done[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nchunk = 0, rc = 0;
+  cudaEventRecord(h->ev0, h->stream);
+  for (uint32_t v0 = 0; v0 < n_views && !rc; v0 += chunk, nchunk++) {
+    const uint32_t nv = std::min(chunk, n_views - v0);
+    uint32_t *dev = (uint32_t *)h->stage + frame * v0;
+    rc = lrf_render_views_dev_async(h, nv, view_inv_host + 16 * (size_t)v0, dev, w, hgt, grey);
+    if (rc) break;
+    if (cudaEventCreateWithFlags(&done[nchunk], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(done[nchunk], h->stream) != cudaSuccess ||
+        cudaStreamWaitEvent(h->side, done[nchunk], 0) != cudaSuccess ||
+        cudaMemcpyAsync(out_host + frame * v0, dev, frame * nv * 4, cudaMemcpyDeviceToHost, h->side) != cudaSuccess)
+      rc = fail(std::string("lrf_render_views: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventRecord(h->ev_join, h->side);
+  cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  const int rs = sync_with_diag(h);
+  for (cudaEvent_t e : done)
+    if (e) cudaEventDestroy(e);
+  if (rc || rs) return 1;
+  cudaEventElapsedTime(&h->t_march, h->ev0, h->ev1);
+  return 0;
+}
 int lrf_render(lrf_ctx *h, uint32_t *out_host, uint32_t w, uint32_t hgt, int grey)
 {
   NEED_GRID(h);

@@ -93,3 +93,47 @@ def test_lean_symmetric_camera_ties(pkg):
     assert ties > 0
     t.close()
     S.close()
+
+
+def _sym_view(eye_z, flip):
+    vi = np.zeros(16, np.float32)
+    vi[0] = 1.0; vi[5] = 1.0; vi[10] = -flip; vi[15] = 1.0
+    vi[12], vi[13], vi[14] = 0.5, 0.5, eye_z
+    return vi
+
+
+@pytest.mark.parametrize("mode", ["dense", "grey", "sparse"])
+def test_render_views_equals_view_by_view(pkg, mode):
+    """lrf_render_views_dev_async: the frames of one batch call are the frames kernel2D_RayMarch renders view by view, bit for bit —
+    one launch over all views for dense colour frames (the symmetric camera's centre row / column travel through the batch's fallback
+    list), the view-by-view route for greyscale and sparse sets; the context's own view matrix is left alone"""
+    gs, w, h = 32, 72, 40          # not a multiple of the 16 x 8 block: partial tiles in every view
+    grid = libs.lcg_grid(gs, 6.0)
+    t = pkg.RayMarcherExample()
+    t.InitGrid(gs)
+    t.SetBoundingBox([0, 0, 0], [1, 1, 1])
+    t.set_grid(grid)
+    if mode == "sparse":
+        t.RebuildOctree()
+    grey = mode == "grey"
+    views = [cameras(pkg, k, 7)[0] for k in (0, 3, 5)] + [_sym_view(-1.5, 1.0)] + [cameras(pkg, 6, 7)[0]]
+    _, pi = cameras(pkg, 0, 7)
+    t.set_proj_inv(pi)
+    t.set_view_inv(views[1])
+    frames = pkg.DeviceBuffer(t, len(views) * w * h * 4)
+    l0 = t.launch_count()
+    t.render_views_dev_async(views, frames.ptr, w, h, grey)
+    launches = t.launch_count() - l0
+    got = np.zeros(len(views) * w * h, np.uint32)
+    frames.download(got)
+    got = got.reshape(len(views), w * h)
+    assert launches == (2 if mode == "dense" else 2 * len(views))
+    one = np.zeros(w * h, np.uint32)
+    t.kernel2D_RayMarch(one, w, h, grey)            # the context's view is still views[1]
+    assert np.array_equal(one, got[1])
+    for k, vi in enumerate(views):
+        t.set_view_inv(vi)
+        t.kernel2D_RayMarch(one, w, h, grey)
+        assert np.array_equal(one, got[k]), "view %d differs on %d pixels" % (k, (one != got[k]).sum())
+        assert one.any()
+    t.close()
