@@ -75,6 +75,15 @@ def time_one(n_views):
         ck = (ck * 1000003 + int(host.astype(np.uint64).sum())) % (1 << 61)
     out = {"lib": os.path.basename(os.environ.get("LRF_B200_LIB", "default")), "ms_per_view": ms / len(pick), "Mrays_s": bench.W * bench.H * len(pick) / ms / 1e3,
            "checksum": ck}
+    if os.environ.get("LRF_VARIANTS_BATCH"):   # the bench's step: all views in one launch (lrf_render_views_dev_async)
+        frames = pkg.DeviceBuffer(t, len(views) * bench.W * bench.H * 4)
+        t.render_views_dev_async(views, frames.ptr, bench.W, bench.H)
+        t.sync()
+        t.timer_start()
+        for _ in range(2):
+            t.render_views_dev_async(views, frames.ptr, bench.W, bench.H)
+        out["batch_ms_per_view"] = t.timer_stop_ms() / (2 * len(views))
+        out["batch_Mrays_s"] = bench.W * bench.H / out["batch_ms_per_view"] / 1e3
     if os.environ.get("LRF_VARIANTS_TRAIN"):   # packed-batch backward: 4096 rays, CUDA events
         rng = np.random.default_rng(1)
         n = 4096
