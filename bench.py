@@ -551,17 +551,13 @@ def other_configs(pkg, t0, local, rank, world, max_over_ranks, barrier):
         proj_inv = pkg.inverse4x4(pkg.perspective(45.0, aspect, 0.1, 100.0))
         views = [pkg.inverse4x4(pkg.orbit_view(k, n_views * world)) for k in shard.shard_views(n_views * world, rank, world)]
         t.set_proj_inv(proj_inv)
-        fr = pkg.DeviceBuffer(t, w * h * 4)
-        for vi in views[:2]:
-            t.set_view_inv(vi)
-            t.render_dev_async(fr.ptr, w, h)
+        fr = pkg.DeviceBuffer(t, len(views) * w * h * 4)     # one frame per view: the batch call (one launch for dense sets, view by view for sparse ones)
+        t.render_views_dev_async(views[:2], fr.ptr, w, h)
         barrier()
         t.sync()
         t.timer_start()
         for _ in range(reps):
-            for vi in views:
-                t.set_view_inv(vi)
-                t.render_dev_async(fr.ptr, w, h)
+            t.render_views_dev_async(views, fr.ptr, w, h)
         ms = max_over_ranks(t.timer_stop_ms())
         barrier()
         fr.free()

@@ -84,7 +84,7 @@ int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t width, uint32_t
 /* n_views frames in one call (ref: the caller's loop over views, main.cpp:87-119 — SetWorldViewMatrix :104, then L1Loss :114, which
  * calls kernel2D_RayMarch, example_tracer.cpp:603-625 — once per view): frame v of out_dev (width*height pixels each, DEVICE memory) is rendered with the inverse view matrix
  * view_inv_host[16 v ..] (HOST memory, copied before the call returns); projection, grid and options are the context's and its own
- * view matrix is left unchanged.  Dense colour frames take one kernel launch for all views, other configurations one per view. */
+ * view matrix is left unchanged.  One kernel launch for all views (dense, sparse and greyscale alike; the opt-in staged kernel: one per view). */
 int lrf_render_views_dev_async(lrf_ctx *h, uint32_t n_views, const float *view_inv_host, uint32_t *out_dev, uint32_t width, uint32_t height,
                                int greyscale);
 /* same with the frames delivered to HOST memory (frame v at out_host + v*width*height), synchronous like kernel2D_RayMarch: complete on

@@ -959,8 +959,8 @@ int lrf_render_dev_async(lrf_ctx *h, uint32_t *out_dev, uint32_t w, uint32_t hgt
   return 0;
 }
 // n_views frames in one call: frame v (w * hgt pixels) of out_dev is the render with view matrix view_inv_host[16 v .. 16 v + 15] (the
-// projection matrix, grid and options are the context's; the context's own view matrix is left as it was).  Dense colour frames go to ONE
-// launch of the register-window march over all views (no idle SMs between views); every other configuration is rendered view by view.
+// projection matrix, grid and options are the context's; the context's own view matrix is left as it was).  ONE launch of the forward
+// kernel over all views (no idle SMs between views); only the opt-in staged kernel is run view by view.
 // The matrices are copied before the call returns; the frames are complete when the stream reaches this point.
 int lrf_render_views_dev_async(lrf_ctx *h, uint32_t n_views, const float *view_inv_host, uint32_t *out_dev, uint32_t w, uint32_t hgt, int grey)
 {
@@ -968,8 +968,8 @@ int lrf_render_views_dev_async(lrf_ctx *h, uint32_t n_views, const float *view_i
   if (n_views == 0 || w == 0 || hgt == 0) return 0;
   if (!view_inv_host || !out_dev) return fail("null view matrices / frame buffer");
   const size_t frame = (size_t)w * hgt;
-  const bool one_launch = h->lean && h->dense && !grey && !h->staged && !h->baked && frame * n_views < (1ull << 32) &&
-                          (uint64_t)n_views * (((w + 15) / 16) * (uint64_t)((hgt + 3) / 4)) < (1ull << 31);
+  // one launch: every configuration the gather kernels render (not the opt-in staged kernel, whose tensor maps are per view)
+  const bool one_launch = !(h->staged && !grey) && frame * n_views < (1ull << 32) && (uint64_t)n_views * (((w + 7) / 8) * (uint64_t)((hgt + 3) / 4)) < (1ull << 31);
   if (!one_launch) {
     float keep[16];
     std::memcpy(keep, h->view_inv, 64);
@@ -993,8 +993,14 @@ int lrf_render_views_dev_async(lrf_ctx *h, uint32_t n_views, const float *view_i
   if (ensure_fb(h, frame * n_views)) return 1;
   // pageable host memory: the copy is staged before cudaMemcpyAsync returns, so the caller may reuse the matrices right away
   CK(cudaMemcpyAsync(h->views_dev, view_inv_host, (size_t)n_views * 64, cudaMemcpyHostToDevice, h->stream));
-  launch_render_views(scene_of(h), h->views_dev, n_views, out_dev, w, hgt, h->fb, h->fb + kFbHeader, h->stream);
-  h->launches += 2;   // render_lean_kernel (all views) + render_fallback_kernel
+  SceneDev S = scene_of(h);
+  if (h->baked && h->dense && !grey) {   // as in render_dispatch
+    const int r = ensure_records(h);
+    if (r == 1) return 1;
+    if (r == 0) S.rec = h->rec;
+  }
+  launch_render_views(S, h->views_dev, n_views, out_dev, w, hgt, grey, h->fb, h->fb + kFbHeader, h->stream, h->lean);
+  h->launches += 2;   // render_lean_kernel / render_image_kernel (all views) + render_fallback_kernel
   h->last_render_staged = 0;
   CK(cudaGetLastError());
   return 0;

@@ -295,10 +295,10 @@ __device__ __forceinline__ void load_exp_table(uint64_t *tab)
 // a 128-bit warp load one quarter-warp at a time and spends one wavefront per distinct 128-byte line in it, so the
 // more compact the quarter's footprint on the grid, the fewer wavefronts a gather costs (ncu: 8.3 per LDG.128 with
 // 8x1 quarters; the pipe was 88 % busy).
-__device__ __forceinline__ bool tile_pixel(uint32_t w, uint32_t h, uint32_t &px, uint32_t &py)
+__device__ __forceinline__ bool tile_pixel(uint32_t w, uint32_t h, uint32_t &px, uint32_t &py, uint32_t bid = blockIdx.x)
 {
   const uint32_t tiles_x = (w + 7) / 8;
-  const uint32_t tile = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t tile = bid * (kBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const uint32_t q = lane >> 3, sub = lane & 7;
   px = (tile % tiles_x) * 8 + (q & 1) * 4 + (sub & 3);
   py = (tile / tiles_x) * 4 + (q >> 1) * 2 + (sub >> 2);
@@ -326,15 +326,15 @@ inline uint32_t tile_grid(uint32_t w, uint32_t h)
 template <bool SPARSE, bool GREY, bool BAKED = false>
 __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *etab, float *ysm, float4 *csm, uint32_t *__restrict__ out, uint32_t w,
                                              uint32_t h, uint32_t px, uint32_t py, bool valid, uint32_t *__restrict__ fb_count,
-                                             uint32_t *__restrict__ fb_list)
+                                             uint32_t *__restrict__ fb_list, const float *view_inv, uint32_t frame0)
 {
   float o[3], d[3];
-  gen_ray(S.view_inv, S.proj_inv, valid ? px : 0u, valid ? py : 0u, w, h, o, d);
+  gen_ray(view_inv, S.proj_inv, valid ? px : 0u, valid ? py : 0u, w, h, o, d);
   const bool fast = fast_path_ok(d);
   const uint32_t mask = __ballot_sync(0xffffffffu, valid && fast);
   if (!valid) return;
   if (!fast) {
-    fb_list[atomicAdd(fb_count, 1u)] = py * w + px;
+    fb_list[atomicAdd(fb_count, 1u)] = frame0 + py * w + px;
     return;
   }
   FastMarch<0, SPARSE, GREY, BAKED> fm(S, etab, ysm + threadIdx.x, csm + threadIdx.x);
@@ -342,23 +342,32 @@ __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *
   uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
   if (fm.n_hit)
     pix = pack_color(lm_clamp(fm.col[0], 0.0f, 1.0f), lm_clamp(fm.col[1], 0.0f, 1.0f), lm_clamp(fm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
-  out[(size_t)py * w + px] = pix;
+  out[(size_t)frame0 + (size_t)py * w + px] = pix;
 }
 
 // Rows [y0, y0 + hb) of the w x h frame (the whole frame: y0 = 0, hb = h).  Row bands are how one frame is split over several GPUs
 // (latency mode; the reference splits the rows of a frame over its OpenMP threads, ref example_tracer.cpp:630).
 template <bool SPARSE, bool GREY, bool BAKED = false>
 __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
-                                                                 uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb)
+                                                                 uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb,
+                                                                 const float *__restrict__ views = nullptr, uint32_t blocks_per_view = 0)
 {
   __shared__ uint64_t etab[32];
   __shared__ float ysm[9 * kFastBlock];
   __shared__ float4 csm[8 * kFastBlock];
   load_exp_table(etab);
-  uint32_t px, py;
-  const bool valid = tile_pixel(w, hb, px, py);
+  // views != nullptr: a batch of views in one launch (see render_lean_kernel<.., BATCH>): block b = block b % blocks_per_view of view b / blocks_per_view
+  uint32_t px, py, bid = blockIdx.x, frame0 = 0;
+  const float *view_inv = S.view_inv;
+  if (views) {
+    const uint32_t v = bid / blocks_per_view;
+    bid -= v * blocks_per_view;
+    view_inv = views + 16 * v;
+    frame0 = v * w * h;
+  }
+  const bool valid = tile_pixel(w, hb, px, py, bid);
   py += y0;
-  render_pixel<SPARSE, GREY, BAKED>(S, etab, ysm, csm, out, w, h, px, py, valid, fb_count, fb_list);
+  render_pixel<SPARSE, GREY, BAKED>(S, etab, ysm, csm, out, w, h, px, py, valid, fb_count, fb_list, view_inv, frame0);
 }
 
 // Dense colour frames: the register-window march of lrf_lean.cuh (same decisions as FastMarch, bit for bit; fewer instructions and
@@ -1636,15 +1645,27 @@ void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint3
   }
   render_fallback_kernel<<<148, kBlock, 0, st>>>(S, out_dev, w, h, grey, fb_count, fb_list);
 }
-// n views in one launch of the register-window march (dense colour frames only; the caller checked that): frames w * h apart in out_dev,
-// fb_list sized for n * w * h entries
-void launch_render_views(const SceneDev &S, const float *views_dev, uint32_t n_views, uint32_t *out_dev, uint32_t w, uint32_t h, uint32_t *fb_count,
-                         uint32_t *fb_list, cudaStream_t st)
+// n views in one launch of the forward kernel launch_render_image would pick: frames w * h apart in out_dev, fb_list sized for n * w * h entries
+void launch_render_views(const SceneDev &S, const float *views_dev, uint32_t n_views, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, uint32_t *fb_count,
+                         uint32_t *fb_list, cudaStream_t st, int lean)
 {
   cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
-  const uint32_t tiles = ((w + kLeanBW - 1) / kLeanBW) * ((h + kLeanBH - 1) / kLeanBH);
-  render_lean_kernel<false, true, true><<<tiles * n_views, LRF_LEAN_BLOCK, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, 0, h, nullptr, nullptr, views_dev, tiles);
-  render_fallback_kernel<<<148, kBlock, 0, st>>>(S, out_dev, w, h, 0, fb_count, fb_list, views_dev);
+  if (lean && !S.occ && !grey && !S.rec) {
+    const uint32_t tiles = ((w + kLeanBW - 1) / kLeanBW) * ((h + kLeanBH - 1) / kLeanBH);
+    render_lean_kernel<false, true, true><<<tiles * n_views, LRF_LEAN_BLOCK, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, 0, h, nullptr, nullptr, views_dev, tiles);
+  } else {
+    const uint32_t bpv = tile_grid(w, h);
+    const dim3 g(bpv * n_views);
+    if (S.occ) {
+      if (grey) render_image_kernel<true, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, 0, h, views_dev, bpv);
+      else render_image_kernel<true, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, 0, h, views_dev, bpv);
+    } else {
+      if (grey) render_image_kernel<false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, 0, h, views_dev, bpv);
+      else if (S.rec) render_image_kernel<false, false, true><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, 0, h, views_dev, bpv);
+      else render_image_kernel<false, false><<<g, kBlock, 0, st>>>(S, out_dev, w, h, fb_count, fb_list, 0, h, views_dev, bpv);
+    }
+  }
+  render_fallback_kernel<<<148, kBlock, 0, st>>>(S, out_dev, w, h, grey, fb_count, fb_list, views_dev);
 }
 void launch_bake_records(const SceneDev &S, float4 *rec, float *max_abs_density, cudaStream_t st)
 {

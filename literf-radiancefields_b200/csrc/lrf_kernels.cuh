@@ -42,8 +42,8 @@ int launch_render_staged(const SceneDev &S, const StagedArgs &T, int nw, uint32_
 // forward
 // fb_count (1 uint32) / fb_list (w*h uint32): fallback queue for rays that need the generic march; 2 kernel launches
 // rows [y0, y1) of the frame only (default: all of it)
-void launch_render_views(const SceneDev &S, const float *views_dev, uint32_t n_views, uint32_t *out_dev, uint32_t w, uint32_t h, uint32_t *fb_count,
-                         uint32_t *fb_list, cudaStream_t st);
+void launch_render_views(const SceneDev &S, const float *views_dev, uint32_t n_views, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, uint32_t *fb_count,
+                         uint32_t *fb_list, cudaStream_t st, int lean);
 void launch_render_image(const SceneDev &S, uint32_t *out_dev, uint32_t w, uint32_t h, int grey, uint32_t *fb_count, uint32_t *fb_list,
                          cudaStream_t st, uint32_t y0 = 0, uint32_t y1 = 0xffffffffu, int lean = 0, uint32_t *tap_n = nullptr, float *tap_thr = nullptr);
 // lean = 1: dense colour frames by the register-window march (lrf_lean.cuh); tap_n / tap_thr: its per-pixel shaded-sample counts and final

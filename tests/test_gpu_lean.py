@@ -102,11 +102,11 @@ def _sym_view(eye_z, flip):
     return vi
 
 
-@pytest.mark.parametrize("mode", ["dense", "grey", "sparse"])
+@pytest.mark.parametrize("mode", ["dense", "grey", "sparse", "staged"])
 def test_render_views_equals_view_by_view(pkg, mode):
     """lrf_render_views_dev_async: the frames of one batch call are the frames kernel2D_RayMarch renders view by view, bit for bit —
-    one launch over all views for dense colour frames (the symmetric camera's centre row / column travel through the batch's fallback
-    list), the view-by-view route for greyscale and sparse sets; the context's own view matrix is left alone"""
+    one launch over all views (the symmetric camera's centre row / column travel through the batch's fallback list), the register-window
+    kernel for dense colour frames, the gather kernel for greyscale and sparse sets; the context's own view matrix is left alone"""
     gs, w, h = 32, 72, 40          # not a multiple of the 16 x 8 block: partial tiles in every view
     grid = libs.lcg_grid(gs, 6.0)
     t = pkg.RayMarcherExample()
@@ -115,6 +115,8 @@ def test_render_views_equals_view_by_view(pkg, mode):
     t.set_grid(grid)
     if mode == "sparse":
         t.RebuildOctree()
+    if mode == "staged":
+        t.set_option("staged_render", 1)            # the opt-in TMA-staged kernel: the batch call runs it view by view
     grey = mode == "grey"
     views = [cameras(pkg, k, 7)[0] for k in (0, 3, 5)] + [_sym_view(-1.5, 1.0)] + [cameras(pkg, 6, 7)[0]]
     _, pi = cameras(pkg, 0, 7)
@@ -127,7 +129,10 @@ def test_render_views_equals_view_by_view(pkg, mode):
     got = np.zeros(len(views) * w * h, np.uint32)
     frames.download(got)
     got = got.reshape(len(views), w * h)
-    assert launches == (2 if mode == "dense" else 2 * len(views))
+    if mode == "staged":
+        assert launches == 2 * len(views) + 1       # two kernels per view + the record bake
+    else:
+        assert launches == 2                        # the forward kernel over all views + the fallback kernel
     one = np.zeros(w * h, np.uint32)
     t.kernel2D_RayMarch(one, w, h, grey)            # the context's view is still views[1]
     assert np.array_equal(one, got[1])
