@@ -382,7 +382,11 @@ __global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(c
 #ifndef LRF_LEAN_WARPS
 #define LRF_LEAN_WARPS (LRF_LEAN_MINB * 4)   // resident warps per SM the register allocation is sized for (12 -> 168 registers)
 #endif
-constexpr uint32_t kLeanBW = LRF_LEAN_BLOCK >= 64 ? 16 : 8, kLeanBH = LRF_LEAN_BLOCK >= 128 ? 8 : 4;
+#ifndef LRF_LEAN_SUPER
+#define LRF_LEAN_SUPER 0     // 1 = a block of LRF_LEAN_BLOCK threads owns a 32 x 32-pixel super-tile and its warps pull the 32 warp tiles of it from a shared
+                             // counter (neighbouring tiles stay on one SM: L1 sharing of the 16 x 8 blocks, with the balance of one-warp blocks)
+#endif
+constexpr uint32_t kLeanBW = LRF_LEAN_SUPER ? 32 : (LRF_LEAN_BLOCK >= 64 ? 16 : 8), kLeanBH = LRF_LEAN_SUPER ? 32 : (LRF_LEAN_BLOCK >= 128 ? 8 : 4);
 // BATCH: one launch renders n views (lrf_render_views_dev_async): block b works on tile b % tiles of view b / tiles, reads that view's
 // matrix from `views` (device, n x 16 floats) and writes frame b / tiles of `out` (frames w * h pixels apart).  Per-view launches leave
 // the SMs idle while the last blocks of a view finish (ncu: SMs active 95 % of the launch, 11.3 of 12 warps resident on average); in
@@ -394,6 +398,10 @@ __global__ void __launch_bounds__(LRF_LEAN_BLOCK, LRF_LEAN_WARPS * 32 / LRF_LEAN
                                                                             const float *__restrict__ views = nullptr, uint32_t tiles = 0)
 {
   __shared__ uint64_t etab[32];
+#if LRF_LEAN_SUPER
+  __shared__ uint32_t next_tile;
+  if (threadIdx.x == 0) next_tile = LRF_LEAN_BLOCK / 32;   // the first tiles are the warps' own
+#endif
   load_exp_table(etab);
   uint32_t px, py, bid = blockIdx.x, frame0 = 0;
   const float *view_inv = S.view_inv;
@@ -403,7 +411,39 @@ __global__ void __launch_bounds__(LRF_LEAN_BLOCK, LRF_LEAN_WARPS * 32 / LRF_LEAN
     view_inv = views + 16 * v;
     frame0 = v * w * h;                  // < 2^32: checked by the host
   }
-#if LRF_LEAN_TILE2D
+  auto render_one = [&](uint32_t px, uint32_t py) {
+    float o[3], d[3];
+    gen_ray(view_inv, S.proj_inv, px, py, w, h, o, d);
+    const size_t pixel = (size_t)frame0 + (size_t)py * w + px;
+    if (!fast_path_ok(d)) {
+      fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)pixel;
+      if (TAPS) { tap_n[pixel] = 0xffffffffu; tap_thr[pixel] = __int_as_float(0x7fc00000); }
+      return;
+    }
+    LeanMarch<TAPS, GATE> lm(S, etab);
+    lm.run(o, d);
+    uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
+    if (lm.any_hit())
+      pix = pack_color(lm_clamp(lm.col[0], 0.0f, 1.0f), lm_clamp(lm.col[1], 0.0f, 1.0f), lm_clamp(lm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
+    out[pixel] = pix;
+    if (TAPS) { tap_n[pixel] = lm.n_shaded; tap_thr[pixel] = lm.thr; }
+  };
+#if LRF_LEAN_SUPER
+  {
+    static_assert(LRF_LEAN_TILE2D, "super-tiles are a 2-D tiling");
+    const uint32_t bx_n = (w + 31) / 32, sx = bid % bx_n, sy = bid / bx_n, lane = threadIdx.x & 31, q = lane >> 3, sub = lane & 7;
+    for (uint32_t tidx = threadIdx.x >> 5; tidx < 32;) {
+      // tile order: 2 x 2 groups (16 x 8 pixels), groups row by row — the warps of a block work on neighbouring tiles
+      const uint32_t g = tidx >> 2, s4 = tidx & 3, tx = (g & 1) * 2 + (s4 & 1), ty = (g >> 1) * 2 + (s4 >> 1);
+      px = sx * 32 + tx * 8 + (q & 1) * 4 + (sub & 3);
+      py = sy * 32 + ty * 4 + (q >> 1) * 2 + (sub >> 2);
+      if (px < w && py < hb) render_one(px, py + y0);
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(&next_tile, 1u);
+      tidx = __shfl_sync(0xffffffffu, t, 0);
+    }
+  }
+#elif LRF_LEAN_TILE2D
   {
     // a block covers 16 x 8 pixels (2 x 2 warp tiles of 8 x 4) instead of a 32 x 4 strip: its four warps share more nodes in L1
     const uint32_t bx_n = (w + kLeanBW - 1) / kLeanBW;
@@ -412,27 +452,13 @@ __global__ void __launch_bounds__(LRF_LEAN_BLOCK, LRF_LEAN_WARPS * 32 / LRF_LEAN
     px = bx * kLeanBW + (wq & 1) * 8 + (q & 1) * 4 + (sub & 3);
     py = by * kLeanBH + (wq >> 1) * 4 + (q >> 1) * 2 + (sub >> 2);
     if (px >= w || py >= hb) return;
+    render_one(px, py + y0);
   }
 #else
   static_assert(!BATCH, "the batch launch needs the 2-D block tiling");
   if (!tile_pixel(w, hb, px, py)) return;
+  render_one(px, py + y0);
 #endif
-  py += y0;
-  float o[3], d[3];
-  gen_ray(view_inv, S.proj_inv, px, py, w, h, o, d);
-  const size_t pixel = (size_t)frame0 + (size_t)py * w + px;
-  if (!fast_path_ok(d)) {
-    fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)pixel;
-    if (TAPS) { tap_n[pixel] = 0xffffffffu; tap_thr[pixel] = __int_as_float(0x7fc00000); }
-    return;
-  }
-  LeanMarch<TAPS, GATE> lm(S, etab);
-  lm.run(o, d);
-  uint32_t pix = 0;  // ref :645,660: rays with an empty hit list pack float4(0)
-  if (lm.any_hit())
-    pix = pack_color(lm_clamp(lm.col[0], 0.0f, 1.0f), lm_clamp(lm.col[1], 0.0f, 1.0f), lm_clamp(lm.col[2], 0.0f, 1.0f), 1.0f);  // :193,:653
-  out[pixel] = pix;
-  if (TAPS) { tap_n[pixel] = lm.n_shaded; tap_thr[pixel] = lm.thr; }
 }
 
 // views != nullptr: the list holds frame * w * h + pixel of a batch of views (render_lean_kernel<.., BATCH>)

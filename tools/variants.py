@@ -104,6 +104,23 @@ def time_one(n_views):
             t._ck(t.lib.lrf_rays_grad_dev_async(t.h, n, od.ptr, dd.ptr, rf.ptr, 0))
         out["ms_backward_4096"] = t.timer_stop_ms() / 10
         out["grad_abs_sum"] = float(np.abs(t.get_grad().astype(np.float64)).sum())
+        if os.environ.get("LRF_VARIANTS_SORT"):   # experiment: longest rays first (chord through the unit cube x L1 norm of the direction ~ cells crossed)
+            o = np.zeros(n * 3, np.float32); d = np.zeros(n * 3, np.float32); r = np.zeros(n * 4, np.float32)
+            od.download(o); dd.download(d); rf.download(r)
+            o = o.reshape(n, 3); d = d.reshape(n, 3); r = r.reshape(n, 4)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t0 = (0.0 - o) / d; t1 = (1.0 - o) / d
+            tn = np.nanmax(np.minimum(t0, t1), axis=1); tx = np.nanmin(np.maximum(t0, t1), axis=1)
+            key = np.clip(tx - np.maximum(tn, 0.0), 0.0, None) * np.abs(d).sum(axis=1)
+            for name, order in (("desc", np.argsort(-key, kind="stable")), ("asc", np.argsort(key, kind="stable"))):
+                od.upload(np.ascontiguousarray(o[order])); dd.upload(np.ascontiguousarray(d[order])); rf.upload(np.ascontiguousarray(r[order]))
+                t.zeroGrad()
+                t._ck(t.lib.lrf_rays_grad_dev_async(t.h, n, od.ptr, dd.ptr, rf.ptr, 0))
+                t.sync()
+                t.timer_start()
+                for _ in range(10):
+                    t._ck(t.lib.lrf_rays_grad_dev_async(t.h, n, od.ptr, dd.ptr, rf.ptr, 0))
+                out["ms_backward_4096_sorted_" + name] = t.timer_stop_ms() / 10
     if os.environ.get("LRF_VARIANTS_IMGGRAD"):   # whole-image backward, 800x800
         t.zeroGrad()
         t.targets_resize(1, bench.W, bench.H)
