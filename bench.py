@@ -552,7 +552,7 @@ def other_configs(pkg, t0, local, rank, world, max_over_ranks, barrier):
         views = [pkg.inverse4x4(pkg.orbit_view(k, n_views * world)) for k in shard.shard_views(n_views * world, rank, world)]
         t.set_proj_inv(proj_inv)
         fr = pkg.DeviceBuffer(t, len(views) * w * h * 4)     # one frame per view: the batch call (one launch for dense sets, view by view for sparse ones)
-        t.render_views_dev_async(views[:2], fr.ptr, w, h)
+        t.render_views_dev_async(views, fr.ptr, w, h)          # warm-up with the timed call's own shape: its buffers are sized here, not inside the timed region
         barrier()
         t.sync()
         t.timer_start()
