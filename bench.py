@@ -390,6 +390,16 @@ def main():
     checksum = int(pinned.array[-W * H:].astype(np.uint64).sum())      # the last view's frame, as before the batch call existed
     e2e_value = rays_per_step * e2e_steps / e2e_s / 1e6
     # the batch frames are the frames the per-view call (kernel2D_RayMarch == lrf_render) delivers: checked on three views, outside the timed regions
+    # the same step view by view through the reference's own entry point (kernel2D_RayMarch == lrf_render: set the view, render, frame to
+    # pinned host memory, synchronous, once per view), timed once, for comparison with the batch call's e2e
+    one_pinned = pkg.PinnedBuffer(W * H, np.uint32)
+    barrier()
+    tv0 = time.perf_counter()
+    for vi in views:
+        t.set_view_inv(vi)
+        t.kernel2D_RayMarch(one_pinned.array, W, H)
+    t.sync()
+    e2e_per_view_value = rays_per_step / max_over_ranks(time.perf_counter() - tv0) / 1e6
     one = np.zeros(W * H, np.uint32)
     batch_ok = True
     for k in sorted({0, len(views) // 2, len(views) - 1}):
@@ -418,7 +428,8 @@ def main():
     if WORKLOAD != "render256":
         roofline["traffic"] = None     # the committed ncu capture is of the default workload
 
-    extra = {"e2e_checksum": checksum, "batch_frames_equal_per_view_frames": batch_ok}
+    extra = {"e2e_checksum": checksum, "batch_frames_equal_per_view_frames": batch_ok,
+             "e2e_view_by_view": {"value": e2e_per_view_value, "unit": "Mrays/s", "call": "kernel2D_RayMarch (lrf_render) once per view, pinned host frame", "steps": 1}}
     if SPARSE:
         extra["boxes"] = int(t.box_count())
         extra["occupancy"] = t.box_count() / float((GS - 1) ** 3)

@@ -110,6 +110,13 @@ void RayMarcherExample::kernel2D_RayMarch(uint32_t *out_color, uint32_t width, u
   if (lrf_last_time_ms(ctx, "RayMarch", t) == 0) rayMarchTime = t[0];
 }
 
+void RayMarcherExample::kernel2D_RayMarchViews(uint32_t *out_color, const float4x4 *a_viewMats, uint32_t n_views, uint32_t width, uint32_t height, bool greyscale)
+{
+  std::vector<float4x4> inv(n_views);
+  for (uint32_t v = 0; v < n_views; v++) inv[v] = inverse4x4(a_viewMats[v]);   // LiteMath's own inverse, as in SetWorldViewMatrix: bit-identical matrices
+  must(lrf_render_views(ctx, n_views, (const float *)inv.data(), out_color, width, height, greyscale ? 1 : 0), "kernel2D_RayMarchViews");
+}
+
 void RayMarcherExample::kernel2D_RayMarchGrad(uint32_t width, uint32_t height, float4 *res, bool greyscale)
 {
   must(lrf_render_grad(ctx, width, height, (const float *)res, greyscale ? 1 : 0), "kernel2D_RayMarchGrad");

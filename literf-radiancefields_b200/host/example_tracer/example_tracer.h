@@ -91,6 +91,9 @@ public:
   // device -> host mirrors (no reference counterpart)
   void syncToHost(bool with_grad = true, bool with_adam = true);
   // the raw model.dat dump / load that main.cpp keeps commented out (main.cpp:54-56,139-141): gridSize^3 x Cell, no header
+  // not in the reference: n_views frames in one call (frame v at out_color + v * width * height), view matrices as SetWorldViewMatrix takes them;
+  // one kernel launch for all views (lrf_render_views).  The current view matrix is left as it is.
+  void kernel2D_RayMarchViews(uint32_t *out_color, const float4x4 *a_viewMats, uint32_t n_views, uint32_t width, uint32_t height, bool greyscale = false);
   void SaveModelDat(const char *path);
   void LoadModelDat(const char *path);
 
