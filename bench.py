@@ -421,7 +421,7 @@ def main():
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(len(views))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "render_lean_kernel", "kernel_ms": kernel_ms, "views_per_launch": len(views), "kernel_ms_per_view": kernel_ms / len(views),
+                "kernel": "render_image_kernel<SPARSE>" if SPARSE else "render_lean_kernel", "kernel_ms": kernel_ms, "views_per_launch": len(views), "kernel_ms_per_view": kernel_ms / len(views),
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_view": alg_bytes_view,
                 "n_touched_nodes_mean": n_touched, "n_touched_sampled_views": len(sel), "peak_source": peak_src,
                 "traffic_source": traffic_src}
