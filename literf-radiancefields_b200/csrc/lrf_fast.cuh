@@ -73,7 +73,8 @@ constexpr int kFastBlock = 128;   // threads per block of the kernels that use F
 #define LRF_GRAD_MERGE 1     // image backward: lanes flushing the same node merge their adjoints before the reductions (0 = off; 1, 2, 4 = largest butterfly step)
 #endif
 #ifndef LRF_SEARCH_TRIPS
-#define LRF_SEARCH_TRIPS 4   // sparse render: traversal events per lane between two shading slots of the warp (see run())
+#define LRF_SEARCH_TRIPS 1   // sparse render: traversal events per lane between two shading slots of the warp (see run()).  4 was the optimum before the
+                             // brick-distance jump shortened the searches; with it (and 3 blocks per SM) 1 / 2 / 3 / 4 events: 463 / 425 / 417 / 409 Mrays/s
 #endif
 
 // BAKED: the render reads the 64-byte node records {density, R, G, B | sh0..sh3 | sh4..sh7 | sh8, 0, 0, 0} (S.rec, lrf_staged.cuh) instead of the

@@ -313,6 +313,10 @@ inline uint32_t tile_grid(uint32_t w, uint32_t h)
 #ifndef LRF_RENDER_MINB
 #define LRF_RENDER_MINB 4   // resident blocks per SM the register allocation is sized for (tools/variants.py)
 #endif
+#ifndef LRF_SPARSE_MINB
+#define LRF_SPARSE_MINB 3   // the same for the sparse instantiations: 168 registers, no spills — with one traversal event per trip (LRF_SEARCH_TRIPS = 1)
+                            // the 512^3 sphere scene renders at 463 Mrays/s in the batch launch against 393 at 4 blocks / 4 events (r2q, variants31.log)
+#endif
 
 // Forward render, one thread per pixel.  Rays that cannot take the fast path (a zero / non-finite reciprocal direction
 // component) are appended to a fallback list and rendered by render_fallback_kernel with the generic march.
@@ -348,7 +352,7 @@ __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *
 // Rows [y0, y0 + hb) of the w x h frame (the whole frame: y0 = 0, hb = h).  Row bands are how one frame is split over several GPUs
 // (latency mode; the reference splits the rows of a frame over its OpenMP threads, ref example_tracer.cpp:630).
 template <bool SPARSE, bool GREY, bool BAKED = false>
-__global__ void __launch_bounds__(kBlock, LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
+__global__ void __launch_bounds__(kBlock, SPARSE ? LRF_SPARSE_MINB : LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
                                                                  uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb,
                                                                  const float *__restrict__ views = nullptr, uint32_t blocks_per_view = 0)
 {
