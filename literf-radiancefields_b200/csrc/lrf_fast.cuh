@@ -58,7 +58,11 @@ __device__ __forceinline__ bool fast_path_ok(const float *d)
 // MODE 3: backward, pass B — the adjoint of every sample in forward order (closed form of the reverse sweep, see
 //         lrf_kernels.cu), accumulated per window slot in shared memory and flushed with red.global.add when the slot's node
 //         changes (gradient window: half the atomics of a per-sample scatter, 5 accumulators per node instead of 13)
-constexpr int kFastBlock = 128;   // threads per block of the kernels that use FastMarch (shared-memory stride)
+#ifndef LRF_KBLOCK
+#define LRF_KBLOCK 128            // threads per block of the thread-per-ray kernels.  Measured (r2r, variants33.log): sparse 512^3 render 463 / 451 / 432 Mrays/s
+                                  // at 128 / 64 / 32 threads (same warps per SM), whole-image backward 12.0 ms at all three
+#endif
+constexpr int kFastBlock = LRF_KBLOCK;   // threads per block of the kernels that use FastMarch (shared-memory stride)
 // Measured dead ends (profiles/r1f_variants.txt; the code is in the history of this file): taking the just-gathered nodes from
 // registers instead of re-reading the shared window, the SH basis in registers, a rolling one-node-at-a-time gather, 96 or 168
 // registers per thread, a branch-free single-basic-block iteration for dense grids (ptxas then schedules the gather

@@ -20,7 +20,7 @@ namespace lrf {
 
 namespace {
 
-constexpr int kBlock = 128;
+constexpr int kBlock = LRF_KBLOCK;
 static_assert(kBlock == kFastBlock, "FastMarch's shared-memory stride assumes the forward kernels' block size");
 
 struct RayCtx
@@ -352,7 +352,7 @@ __device__ __forceinline__ void render_pixel(const SceneDev &S, const uint64_t *
 // Rows [y0, y0 + hb) of the w x h frame (the whole frame: y0 = 0, hb = h).  Row bands are how one frame is split over several GPUs
 // (latency mode; the reference splits the rows of a frame over its OpenMP threads, ref example_tracer.cpp:630).
 template <bool SPARSE, bool GREY, bool BAKED = false>
-__global__ void __launch_bounds__(kBlock, SPARSE ? LRF_SPARSE_MINB : LRF_RENDER_MINB) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
+__global__ void __launch_bounds__(kBlock, (SPARSE ? LRF_SPARSE_MINB : LRF_RENDER_MINB) * 128 / kBlock) render_image_kernel(const __grid_constant__ SceneDev S, uint32_t *__restrict__ out, uint32_t w, uint32_t h,
                                                                  uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list, uint32_t y0, uint32_t hb,
                                                                  const float *__restrict__ views = nullptr, uint32_t blocks_per_view = 0)
 {
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(kBlock) grad_kernel(const __grid_constant__ Sc
 // in shared memory and flushed with red.global.add when the slot's node changes.  Rays the streamlined march cannot take go
 // to a queue that grad_kernel<true> (generic march) works off afterwards.
 template <bool SPARSE, bool GREY>
-__global__ void __launch_bounds__(kBlock, 3) grad_image_fast_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h,
+__global__ void __launch_bounds__(kBlock, 3 * 128 / kBlock) grad_image_fast_kernel(const __grid_constant__ SceneDev S, uint32_t w, uint32_t h,
                                                                     const float *__restrict__ ref_rgba, uint32_t *__restrict__ fb_count,
                                                                     uint32_t *__restrict__ fb_list)
 {
