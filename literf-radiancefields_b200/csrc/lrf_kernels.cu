@@ -295,19 +295,34 @@ __device__ __forceinline__ void load_exp_table(uint64_t *tab)
 // a 128-bit warp load one quarter-warp at a time and spends one wavefront per distinct 128-byte line in it, so the
 // more compact the quarter's footprint on the grid, the fewer wavefronts a gather costs (ncu: 8.3 per LDG.128 with
 // 8x1 quarters; the pipe was 88 % busy).
+#ifndef LRF_TILE2D
+#define LRF_TILE2D 1   // 1 = a 128-thread block covers 16 x 8 pixels (2 x 2 warp tiles) instead of a 32 x 4 strip: its warps share more nodes in L1
+                       // (sparse 512^3 render 460 -> 476 Mrays/s, whole-image backward 12.07 -> 11.99 ms; r2r variants34.log)
+#endif
 __device__ __forceinline__ bool tile_pixel(uint32_t w, uint32_t h, uint32_t &px, uint32_t &py, uint32_t bid = blockIdx.x)
 {
+  const uint32_t lane = threadIdx.x & 31, q = lane >> 3, sub = lane & 7;
+#if LRF_TILE2D
+  static_assert(kBlock == 128, "2 x 2 warp tiles per block");
+  const uint32_t bx_n = (w + 15) / 16, wq = threadIdx.x >> 5;
+  px = (bid % bx_n) * 16 + (wq & 1) * 8 + (q & 1) * 4 + (sub & 3);
+  py = (bid / bx_n) * 8 + (wq >> 1) * 4 + (q >> 1) * 2 + (sub >> 2);
+#else
   const uint32_t tiles_x = (w + 7) / 8;
-  const uint32_t tile = bid * (kBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const uint32_t q = lane >> 3, sub = lane & 7;
+  const uint32_t tile = bid * (kBlock / 32) + (threadIdx.x >> 5);
   px = (tile % tiles_x) * 8 + (q & 1) * 4 + (sub & 3);
   py = (tile / tiles_x) * 4 + (q >> 1) * 2 + (sub >> 2);
+#endif
   return px < w && py < h;
 }
 inline uint32_t tile_grid(uint32_t w, uint32_t h)
 {
+#if LRF_TILE2D
+  return ((w + 15) / 16) * ((h + 7) / 8);
+#else
   const uint32_t tiles = ((w + 7) / 8) * ((h + 3) / 4);
   return (tiles + (kBlock / 32) - 1) / (kBlock / 32);
+#endif
 }
 
 #ifndef LRF_RENDER_MINB
